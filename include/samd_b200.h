@@ -1,0 +1,207 @@
+/*
+ * samd_b200.h - C ABI of the B200-native SAM-Decoding hot path (libsamd_b200.so).
+ *
+ * The reference (hyx1999/SAM-Decoding) is pure Python and has no FFI of its own; the
+ * boundary it exposes for this path is the Python class surface of samd/ and
+ * samd_sam_only/ (SURVEY.md section 8b).  Every entry point below names the reference
+ * method(s) it replaces (file:line relative to the reference checkout).  The Python
+ * drop-in packages under sam-decoding_b200/{samd,samd_sam_only} bind these symbols with
+ * ctypes (sam-decoding_b200/samd_b200/_cabi.py); INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - pointers named *_dev are device pointers, *_host are host pointers
+ *   - every function returns 0 on success, non-zero on error (samd_last_error() explains)
+ *   - no call synchronises the stream unless its comment says so
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ */
+#ifndef SAMD_B200_H
+#define SAMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAMD_ABI_VERSION 1
+
+/* draft flavours (which reference package's rules apply) */
+#define SAMD_FLAVOUR_SAMD      0   /* samd/draft.py:52-63, fixed n_predicts, zero padding      */
+#define SAMD_FLAVOUR_SAM_ONLY  1   /* samd_sam_only/draft.py:49-59, n = min(max,1+int(m*alpha)) */
+
+/* draft source written to out_type */
+#define SAMD_DRAFT_DYN_SEQ     0   /* sequence read from the request's own history             */
+#define SAMD_DRAFT_STATIC_SEQ  1   /* sequence read from the static corpus                     */
+#define SAMD_DRAFT_TREE_MODEL  2   /* samd: match below len_threshold -> tree-model fallback   */
+#define SAMD_DRAFT_STATIC_TREE 3   /* sam_only: static SAM wins -> samd_static_tree_draft      */
+
+/* logits dtypes */
+#define SAMD_DTYPE_BF16 0
+#define SAMD_DTYPE_FP16 1
+
+typedef struct samd_dyn_s    *samd_dyn_t;     /* batch of per-request dynamic automata        */
+typedef struct samd_static_s *samd_static_t;  /* read-only static automaton over a corpus     */
+typedef struct samd_verify_s *samd_verify_t;  /* scratch of the verify+compact kernel         */
+
+int         samd_abi_version(void);
+const char *samd_last_error(void);            /* thread-local message of the last failure     */
+int         samd_device_count(void);          /* 0 without a usable CUDA device               */
+
+/* ----------------------------------------------------------------------------------------
+ * Dynamic suffix automaton, one per request           (samd/sam/dyn_sam.py:8-113,
+ *                                                       samd_sam_only/sam/dyn_sam.py:11-121)
+ * Per-request arenas in HBM: state records {link,len,min_endpos,edge_head} (16 B), a
+ * bucketed open-addressing transition table keyed (state, token) (16 B slots, 128 B
+ * buckets), the token history (1-based, text[0] = -1) and a small meta block.
+ * -------------------------------------------------------------------------------------- */
+/* DynSAM.__init__ for n_requests independent requests; max_tokens bounds prompt + decoded. */
+int samd_dyn_create(int n_requests, int max_tokens, samd_dyn_t *out);
+int samd_dyn_destroy(samd_dyn_t h);
+/* DynSAM.reset (dyn_sam.py:27-34) for requests with mask_dev[r] != 0 (NULL = all). */
+int samd_dyn_reset(samd_dyn_t h, const uint8_t *mask_dev, void *stream);
+/* device bytes held by the arenas */
+int64_t samd_dyn_bytes(samd_dyn_t h);
+/* Copy one request's automaton to the host (synchronises): meta[8] = {n_states, last,
+ * max_length, cur_index, cur_length, n_edges, overflow, n_clones}; link/length/min_endpos
+ * arrays of n_states entries (pass NULL to skip) and the token history text[0..max_length]. */
+int samd_dyn_export(samd_dyn_t h, int request, int32_t *meta_host, int32_t *link_host, int32_t *length_host,
+                    int32_t *endpos_host, int32_t *text_host, int64_t capacity);
+
+/* ----------------------------------------------------------------------------------------
+ * Static suffix automaton over a corpus                (samd/sam/static_sam.py:8-137,
+ *                                                       samd_sam_only/sam/static_sam.py:22-215)
+ * -------------------------------------------------------------------------------------- */
+/* StaticSAM.build (static_sam.py:38-46; build_sam, samd/sam/utils.py:10-18): host-side online
+ * construction over doc_1 EOS doc_2 EOS ... (EOS appended unless the doc ends with it), flat
+ * upload to the current device.  with_counts != 0 also computes cnt_endpos and the stable
+ * top-8 successor table (samd_sam_only/sam/static_sam.py:94-96,137-146).  Synchronises. */
+int samd_static_build(const int32_t *docs_flat_host, const int64_t *doc_offsets_host, int64_t n_docs, int32_t eos,
+                      int with_counts, samd_static_t *out);
+/* The two halves of samd_static_build: host construction only (no CUDA device needed; lets the
+ * builder be checked on a CPU-only machine and its result saved), and the upload. */
+int samd_static_build_host(const int32_t *docs_flat_host, const int64_t *doc_offsets_host, int64_t n_docs, int32_t eos,
+                           int with_counts, samd_static_t *out);
+int samd_static_upload(samd_static_t h);
+int samd_static_destroy(samd_static_t h);
+/* info[8] = {n_states, n_edges, n_tokens, n_slots, device_bytes, with_counts, n_clones, 0} */
+int samd_static_info(samd_static_t h, int64_t *info_host);
+/* Host copies for parity tests: link/length/min_endpos/cnt_endpos [n_states], topk [n_states*8*2]
+ * as (token,target) pairs, -1 padded.  NULL skips an array. */
+int samd_static_export(samd_static_t h, int32_t *link_host, int32_t *length_host, int32_t *endpos_host,
+                       int32_t *count_host, int32_t *topk_host);
+/* dump_sam / load_sam (samd/sam/utils.py:20-37) in a flat, mmap-able format. */
+int samd_static_save(samd_static_t h, const char *path);
+int samd_static_load(const char *path, samd_static_t *out);
+int samd_static_load_host(const char *path, samd_static_t *out);   /* no upload */
+/* Pin the hottest prefix of the automaton (state records first, then the transition
+ * table) in L2 through an access-policy window on `stream`; bytes <= 0 removes it. */
+int samd_static_set_l2_window(samd_static_t h, void *stream, int64_t bytes);
+
+/* ----------------------------------------------------------------------------------------
+ * The per-step draft kernel: DraftModel.update + DraftModel.lookup, batched
+ *   (samd/draft.py:52-79, samd_sam_only/draft.py:49-67; DynSAM.add_tokens dyn_sam.py:84-88,
+ *    StaticSAM.transfer_tokens static_sam.py:102-104, lookup :106-109, gen_draft :107-125)
+ * One warp per request.  Phase 1 (tokens_dev != NULL): append counts[r] tokens to request
+ * r's dynamic automaton (match-then-append, clone-on-split) and advance its static cursor.
+ * Phase 2 (start_tok_dev != NULL): peek both automata with the candidate next token, select
+ * the draft source by match length and write the draft tokens.
+ * -------------------------------------------------------------------------------------- */
+typedef struct samd_step_args {
+    samd_dyn_t     dyn;              /* required */
+    samd_static_t  stat;             /* NULL = NullStaticSAM (samd/sam/static_sam.py:128-137) */
+    int32_t       *static_cursor_dev;/* [n_requests][2] (index, length), in/out; NULL iff stat NULL */
+    const int32_t *tokens_dev;       /* [n_requests][token_stride] accepted tokens, or NULL */
+    int32_t        token_stride;
+    const int32_t *counts_dev;       /* [n_requests] tokens to append this step (0 allowed) */
+    const int32_t *start_tok_dev;    /* [n_requests] candidate next token, or NULL (no lookup) */
+    int32_t        flavour;          /* SAMD_FLAVOUR_* */
+    int32_t        n_predicts;       /* samd: n_predicts; sam_only: max_predicts */
+    int32_t        len_bias;
+    int32_t        len_threshold;    /* samd only */
+    double         alpha;            /* sam_only only */
+    /* outputs, each [n_requests] unless noted; any may be NULL */
+    int32_t *out_type_dev;           /* SAMD_DRAFT_* */
+    int32_t *out_match_dyn_dev;
+    int32_t *out_match_static_dev;   /* unbiased */
+    int32_t *out_index_dyn_dev;
+    int32_t *out_index_static_dev;
+    int32_t *out_draft_dev;          /* [n_requests][draft_stride] */
+    int32_t  draft_stride;
+    int32_t *out_draft_len_dev;
+} samd_step_args;
+
+int samd_step(const samd_step_args *args, void *stream);
+
+/* sam_only static tree drafter (samd_sam_only/sam/static_sam.py:148-215): best-first search
+ * over occurrence-count ratios with CPython-heapq tie order, for the requests whose
+ * type_dev[r] == SAMD_DRAFT_STATIC_TREE (type_dev NULL = all).  Writes per request the tree
+ * tokens and parent indices [max_nodes], the node count, the per-node depth
+ * (= tree_position_ids), and the padded retrieve table [max_paths][max_depth] (-1 padded,
+ * leaves ascending) with its shape.  match_static_dev is the UNBIASED match length. */
+int samd_static_tree_draft(samd_static_t h, int n_requests, const int32_t *type_dev, const int32_t *index_static_dev,
+                           const int32_t *match_static_dev, const int32_t *start_tok_dev, int32_t max_predicts,
+                           double alpha, int32_t K, int32_t len_bias, int32_t *out_tokens_dev,
+                           int32_t *out_parents_dev, int32_t *out_depth_dev, int32_t *out_n_nodes_dev,
+                           int32_t *out_retrieve_dev, int32_t max_paths, int32_t max_depth,
+                           int32_t *out_retrieve_shape_dev, void *stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Document-sharded static SAM: per-shard packed keys
+ *   key = (match_len << 32) | (0xFFFFFFFF - (shard_offset + min_endpos)), 0 when no match,
+ * to be max-reduced across shards (ncclMax on 64-bit), then the draft is read from the
+ * replicated corpus token array at the winning global position.
+ * -------------------------------------------------------------------------------------- */
+int samd_static_lookup_keys(samd_static_t h, const int32_t *static_cursor_dev, const int32_t *start_tok_dev,
+                            int n_requests, int64_t shard_offset, int64_t *out_keys_dev, void *stream);
+int samd_draft_from_keys(const int64_t *keys_dev, const int32_t *corpus_dev, int64_t n_corpus_tokens,
+                         const int32_t *start_tok_dev, int n_requests, int32_t n_predicts, int32_t *out_match_dev,
+                         int32_t *out_draft_dev, int32_t draft_stride, void *stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Fused greedy verification + KV-cache compaction
+ *   (gather samd/samd_model.py:159-168, eval_posterior greedy samd/utils.py:127-141,
+ *    update_state samd/samd_model.py:185-211, SamdStaticCache.select_indices samd/cache.py:118-133)
+ * One persistent launch: streams logits [B,T,V] once (row argmax with torch.argmax's
+ * lowest-index / NaN-is-max rule), walks the P x D path table per request, writes best /
+ * accept_len (= accepted + 1) / next_token / accepted tokens + indices, then moves KV rows
+ * cache_len+indices[j] -> cache_len+j in every K and V tensor and bumps cache_len.
+ * -------------------------------------------------------------------------------------- */
+int samd_verify_create(int max_batch, int max_nodes, samd_verify_t *out);
+int samd_verify_destroy(samd_verify_t h);
+
+typedef struct samd_verify_args {
+    const void    *logits_dev;        /* [B][T][V], dtype below */
+    int32_t        dtype;             /* SAMD_DTYPE_* */
+    int32_t        batch, n_nodes, vocab;
+    int64_t        batch_stride, row_stride;       /* in elements */
+    const int32_t *tree_tokens_dev;   /* [B][n_nodes] draft tokens fed to the LM */
+    const int32_t *n_nodes_dev;       /* [B] live rows per request, or NULL (= n_nodes) */
+    const int32_t *retrieve_dev;      /* [P][D] shared, or [B][P][D] when retrieve_batch_stride != 0;
+                                         NULL = one identity path of n_nodes entries (sequence) */
+    int32_t        n_paths, depth;
+    int64_t        retrieve_batch_stride;          /* elements; 0 = shared */
+    const int32_t *n_paths_dev;       /* [B] live paths per request, or NULL */
+    /* KV cache: n_kv tensors [B][H][max_len][Dh]; NULL kv_ptrs_dev or move_kv == 0 = no row moves */
+    void *const   *kv_ptrs_dev;       /* device array of n_kv base pointers */
+    int32_t        n_kv, n_heads, row_bytes;       /* row_bytes = Dh * sizeof(element) */
+    int64_t        kv_batch_stride, kv_head_stride, kv_pos_stride;   /* bytes */
+    int32_t        move_kv;
+    int32_t       *cache_len_dev;     /* [B] in/out, or NULL */
+    /* outputs */
+    int32_t *out_best_dev, *out_accept_len_dev, *out_next_token_dev;   /* [B] */
+    int32_t *out_tokens_dev, *out_indices_dev;      /* [B][depth] (sequence: [B][n_nodes]) */
+    int32_t *out_node_argmax_dev;     /* [B][n_nodes] or NULL */
+} samd_verify_args;
+
+int samd_verify_compact(samd_verify_t h, const samd_verify_args *args, void *stream);
+/* tuning hook: logits elements per phase-1 work item (0 = default) */
+void samd_verify_set_chunk(int elements);
+/* number of kernel launches the library has issued (for bench.py's gpu_launches) */
+int64_t samd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAMD_B200_H */

@@ -1,0 +1,515 @@
+// Static suffix automaton: host-side online builder into the flat device layout, upload,
+// persistence, L2 window, and the sam_only best-first tree drafter.
+#include "samd_common.cuh"
+#include "../../include/samd_b200.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------
+// host builder (StaticSAM.build, samd/sam/static_sam.py:32-79; counts/top-k of
+// samd_sam_only/sam/static_sam.py:94-96,137-146)
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct HostSam {
+    int4 *states = nullptr;
+    uint4 *slots = nullptr;
+    int32_t *text = nullptr;
+    uint64_t s_cap = 0, h_cap = 0;
+    uint32_t bmask = 0;
+    int64_t n_states = 1, n = 0, n_edges = 0, n_clones = 0;
+    int last = 0;
+    std::vector<uint8_t> is_clone;
+
+    bool probe(uint32_t state, uint32_t tok, uint32_t &slot) const {
+        uint32_t b = samd_hash(state, tok) & bmask;
+        for (;;) {
+            const uint4 *bk = slots + (size_t)b * SAMD_BUCKET;
+            for (int l = 0; l < SAMD_BUCKET; ++l) {
+                if (bk[l].x == state && bk[l].y == tok) {
+                    slot = b * SAMD_BUCKET + l;
+                    return true;
+                }
+                if (bk[l].x == SAMD_EMPTY) {
+                    slot = b * SAMD_BUCKET + l;
+                    return false;
+                }
+            }
+            b = (b + 1) & bmask;
+        }
+    }
+    void add_edge(int state, int tok, int target) {
+        uint32_t slot;
+        probe((uint32_t)state, (uint32_t)tok, slot);
+        slots[slot] = make_uint4((uint32_t)state, (uint32_t)tok, (uint32_t)target, (uint32_t)states[state].w);
+        states[state].w = (int)slot;
+        n_edges++;
+    }
+    void append(int tok) {
+        n += 1;
+        const int cur = (int)n_states++;
+        states[cur] = make_int4(-1, (int)n, (int)n, (int)SAMD_NIL);
+        is_clone.push_back(0);
+        text[n] = tok;
+        int p = last;
+        uint32_t slot = 0;
+        while (p != -1 && !probe((uint32_t)p, (uint32_t)tok, slot)) {
+            slots[slot] = make_uint4((uint32_t)p, (uint32_t)tok, (uint32_t)cur, (uint32_t)states[p].w);
+            states[p].w = (int)slot;
+            n_edges++;
+            p = states[p].x;
+        }
+        if (p == -1) {
+            states[cur].x = 0;
+        } else {
+            const int q = (int)slots[slot].z;
+            if (states[p].y + 1 == states[q].y) {
+                states[cur].x = q;
+            } else {
+                const int clone = (int)n_states++;
+                n_clones++;
+                is_clone.push_back(1);
+                states[clone] = make_int4(states[q].x, states[p].y + 1, states[q].z, (int)SAMD_NIL);
+                // copy q's edges oldest-first so that the clone keeps q's insertion order
+                uint32_t chain[64];
+                std::vector<uint32_t> big;
+                int cnt = 0;
+                for (uint32_t e = (uint32_t)states[q].w; e != SAMD_NIL; e = slots[e].w) {
+                    if (cnt < 64) chain[cnt] = e;
+                    else big.push_back(e);
+                    cnt++;
+                }
+                for (int i = (int)big.size() - 1; i >= 0; --i) add_edge(clone, (int)slots[big[i]].y, (int)slots[big[i]].z);
+                for (int i = std::min(cnt, 64) - 1; i >= 0; --i) add_edge(clone, (int)slots[chain[i]].y, (int)slots[chain[i]].z);
+                while (p != -1 && probe((uint32_t)p, (uint32_t)tok, slot) && (int)slots[slot].z == q) {
+                    slots[slot].z = (uint32_t)clone;
+                    p = states[p].x;
+                }
+                states[q].x = clone;
+                states[cur].x = clone;
+            }
+        }
+        last = cur;
+    }
+};
+
+void free_handle(samd_static_s *h) {
+    if (!h) return;
+    cudaFree((void *)h->dev.states);
+    cudaFree((void *)h->dev.slots);
+    cudaFree((void *)h->dev.text);
+    cudaFree((void *)h->dev.occ);
+    cudaFree((void *)h->dev.topk);
+    free(h->h_states);
+    free(h->h_slots);
+    free(h->h_text);
+    free(h->h_occ);
+    free(h->h_topk);
+    delete h;
+}
+
+int upload(samd_static_s *h) {
+    StaticDev &d = h->dev;
+    SAMD_CUDA(cudaGetDevice(&h->device));
+    void *p = nullptr;
+    SAMD_CUDA(cudaMalloc(&p, (size_t)d.n_states * sizeof(int4)));
+    d.states = (const int4 *)p;
+    SAMD_CUDA(cudaMemcpy(p, h->h_states, (size_t)d.n_states * sizeof(int4), cudaMemcpyHostToDevice));
+    SAMD_CUDA(cudaMalloc(&p, (size_t)d.n_slots * sizeof(uint4)));
+    d.slots = (const uint4 *)p;
+    SAMD_CUDA(cudaMemcpy(p, h->h_slots, (size_t)d.n_slots * sizeof(uint4), cudaMemcpyHostToDevice));
+    SAMD_CUDA(cudaMalloc(&p, (size_t)(d.n_tokens + 1) * sizeof(int32_t)));
+    d.text = (const int32_t *)p;
+    SAMD_CUDA(cudaMemcpy(p, h->h_text, (size_t)(d.n_tokens + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (h->with_counts) {
+        SAMD_CUDA(cudaMalloc(&p, (size_t)d.n_states * sizeof(int32_t)));
+        d.occ = (const int32_t *)p;
+        SAMD_CUDA(cudaMemcpy(p, h->h_occ, (size_t)d.n_states * sizeof(int32_t), cudaMemcpyHostToDevice));
+        SAMD_CUDA(cudaMalloc(&p, (size_t)d.n_states * 8 * sizeof(int2)));
+        d.topk = (const int2 *)p;
+        SAMD_CUDA(cudaMemcpy(p, h->h_topk, (size_t)d.n_states * 8 * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int samd_static_build_host(const int32_t *docs, const int64_t *offs, int64_t n_docs, int32_t eos, int with_counts,
+                                      samd_static_t *out) {
+    SAMD_REQUIRE(docs && offs && n_docs > 0 && out, "samd_static_build: bad arguments");
+    int64_t total = 0;
+    for (int64_t d = 0; d < n_docs; ++d) {
+        const int64_t len = offs[d + 1] - offs[d];
+        SAMD_REQUIRE(len > 0, "samd_static_build: empty document");
+        total += len + (docs[offs[d + 1] - 1] != eos ? 1 : 0);
+    }
+    SAMD_REQUIRE(total < (int64_t)1 << 30, "samd_static_build: corpus too large for one shard (>= 2^30 tokens)");
+    HostSam b;
+    b.s_cap = 2 * (uint64_t)total + 2;
+    b.h_cap = samd_table_slots((uint64_t)total);
+    b.bmask = (uint32_t)(b.h_cap / SAMD_BUCKET - 1);
+    b.states = (int4 *)malloc(b.s_cap * sizeof(int4));
+    b.slots = (uint4 *)malloc(b.h_cap * sizeof(uint4));
+    b.text = (int32_t *)malloc((size_t)(total + 1) * sizeof(int32_t));
+    SAMD_REQUIRE(b.states && b.slots && b.text, "samd_static_build: host allocation failed");
+    memset(b.slots, 0xFF, b.h_cap * sizeof(uint4));
+    b.states[0] = make_int4(-1, 0, 0, (int)SAMD_NIL);
+    b.text[0] = -1;
+    b.is_clone.reserve(b.s_cap);
+    b.is_clone.push_back(0);
+    for (int64_t d = 0; d < n_docs; ++d) {
+        for (int64_t i = offs[d]; i < offs[d + 1]; ++i) b.append(docs[i]);
+        if (docs[offs[d + 1] - 1] != eos) b.append(eos);
+    }
+    samd_static_s *h = new samd_static_s();
+    memset(h, 0, sizeof(*h));
+    h->h_states = (int4 *)realloc(b.states, (size_t)b.n_states * sizeof(int4));
+    h->h_slots = b.slots;
+    h->h_text = b.text;
+    h->n_edges = b.n_edges;
+    h->n_clones = b.n_clones;
+    h->with_counts = with_counts != 0;
+    h->dev.n_states = b.n_states;
+    h->dev.n_slots = (int64_t)b.h_cap;
+    h->dev.n_tokens = b.n;
+    h->dev.bmask = b.bmask;
+    if (with_counts) {
+        const int64_t ns = b.n_states;
+        h->h_occ = (int32_t *)calloc((size_t)ns, sizeof(int32_t));
+        // |endpos| by accumulation up the link tree in decreasing-length order (counting sort)
+        std::vector<int32_t> order((size_t)ns), bucket((size_t)b.n + 2, 0);
+        for (int64_t v = 0; v < ns; ++v) bucket[(size_t)h->h_states[v].y + 1]++;
+        for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
+        for (int64_t v = 0; v < ns; ++v) order[(size_t)bucket[(size_t)h->h_states[v].y]++] = (int32_t)v;
+        for (int64_t v = 1; v < ns; ++v) h->h_occ[v] = b.is_clone[(size_t)v] ? 0 : 1;
+        for (int64_t i = ns - 1; i > 0; --i) {
+            const int v = order[(size_t)i];
+            const int l = h->h_states[v].x;
+            if (l > 0) h->h_occ[l] += h->h_occ[v];
+        }
+        h->h_topk = (int2 *)malloc((size_t)ns * 8 * sizeof(int2));
+        std::vector<int2> edges;
+        for (int64_t v = 0; v < ns; ++v) {
+            edges.clear();
+            for (uint32_t e = (uint32_t)h->h_states[v].w; e != SAMD_NIL; e = h->h_slots[e].w)
+                edges.push_back(make_int2((int)h->h_slots[e].y, (int)h->h_slots[e].z));
+            std::reverse(edges.begin(), edges.end());                 // oldest first = dict insertion order
+            std::stable_sort(edges.begin(), edges.end(),
+                             [&](const int2 &x, const int2 &y) { return h->h_occ[x.y] > h->h_occ[y.y]; });
+            for (int j = 0; j < 8; ++j)
+                h->h_topk[(size_t)v * 8 + j] = j < (int)edges.size() ? edges[(size_t)j] : make_int2(-1, -1);
+        }
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int samd_static_upload(samd_static_t h) {
+    SAMD_REQUIRE(h && h->h_states, "samd_static_upload: no host automaton");
+    SAMD_REQUIRE(!h->dev.states, "samd_static_upload: already on the device");
+    return upload(h);
+}
+
+extern "C" int samd_static_build(const int32_t *docs, const int64_t *offs, int64_t n_docs, int32_t eos, int with_counts,
+                                 samd_static_t *out) {
+    samd_static_s *h = nullptr;
+    int rc = samd_static_build_host(docs, offs, n_docs, eos, with_counts, &h);
+    if (rc) return rc;
+    if (upload(h)) {
+        free_handle(h);
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int samd_static_destroy(samd_static_t h) {
+    free_handle(h);
+    return 0;
+}
+
+extern "C" int samd_static_info(samd_static_t h, int64_t *info) {
+    SAMD_REQUIRE(h && info, "samd_static_info: bad arguments");
+    info[0] = h->dev.n_states;
+    info[1] = h->n_edges;
+    info[2] = h->dev.n_tokens;
+    info[3] = h->dev.n_slots;
+    info[4] = h->dev.n_states * 16 + h->dev.n_slots * 16 + (h->dev.n_tokens + 1) * 4 +
+              (h->with_counts ? h->dev.n_states * (4 + 64) : 0);
+    info[5] = h->with_counts;
+    info[6] = h->n_clones;
+    info[7] = 0;
+    return 0;
+}
+
+extern "C" int samd_static_export(samd_static_t h, int32_t *link, int32_t *length, int32_t *endpos, int32_t *count,
+                                  int32_t *topk) {
+    SAMD_REQUIRE(h && h->h_states, "samd_static_export: no host mirror");
+    for (int64_t v = 0; v < h->dev.n_states; ++v) {
+        if (link) link[v] = h->h_states[v].x;
+        if (length) length[v] = h->h_states[v].y;
+        if (endpos) endpos[v] = h->h_states[v].z;
+    }
+    if (count) {
+        SAMD_REQUIRE(h->h_occ, "samd_static_export: automaton built without counts");
+        memcpy(count, h->h_occ, (size_t)h->dev.n_states * sizeof(int32_t));
+    }
+    if (topk) {
+        SAMD_REQUIRE(h->h_topk, "samd_static_export: automaton built without counts");
+        memcpy(topk, h->h_topk, (size_t)h->dev.n_states * 8 * sizeof(int2));
+    }
+    return 0;
+}
+
+// flat file: header (8 x int64) then states, slots, text, [occ, topk]
+static const int64_t kMagic = 0x30304232444d4153ll;   // "SAMD2B00"
+
+extern "C" int samd_static_save(samd_static_t h, const char *path) {
+    SAMD_REQUIRE(h && path && h->h_states, "samd_static_save: bad arguments");
+    FILE *f = fopen(path, "wb");
+    SAMD_REQUIRE(f, "samd_static_save: cannot open file");
+    int64_t hdr[8] = {kMagic, SAMD_ABI_VERSION, h->dev.n_states, h->dev.n_slots, h->dev.n_tokens, h->n_edges,
+                      h->with_counts, h->n_clones};
+    bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1;
+    ok = ok && fwrite(h->h_states, sizeof(int4), (size_t)h->dev.n_states, f) == (size_t)h->dev.n_states;
+    ok = ok && fwrite(h->h_slots, sizeof(uint4), (size_t)h->dev.n_slots, f) == (size_t)h->dev.n_slots;
+    ok = ok && fwrite(h->h_text, sizeof(int32_t), (size_t)h->dev.n_tokens + 1, f) == (size_t)h->dev.n_tokens + 1;
+    if (h->with_counts) {
+        ok = ok && fwrite(h->h_occ, sizeof(int32_t), (size_t)h->dev.n_states, f) == (size_t)h->dev.n_states;
+        ok = ok && fwrite(h->h_topk, sizeof(int2), (size_t)h->dev.n_states * 8, f) == (size_t)h->dev.n_states * 8;
+    }
+    fclose(f);
+    SAMD_REQUIRE(ok, "samd_static_save: short write");
+    return 0;
+}
+
+static int load_impl(const char *path, samd_static_t *out, bool to_device) {
+    SAMD_REQUIRE(path && out, "samd_static_load: bad arguments");
+    FILE *f = fopen(path, "rb");
+    SAMD_REQUIRE(f, "samd_static_load: cannot open file");
+    int64_t hdr[8];
+    if (fread(hdr, sizeof(hdr), 1, f) != 1 || hdr[0] != kMagic || hdr[1] != SAMD_ABI_VERSION) {
+        fclose(f);
+        samd_set_error("samd_static_load: not a samd_b200 automaton file (or ABI mismatch)");
+        return 2;
+    }
+    samd_static_s *h = new samd_static_s();
+    memset(h, 0, sizeof(*h));
+    h->dev.n_states = hdr[2];
+    h->dev.n_slots = hdr[3];
+    h->dev.n_tokens = hdr[4];
+    h->n_edges = hdr[5];
+    h->with_counts = (int)hdr[6];
+    h->n_clones = hdr[7];
+    h->dev.bmask = (uint32_t)(h->dev.n_slots / SAMD_BUCKET - 1);
+    h->h_states = (int4 *)malloc((size_t)h->dev.n_states * sizeof(int4));
+    h->h_slots = (uint4 *)malloc((size_t)h->dev.n_slots * sizeof(uint4));
+    h->h_text = (int32_t *)malloc((size_t)(h->dev.n_tokens + 1) * sizeof(int32_t));
+    bool ok = h->h_states && h->h_slots && h->h_text;
+    ok = ok && fread(h->h_states, sizeof(int4), (size_t)h->dev.n_states, f) == (size_t)h->dev.n_states;
+    ok = ok && fread(h->h_slots, sizeof(uint4), (size_t)h->dev.n_slots, f) == (size_t)h->dev.n_slots;
+    ok = ok && fread(h->h_text, sizeof(int32_t), (size_t)h->dev.n_tokens + 1, f) == (size_t)h->dev.n_tokens + 1;
+    if (ok && h->with_counts) {
+        h->h_occ = (int32_t *)malloc((size_t)h->dev.n_states * sizeof(int32_t));
+        h->h_topk = (int2 *)malloc((size_t)h->dev.n_states * 8 * sizeof(int2));
+        ok = h->h_occ && h->h_topk;
+        ok = ok && fread(h->h_occ, sizeof(int32_t), (size_t)h->dev.n_states, f) == (size_t)h->dev.n_states;
+        ok = ok && fread(h->h_topk, sizeof(int2), (size_t)h->dev.n_states * 8, f) == (size_t)h->dev.n_states * 8;
+    }
+    fclose(f);
+    if (!ok) {
+        free_handle(h);
+        samd_set_error("samd_static_load: short read");
+        return 2;
+    }
+    if (to_device && upload(h)) {
+        free_handle(h);
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int samd_static_load(const char *path, samd_static_t *out) { return load_impl(path, out, true); }
+extern "C" int samd_static_load_host(const char *path, samd_static_t *out) { return load_impl(path, out, false); }
+
+extern "C" int samd_static_set_l2_window(samd_static_t h, void *stream, int64_t bytes) {
+    SAMD_REQUIRE(h, "samd_static_set_l2_window: null handle");
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (bytes <= 0) {
+        attr.accessPolicyWindow.num_bytes = 0;
+        SAMD_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        SAMD_CUDA(cudaCtxResetPersistingL2Cache());
+        return 0;
+    }
+    cudaDeviceProp prop;
+    SAMD_CUDA(cudaGetDeviceProperties(&prop, h->device));
+    size_t carve = std::min((size_t)bytes, (size_t)prop.persistingL2CacheMaxSize);
+    SAMD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    // state records are contiguous and come first in creation (= document) order; the window
+    // covers their prefix.  hitRatio scales the window down to the carve-out.
+    size_t span = std::min((size_t)h->dev.n_states * sizeof(int4), (size_t)prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.base_ptr = (void *)h->dev.states;
+    attr.accessPolicyWindow.num_bytes = span;
+    attr.accessPolicyWindow.hitRatio = span <= carve ? 1.0f : (float)((double)carve / (double)span);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    SAMD_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// sam_only static tree drafter (samd_sam_only/sam/static_sam.py:148-215)
+// one warp per query; lane 0 runs the heap (CPython heapq sift order), the warp builds buffers
+// ---------------------------------------------------------------------------------------
+#define TREE_MAX 128
+#define HEAP_MAX (8 * TREE_MAX + 1)
+
+struct HeapItem {
+    double prob;
+    int tok, state;
+    short parent, depth;
+};
+
+__device__ __forceinline__ void heap_sift_down(HeapItem *a, int start, int pos) {   // heapq._siftdown
+    HeapItem item = a[pos];
+    while (pos > start) {
+        const int parent = (pos - 1) >> 1;
+        if (item.prob < a[parent].prob) {
+            a[pos] = a[parent];
+            pos = parent;
+            continue;
+        }
+        break;
+    }
+    a[pos] = item;
+}
+
+__device__ __forceinline__ HeapItem heap_pop(HeapItem *a, int &size) {   // heapq.heappop
+    HeapItem last = a[--size];
+    if (size == 0) return last;
+    HeapItem top = a[0];
+    a[0] = last;
+    int pos = 0, child = 1;
+    while (child < size) {                                                // heapq._siftup
+        const int right = child + 1;
+        if (right < size && !(a[child].prob < a[right].prob)) child = right;
+        a[pos] = a[child];
+        pos = child;
+        child = 2 * pos + 1;
+    }
+    a[pos] = last;
+    heap_sift_down(a, 0, pos);
+    return top;
+}
+
+__global__ void __launch_bounds__(32) static_tree_kernel(StaticDev st, int n_req, const int32_t *type, const int32_t *index,
+                                                         const int32_t *match, const int32_t *start_tok, int max_predicts,
+                                                         double alpha, int K, int len_bias, int32_t *out_tokens,
+                                                         int32_t *out_parents, int32_t *out_depth, int32_t *out_n,
+                                                         int32_t *out_ret, int max_paths, int max_depth, int32_t *out_shape) {
+    __shared__ HeapItem heap[HEAP_MAX];
+    __shared__ int s_tok[TREE_MAX], s_par[TREE_MAX], s_dep[TREE_MAX], s_cnt[TREE_MAX], s_leaf[TREE_MAX];
+    __shared__ int s_n;
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (r >= n_req) return;
+    if (type && type[r] != SAMD_DRAFT_STATIC_TREE) {
+        if (lane == 0 && out_n) out_n[r] = 0;
+        return;
+    }
+    const int m = match[r] - len_bias;
+    const int n = min(min(max_predicts, TREE_MAX), 1 + (int)((double)m * alpha));
+    for (int i = lane; i < TREE_MAX; i += 32) s_cnt[i] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        int size = 0, nt = 0;
+        heap[size++] = HeapItem{-1.0, start_tok[r], index[r], (short)-1, (short)0};
+        while (nt != n && size != 0) {
+            HeapItem it = heap_pop(heap, size);
+            if (s_cnt[it.depth] + 1 > K) continue;
+            s_cnt[it.depth] += 1;
+            const int me = nt++;
+            s_tok[me] = it.tok;
+            s_par[me] = it.parent;
+            if (nt == n) break;
+            const double total = (double)__ldg(st.occ + it.state);
+            const int2 *tk = st.topk + (size_t)it.state * 8;
+            for (int j = 0; j < K && j < 8; ++j) {
+                const int2 e = __ldg(tk + j);
+                if (e.x < 0) break;
+                const double ratio = __ddiv_rn((double)__ldg(st.occ + e.y), total);   // division first,
+                HeapItem ch{__dmul_rn(it.prob, ratio), e.x, e.y, (short)me, (short)(it.depth + 1)};   // then multiply
+                heap[size] = ch;
+                heap_sift_down(heap, 0, size);
+                size++;
+            }
+        }
+        s_n = nt;
+    }
+    __syncwarp();
+    const int nt = s_n;
+    // gen_buffers (static_sam.py:148-180): depth, leaves ascending, root-to-leaf paths, -1 padding
+    for (int i = lane; i < nt; i += 32) s_leaf[i] = 1;
+    __syncwarp();
+    for (int i = lane; i < nt; i += 32)
+        if (i > 0) s_leaf[s_par[i]] = 0;
+    for (int i = lane; i < nt; i += 32) {
+        int d = 0;
+        for (int j = i; s_par[j] >= 0; j = s_par[j]) d++;
+        s_dep[i] = d;
+    }
+    __syncwarp();
+    int n_leaves = 0, depth_max = 0;
+    for (int base = 0; base < nt; base += 32) {
+        const int i = base + lane;
+        const bool leaf = i < nt && s_leaf[i];
+        const unsigned bal = __ballot_sync(SAMD_FULL, leaf);
+        const int rank = n_leaves + __popc(bal & ((1u << lane) - 1));
+        int d = leaf ? s_dep[i] + 1 : 0;
+        for (int o = 16; o; o >>= 1) d = max(d, __shfl_xor_sync(SAMD_FULL, d, o));
+        depth_max = max(depth_max, d);
+        if (leaf && out_ret && rank < max_paths) {
+            int32_t *row = out_ret + ((size_t)r * max_paths + rank) * max_depth;
+            for (int c = s_dep[i] + 1; c < max_depth; ++c) row[c] = -1;
+            for (int j = i; j >= 0; j = s_par[j])
+                if (s_dep[j] < max_depth) row[s_dep[j]] = j;
+        }
+        n_leaves += __popc(bal);
+    }
+    for (int i = lane; i < nt; i += 32) {
+        if (out_tokens) out_tokens[(size_t)r * max_predicts + i] = s_tok[i];
+        if (out_parents) out_parents[(size_t)r * max_predicts + i] = s_par[i];
+        if (out_depth) out_depth[(size_t)r * max_predicts + i] = s_dep[i];
+    }
+    if (lane == 0) {
+        if (out_n) out_n[r] = nt;
+        if (out_shape) {
+            out_shape[2 * r] = n_leaves;
+            out_shape[2 * r + 1] = depth_max;
+        }
+    }
+}
+
+extern "C" int samd_static_tree_draft(samd_static_t h, int n_requests, const int32_t *type_dev, const int32_t *index_static_dev,
+                                      const int32_t *match_static_dev, const int32_t *start_tok_dev, int32_t max_predicts,
+                                      double alpha, int32_t K, int32_t len_bias, int32_t *out_tokens_dev,
+                                      int32_t *out_parents_dev, int32_t *out_depth_dev, int32_t *out_n_nodes_dev,
+                                      int32_t *out_retrieve_dev, int32_t max_paths, int32_t max_depth,
+                                      int32_t *out_retrieve_shape_dev, void *stream) {
+    SAMD_REQUIRE(h && h->with_counts, "samd_static_tree_draft: automaton was built without counts");
+    SAMD_REQUIRE(n_requests > 0 && index_static_dev && match_static_dev && start_tok_dev, "samd_static_tree_draft: bad arguments");
+    SAMD_REQUIRE(max_predicts > 0 && max_predicts <= TREE_MAX, "samd_static_tree_draft: max_predicts must be in [1,128]");
+    SAMD_REQUIRE(K > 0 && K <= 8, "samd_static_tree_draft: K must be in [1,8]");
+    static_tree_kernel<<<n_requests, 32, 0, (cudaStream_t)stream>>>(
+        h->dev, n_requests, type_dev, index_static_dev, match_static_dev, start_tok_dev, max_predicts, alpha, K, len_bias,
+        out_tokens_dev, out_parents_dev, out_depth_dev, out_n_nodes_dev, out_retrieve_dev, max_paths, max_depth,
+        out_retrieve_shape_dev);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,439 @@
+// Dynamic-SAM arenas and the per-step draft kernel (extend + advance + lookup + select + draft).
+// One warp per request; see include/samd_b200.h for the reference methods each entry replaces.
+#include "samd_common.cuh"
+#include "../../include/samd_b200.h"
+
+// ---------------------------------------------------------------------------------------
+// arena management
+// ---------------------------------------------------------------------------------------
+__global__ void dyn_reset_kernel(DynArena a, const uint8_t *mask) {
+    // one CTA per request: clear the edge table (0xFF = free), write the root and the meta block
+    int r = blockIdx.x;
+    if (mask && !mask[r]) return;
+    uint4 *slots = a.slots + (size_t)r * a.h_cap;
+    const uint4 e = make_uint4(SAMD_EMPTY, SAMD_EMPTY, SAMD_EMPTY, SAMD_EMPTY);
+    for (uint32_t i = threadIdx.x; i < a.h_cap; i += blockDim.x) slots[i] = e;
+    if (threadIdx.x == 0) {
+        a.states[(size_t)r * a.s_cap] = make_int4(-1, 0, 0, (int)SAMD_NIL);   // root (dyn_sam.py:19)
+        a.text[(size_t)r * a.t_cap] = -1;                                       // sentinel (dyn_sam.py:20)
+        int32_t *m = a.meta + (size_t)r * META_WORDS;
+        m[META_NSTATES] = 1;
+        m[META_LAST] = 0;
+        m[META_N] = 0;
+        m[META_CUR] = 0;
+        m[META_CURLEN] = 0;
+        m[META_NEDGES] = 0;
+        m[META_OVERFLOW] = 0;
+        m[META_NCLONES] = 0;
+    }
+}
+
+extern "C" int samd_dyn_create(int n_requests, int max_tokens, samd_dyn_t *out) {
+    SAMD_REQUIRE(n_requests > 0 && max_tokens > 0 && out, "samd_dyn_create: bad arguments");
+    SAMD_REQUIRE(max_tokens < (1 << 28), "samd_dyn_create: max_tokens too large");
+    samd_dyn_s *h = new samd_dyn_s();
+    DynArena &a = h->a;
+    a.n_requests = n_requests;
+    a.max_tokens = max_tokens;
+    a.s_cap = 2u * (uint32_t)max_tokens + 2u;                 // states <= 2n - 1 (+ root)
+    a.h_cap = (uint32_t)samd_table_slots((uint64_t)max_tokens);
+    a.t_cap = ((uint32_t)max_tokens + 1u + 3u) & ~3u;
+    a.bmask = a.h_cap / SAMD_BUCKET - 1u;
+    SAMD_CUDA(cudaGetDevice(&h->device));
+    size_t b_states = (size_t)n_requests * a.s_cap * sizeof(int4);
+    size_t b_slots = (size_t)n_requests * a.h_cap * sizeof(uint4);
+    size_t b_text = (size_t)n_requests * a.t_cap * sizeof(int32_t);
+    size_t b_meta = (size_t)n_requests * META_WORDS * sizeof(int32_t);
+    SAMD_CUDA(cudaMalloc(&a.states, b_states));
+    SAMD_CUDA(cudaMalloc(&a.slots, b_slots));
+    SAMD_CUDA(cudaMalloc(&a.text, b_text));
+    SAMD_CUDA(cudaMalloc(&a.meta, b_meta));
+    h->bytes = (int64_t)(b_states + b_slots + b_text + b_meta);
+    *out = h;
+    return samd_dyn_reset(h, nullptr, nullptr);
+}
+
+extern "C" int samd_dyn_destroy(samd_dyn_t h) {
+    if (!h) return 0;
+    cudaFree(h->a.states);
+    cudaFree(h->a.slots);
+    cudaFree(h->a.text);
+    cudaFree(h->a.meta);
+    delete h;
+    return 0;
+}
+
+extern "C" int64_t samd_dyn_bytes(samd_dyn_t h) { return h ? h->bytes : 0; }
+
+extern "C" int samd_dyn_reset(samd_dyn_t h, const uint8_t *mask_dev, void *stream) {
+    SAMD_REQUIRE(h, "samd_dyn_reset: null handle");
+    dyn_reset_kernel<<<h->a.n_requests, 256, 0, (cudaStream_t)stream>>>(h->a, mask_dev);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int samd_dyn_export(samd_dyn_t h, int request, int32_t *meta_host, int32_t *link_host, int32_t *length_host,
+                               int32_t *endpos_host, int32_t *text_host, int64_t capacity) {
+    SAMD_REQUIRE(h && request >= 0 && request < h->a.n_requests, "samd_dyn_export: bad request index");
+    SAMD_CUDA(cudaDeviceSynchronize());
+    int32_t meta[META_WORDS];
+    SAMD_CUDA(cudaMemcpy(meta, h->a.meta + (size_t)request * META_WORDS, sizeof(meta), cudaMemcpyDeviceToHost));
+    if (meta_host)
+        for (int i = 0; i < META_WORDS; ++i) meta_host[i] = meta[i];
+    int ns = meta[META_NSTATES];
+    if (link_host || length_host || endpos_host) {
+        SAMD_REQUIRE(capacity >= ns, "samd_dyn_export: capacity too small");
+        int4 *tmp = (int4 *)malloc((size_t)ns * sizeof(int4));
+        SAMD_CUDA(cudaMemcpy(tmp, h->a.states + (size_t)request * h->a.s_cap, (size_t)ns * sizeof(int4),
+                             cudaMemcpyDeviceToHost));
+        for (int i = 0; i < ns; ++i) {
+            if (link_host) link_host[i] = tmp[i].x;
+            if (length_host) length_host[i] = tmp[i].y;
+            if (endpos_host) endpos_host[i] = tmp[i].z;
+        }
+        free(tmp);
+    }
+    if (text_host) {
+        SAMD_REQUIRE(capacity >= meta[META_N] + 1, "samd_dyn_export: capacity too small for text");
+        SAMD_CUDA(cudaMemcpy(text_host, h->a.text + (size_t)request * h->a.t_cap,
+                             (size_t)(meta[META_N] + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// online append with clone-on-split (dyn_sam.py:41-67); registers are warp-uniform
+// ---------------------------------------------------------------------------------------
+struct DynRegs {
+    int n_states, last, n, cur, cur_len, n_edges, n_clones;
+};
+
+__device__ __forceinline__ void dyn_append(int4 *states, uint4 *slots, int32_t *text, uint32_t bmask, DynRegs &g, int tok,
+                                           int lane) {
+    g.n += 1;
+    const int cur = g.n_states++;
+    if (lane == 0) {
+        states[cur] = make_int4(-1, g.n, g.n, (int)SAMD_NIL);
+        text[g.n] = tok;
+    }
+    __syncwarp();
+    int p = g.last;
+    int link_cur = 0;
+    while (p != -1) {
+        Probe pr = warp_probe<true, false>(slots, bmask, states, (uint32_t)p, (uint32_t)tok, lane);
+        if (!pr.found) {
+            // p has no edge on tok: add p --tok--> cur at the free slot the probe ended on
+            if (lane == 0) {
+                slots[pr.slot] = make_uint4((uint32_t)p, (uint32_t)tok, (uint32_t)cur, (uint32_t)pr.rec.w);
+                reinterpret_cast<int32_t *>(states + p)[3] = (int)pr.slot;
+            }
+            g.n_edges++;
+            __syncwarp();
+            p = pr.rec.x;
+            continue;
+        }
+        const int q = (int)pr.target;
+        const int4 rq = states[q];
+        if (pr.rec.y + 1 == rq.y) {
+            link_cur = q;
+        } else {
+            // clone-on-split: copy q's edges, link and min_endpos; length = len(p) + 1
+            const int clone = g.n_states++;
+            g.n_clones++;
+            uint32_t head_c = SAMD_NIL;
+            uint32_t e = (uint32_t)rq.w;
+            while (e != SAMD_NIL) {
+                const uint4 se = slots[e];
+                Probe pi = warp_probe<false, false>(slots, bmask, states, (uint32_t)clone, se.y, lane);
+                if (lane == 0) slots[pi.slot] = make_uint4((uint32_t)clone, se.y, se.z, head_c);
+                head_c = pi.slot;
+                g.n_edges++;
+                __syncwarp();
+                e = se.w;
+            }
+            if (lane == 0) states[clone] = make_int4(rq.x, pr.rec.y + 1, rq.z, (int)head_c);
+            // redirect p's suffix chain from q to the clone
+            Probe cp = pr;
+            while (true) {
+                if (lane == 0) slots[cp.slot].z = (uint32_t)clone;
+                __syncwarp();
+                const int pp = cp.rec.x;
+                if (pp == -1) break;
+                cp = warp_probe<true, false>(slots, bmask, states, (uint32_t)pp, (uint32_t)tok, lane);
+                if (!(cp.found && (int)cp.target == q)) break;
+            }
+            if (lane == 0) reinterpret_cast<int32_t *>(states + q)[0] = clone;
+            link_cur = clone;
+        }
+        break;
+    }
+    if (lane == 0) reinterpret_cast<int32_t *>(states + cur)[0] = link_cur;
+    __syncwarp();
+    g.last = cur;
+}
+
+struct StepParams {
+    DynArena dyn;
+    StaticDev st;
+    int has_static;
+    int32_t *static_cursor;
+    const int32_t *tokens;
+    int token_stride;
+    const int32_t *counts;
+    const int32_t *start_tok;
+    int flavour, n_predicts, len_bias, len_threshold;
+    double alpha;
+    int32_t *out_type, *out_match_dyn, *out_match_static, *out_index_dyn, *out_index_static, *out_draft, *out_draft_len;
+    int draft_stride;
+};
+
+__global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (r >= P.dyn.n_requests) return;
+    int4 *states = P.dyn.states + (size_t)r * P.dyn.s_cap;
+    uint4 *slots = P.dyn.slots + (size_t)r * P.dyn.h_cap;
+    int32_t *text = P.dyn.text + (size_t)r * P.dyn.t_cap;
+    int32_t *meta = P.dyn.meta + (size_t)r * META_WORDS;
+    const uint32_t bmask = P.dyn.bmask;
+
+    DynRegs g;
+    {
+        int m = (lane < META_WORDS) ? meta[lane] : 0;
+        g.n_states = __shfl_sync(SAMD_FULL, m, META_NSTATES);
+        g.last = __shfl_sync(SAMD_FULL, m, META_LAST);
+        g.n = __shfl_sync(SAMD_FULL, m, META_N);
+        g.cur = __shfl_sync(SAMD_FULL, m, META_CUR);
+        g.cur_len = __shfl_sync(SAMD_FULL, m, META_CURLEN);
+        g.n_edges = __shfl_sync(SAMD_FULL, m, META_NEDGES);
+        g.n_clones = __shfl_sync(SAMD_FULL, m, META_NCLONES);
+    }
+    int s_idx = 0, s_len = 0;
+    if (P.has_static) {
+        s_idx = P.static_cursor[2 * r];
+        s_len = P.static_cursor[2 * r + 1];
+    }
+
+    // ---- phase 1: DraftModel.update (draft.py:65-79) ------------------------------------
+    if (P.tokens) {
+        const int k = P.counts ? P.counts[r] : P.token_stride;
+        const int32_t *tk = P.tokens + (size_t)r * P.token_stride;
+        bool overflow = false;
+        for (int i = 0; i < k; i += 32) {
+            const int mine = (i + lane < k) ? tk[i + lane] : 0;     // coalesced token fetch
+            const int lim = min(32, k - i);
+            for (int j = 0; j < lim; ++j) {
+                const int tok = __shfl_sync(SAMD_FULL, mine, j);
+                if (g.n >= P.dyn.max_tokens) {
+                    overflow = true;
+                    break;
+                }
+                // add_tokens: match first, then append (dyn_sam.py:84-88)
+                warp_transfer<false>(slots, bmask, states, g.cur, g.cur_len, tok, lane);
+                dyn_append(states, slots, text, bmask, g, tok, lane);
+                // StaticSAM.transfer_tokens (static_sam.py:102-104)
+                if (P.has_static) warp_transfer<true>(P.st.slots, P.st.bmask, P.st.states, s_idx, s_len, tok, lane);
+            }
+            if (overflow) break;
+        }
+        if (lane == 0) {
+            meta[META_NSTATES] = g.n_states;
+            meta[META_LAST] = g.last;
+            meta[META_N] = g.n;
+            meta[META_CUR] = g.cur;
+            meta[META_CURLEN] = g.cur_len;
+            meta[META_NEDGES] = g.n_edges;
+            meta[META_NCLONES] = g.n_clones;
+            if (overflow) meta[META_OVERFLOW] = 1;
+            if (P.has_static) {
+                P.static_cursor[2 * r] = s_idx;
+                P.static_cursor[2 * r + 1] = s_len;
+            }
+        }
+    }
+    if (!P.start_tok) return;
+
+    // ---- phase 2: DraftModel.lookup (draft.py:52-63 / samd_sam_only/draft.py:49-59) -------
+    const int tok = P.start_tok[r];
+    int d_idx = g.cur, d_len = g.cur_len;
+    warp_transfer<false>(slots, bmask, states, d_idx, d_len, tok, lane);
+    int t_idx = 0, t_len = 0;
+    if (P.has_static) {
+        t_idx = s_idx;
+        t_len = s_len;
+        warp_transfer<true>(P.st.slots, P.st.bmask, P.st.states, t_idx, t_len, tok, lane);
+    }
+    const int t_biased = t_len - P.len_bias;
+    int type, n_out, endpos = 0, text_n = 0;
+    const int32_t *src = nullptr;
+    if (P.flavour == SAMD_FLAVOUR_SAMD) {
+        n_out = P.n_predicts;
+        if (max(d_len, t_biased) >= P.len_threshold) {
+            if (d_len >= t_biased) {
+                type = SAMD_DRAFT_DYN_SEQ;
+                // to_anc (dyn_sam.py:99-105)
+                int idx = d_idx;
+                int4 rec = states[idx];
+                if (idx != 0) {
+                    while (rec.x != 0 && P.n_predicts > g.n - rec.z) {
+                        idx = rec.x;
+                        rec = states[idx];
+                    }
+                }
+                endpos = rec.z;
+                src = text;
+                text_n = g.n;
+            } else {
+                type = SAMD_DRAFT_STATIC_SEQ;
+                endpos = __ldg(P.st.states + t_idx).z;
+                src = P.st.text;
+                text_n = (int)P.st.n_tokens;
+            }
+        } else {
+            type = SAMD_DRAFT_TREE_MODEL;
+            n_out = 0;
+        }
+    } else {
+        if (d_len >= t_biased) {
+            type = SAMD_DRAFT_DYN_SEQ;
+            const int budget = min(P.n_predicts, 1 + (int)((double)d_len * P.alpha));
+            endpos = states[d_idx].z;
+            src = text;
+            text_n = g.n;
+            // [start] + text[e+1 : e+n]  (no padding; samd_sam_only/sam/dyn_sam.py:116-119)
+            const int avail = max(0, min(endpos + budget, text_n + 1) - (endpos + 1));
+            n_out = 1 + avail;
+        } else {
+            type = SAMD_DRAFT_STATIC_TREE;
+            n_out = 0;
+        }
+    }
+    if (P.out_draft) {
+        int32_t *dr = P.out_draft + (size_t)r * P.draft_stride;
+        for (int j = lane; j < P.draft_stride; j += 32) {
+            int v = 0;
+            if (j < n_out) {
+                if (j == 0) v = tok;
+                else {
+                    const int pos = endpos + j;
+                    v = (pos <= text_n) ? src[pos] : 0;       // zero padding past the end of the text
+                }
+            }
+            dr[j] = v;
+        }
+    }
+    if (lane == 0) {
+        if (P.out_type) P.out_type[r] = type;
+        if (P.out_match_dyn) P.out_match_dyn[r] = d_len;
+        if (P.out_match_static) P.out_match_static[r] = t_len;
+        if (P.out_index_dyn) P.out_index_dyn[r] = d_idx;
+        if (P.out_index_static) P.out_index_static[r] = t_idx;
+        if (P.out_draft_len) P.out_draft_len[r] = n_out;
+    }
+}
+
+extern "C" int samd_step(const samd_step_args *a, void *stream) {
+    SAMD_REQUIRE(a && a->dyn, "samd_step: dyn handle required");
+    SAMD_REQUIRE((a->stat == nullptr) == (a->static_cursor_dev == nullptr),
+                 "samd_step: static handle and static cursor must be given together");
+    StepParams P;
+    P.dyn = a->dyn->a;
+    P.has_static = a->stat != nullptr;
+    if (a->stat) P.st = a->stat->dev;
+    else P.st = StaticDev{};
+    P.static_cursor = a->static_cursor_dev;
+    P.tokens = a->tokens_dev;
+    P.token_stride = a->token_stride;
+    P.counts = a->counts_dev;
+    P.start_tok = a->start_tok_dev;
+    P.flavour = a->flavour;
+    P.n_predicts = a->n_predicts;
+    P.len_bias = a->len_bias;
+    P.len_threshold = a->len_threshold;
+    P.alpha = a->alpha;
+    P.out_type = a->out_type_dev;
+    P.out_match_dyn = a->out_match_dyn_dev;
+    P.out_match_static = a->out_match_static_dev;
+    P.out_index_dyn = a->out_index_dyn_dev;
+    P.out_index_static = a->out_index_static_dev;
+    P.out_draft = a->out_draft_dev;
+    P.out_draft_len = a->out_draft_len_dev;
+    P.draft_stride = a->draft_stride;
+    SAMD_REQUIRE(a->flavour == SAMD_FLAVOUR_SAMD || a->flavour == SAMD_FLAVOUR_SAM_ONLY, "samd_step: bad flavour");
+    SAMD_REQUIRE(!a->tokens_dev || a->token_stride > 0, "samd_step: token_stride must be positive");
+    SAMD_REQUIRE(!a->out_draft_dev || a->draft_stride >= a->n_predicts, "samd_step: draft_stride < n_predicts");
+    sam_step_kernel<<<P.dyn.n_requests, 32, 0, (cudaStream_t)stream>>>(P);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// document-sharded static SAM: per-shard packed keys, draft from the winning global position
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) static_keys_kernel(StaticDev st, const int32_t *cursor, const int32_t *start_tok,
+                                                         int n, long long shard_offset, long long *keys) {
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (r >= n) return;
+    int idx = cursor[2 * r], len = cursor[2 * r + 1];
+    warp_transfer<true>(st.slots, st.bmask, st.states, idx, len, start_tok[r], lane);
+    if (lane == 0) {
+        long long key = 0;
+        if (len > 0) {
+            const long long e = shard_offset + (long long)__ldg(st.states + idx).z;
+            key = ((long long)len << 32) | (long long)(0xFFFFFFFFu - (uint32_t)e);
+        }
+        keys[r] = key;
+    }
+}
+
+extern "C" int samd_static_lookup_keys(samd_static_t h, const int32_t *static_cursor_dev, const int32_t *start_tok_dev,
+                                       int n_requests, int64_t shard_offset, int64_t *out_keys_dev, void *stream) {
+    SAMD_REQUIRE(h && static_cursor_dev && start_tok_dev && out_keys_dev && n_requests > 0,
+                 "samd_static_lookup_keys: bad arguments");
+    static_keys_kernel<<<n_requests, 32, 0, (cudaStream_t)stream>>>(h->dev, static_cursor_dev, start_tok_dev, n_requests,
+                                                                     (long long)shard_offset, (long long *)out_keys_dev);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void draft_from_keys_kernel(const long long *keys, const int32_t *corpus, long long n_tokens,
+                                       const int32_t *start_tok, int n, int n_predicts, int32_t *out_match, int32_t *out_draft,
+                                       int stride) {
+    const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const long long key = keys[r];
+    const int len = (int)(key >> 32);
+    // no match anywhere: endpos 0 (root), like StaticSAM.gen_draft on index 0 (static_sam.py:119-125)
+    const long long e = len > 0 ? (long long)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFll)) : 0;
+    if (lane == 0 && out_match) out_match[r] = len;
+    for (int j = lane; j < stride; j += 32) {
+        int v = 0;
+        if (j < n_predicts) {
+            if (j == 0) v = start_tok[r];
+            else {
+                const long long pos = e + j;
+                v = pos <= n_tokens ? corpus[pos] : 0;
+            }
+        }
+        out_draft[(size_t)r * stride + j] = v;
+    }
+}
+
+extern "C" int samd_draft_from_keys(const int64_t *keys_dev, const int32_t *corpus_dev, int64_t n_corpus_tokens,
+                                    const int32_t *start_tok_dev, int n_requests, int32_t n_predicts, int32_t *out_match_dev,
+                                    int32_t *out_draft_dev, int32_t draft_stride, void *stream) {
+    SAMD_REQUIRE(keys_dev && corpus_dev && start_tok_dev && out_draft_dev && n_requests > 0 && draft_stride >= n_predicts,
+                 "samd_draft_from_keys: bad arguments");
+    const int wpb = 8;
+    draft_from_keys_kernel<<<(n_requests + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const long long *)keys_dev, corpus_dev, (long long)n_corpus_tokens, start_tok_dev, n_requests, n_predicts,
+        out_match_dev, out_draft_dev, draft_stride);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,345 @@
+"""Batched host API over the C ABI: the device-resident counterparts of the reference's
+DynSAM / StaticSAM / DraftModel.lookup+update / eval_posterior+select_indices.
+
+Everything here marshals torch tensors (device memory + the current stream) into
+libsamd_b200.so calls; no arithmetic of the hot path runs in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi as K
+
+
+def _i32(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.int32 and t.is_cuda and t.is_contiguous(), "expected a contiguous int32 CUDA tensor"
+    return t
+
+
+class DynSamBatch:
+    """`n_requests` independent dynamic suffix automata in HBM (samd/sam/dyn_sam.py:8-113)."""
+
+    def __init__(self, n_requests: int, max_tokens: int, device: Optional[torch.device] = None):
+        K.require_device()
+        self.device = torch.device(device if device is not None else "cuda")
+        self.n_requests = int(n_requests)
+        self.max_tokens = int(max_tokens)
+        self._h = K.vp()
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_dyn_create(self.n_requests, self.max_tokens, C.byref(self._h)), "samd_dyn_create")
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def nbytes(self) -> int:
+        return int(K.lib().samd_dyn_bytes(self._h))
+
+    def reset(self, mask: Optional[torch.Tensor] = None):
+        """DynSAM.reset for the masked requests (uint8 CUDA tensor; None = all)."""
+        if mask is not None:
+            assert mask.dtype == torch.uint8 and mask.is_cuda and mask.numel() == self.n_requests
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_dyn_reset(self._h, K.ptr(mask), K.stream_ptr()), "samd_dyn_reset")
+
+    def export(self, request: int, with_text: bool = True):
+        """Host copy of one request's automaton (synchronises) - for parity tests."""
+        meta = np.zeros(8, dtype=np.int32)
+        cap = 2 * self.max_tokens + 2
+        link = np.zeros(cap, dtype=np.int32)
+        length = np.zeros(cap, dtype=np.int32)
+        endpos = np.zeros(cap, dtype=np.int32)
+        text = np.zeros(cap, dtype=np.int32)
+        as_p = lambda a: a.ctypes.data_as(K.c_i32p)
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_dyn_export(self._h, int(request), as_p(meta), as_p(link), as_p(length), as_p(endpos),
+                                            as_p(text) if with_text else None, cap), "samd_dyn_export")
+        ns, n = int(meta[0]), int(meta[2])
+        return dict(n_states=ns, last=int(meta[1]), max_length=n, cur_index=int(meta[3]), cur_length=int(meta[4]),
+                    n_edges=int(meta[5]), overflow=int(meta[6]), n_clones=int(meta[7]), link=link[:ns], length=length[:ns],
+                    min_endpos=endpos[:ns], text=text[:n + 1])
+
+    def close(self):
+        if self._h:
+            K.lib().samd_dyn_destroy(self._h)
+            self._h = K.vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class StaticSamDevice:
+    """Read-only static suffix automaton in HBM (samd/sam/static_sam.py, samd_sam_only/sam/static_sam.py)."""
+
+    def __init__(self, handle, device):
+        self._h = handle
+        self.device = device
+        info = np.zeros(8, dtype=np.int64)
+        K.check(K.lib().samd_static_info(self._h, info.ctypes.data_as(K.c_i64p)), "samd_static_info")
+        self.n_states, self.n_edges, self.n_tokens, self.n_slots, self.nbytes, wc, self.n_clones, _ = (int(x) for x in info)
+        self.with_counts = bool(wc)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @staticmethod
+    def build(docs: Sequence[Sequence[int]], eos: int, with_counts: bool = False,
+              device: Optional[torch.device] = None, host_only: bool = False) -> "StaticSamDevice":
+        """StaticSAM.build (static_sam.py:38-46): host construction, flat upload."""
+        lens = np.fromiter((len(d) for d in docs), dtype=np.int64, count=len(docs))
+        offs = np.zeros(len(docs) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        flat = np.empty(int(offs[-1]), dtype=np.int32)
+        for i, d in enumerate(docs):
+            flat[offs[i]:offs[i + 1]] = d
+        return StaticSamDevice.build_flat(flat, offs, eos, with_counts, device, host_only)
+
+    @staticmethod
+    def build_flat(flat: np.ndarray, offs: np.ndarray, eos: int, with_counts: bool = False,
+                   device: Optional[torch.device] = None, host_only: bool = False) -> "StaticSamDevice":
+        """host_only=True stops after the host construction (no CUDA device needed): the result
+        can be exported / saved but not queried until upload()."""
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        h = K.vp()
+        args = (flat.ctypes.data_as(K.c_i32p), offs.ctypes.data_as(K.c_i64p), len(offs) - 1, int(eos), int(with_counts),
+                C.byref(h))
+        if host_only:
+            K.check(K.lib().samd_static_build_host(*args), "samd_static_build_host")
+            return StaticSamDevice(h, None)
+        K.require_device()
+        device = torch.device(device if device is not None else "cuda")
+        with torch.cuda.device(device):
+            K.check(K.lib().samd_static_build(*args), "samd_static_build")
+        return StaticSamDevice(h, device)
+
+    def upload(self, device: Optional[torch.device] = None):
+        K.require_device()
+        self.device = torch.device(device if device is not None else "cuda")
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_static_upload(self._h), "samd_static_upload")
+        return self
+
+    @staticmethod
+    def load(path: str, device: Optional[torch.device] = None, host_only: bool = False) -> "StaticSamDevice":
+        h = K.vp()
+        if host_only:
+            K.check(K.lib().samd_static_load_host(path.encode(), C.byref(h)), "samd_static_load_host")
+            return StaticSamDevice(h, None)
+        K.require_device()
+        device = torch.device(device if device is not None else "cuda")
+        with torch.cuda.device(device):
+            K.check(K.lib().samd_static_load(path.encode(), C.byref(h)), "samd_static_load")
+        return StaticSamDevice(h, device)
+
+    def save(self, path: str):
+        K.check(K.lib().samd_static_save(self._h, path.encode()), "samd_static_save")
+
+    def export(self):
+        n = self.n_states
+        link = np.zeros(n, dtype=np.int32)
+        length = np.zeros(n, dtype=np.int32)
+        endpos = np.zeros(n, dtype=np.int32)
+        as_p = lambda a: a.ctypes.data_as(K.c_i32p)
+        count = topk = None
+        if self.with_counts:
+            count = np.zeros(n, dtype=np.int32)
+            topk = np.zeros((n, 8, 2), dtype=np.int32)
+        K.check(K.lib().samd_static_export(self._h, as_p(link), as_p(length), as_p(endpos),
+                                           as_p(count) if count is not None else None,
+                                           as_p(topk) if topk is not None else None), "samd_static_export")
+        return dict(link=link, length=length, min_endpos=endpos, cnt_endpos=count, topk=topk)
+
+    def set_l2_window(self, nbytes: int):
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_static_set_l2_window(self._h, K.stream_ptr(), int(nbytes)), "samd_static_set_l2_window")
+
+    def new_cursors(self, n_requests: int) -> torch.Tensor:
+        """StaticSAM.reset (static_sam.py:28-30) for n_requests queries: (index, length) = (0, 0)."""
+        return torch.zeros(n_requests, 2, dtype=torch.int32, device=self.device)
+
+    def close(self):
+        if self._h:
+            K.lib().samd_static_destroy(self._h)
+            self._h = K.vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DraftEngine:
+    """DraftModel.update + DraftModel.lookup for a batch of requests (samd/draft.py:52-79,
+    samd_sam_only/draft.py:49-67): one `samd_step` launch per call, outputs stay on the device."""
+
+    def __init__(self, dyn: DynSamBatch, static: Optional[StaticSamDevice] = None, flavour: int = K.FLAVOUR_SAMD,
+                 n_predicts: int = 40, len_bias: int = 5, len_threshold: int = 5, alpha: float = 4.0):
+        self.dyn, self.static = dyn, static
+        self.flavour, self.n_predicts, self.len_bias, self.len_threshold, self.alpha = \
+            int(flavour), int(n_predicts), int(len_bias), int(len_threshold), float(alpha)
+        B, dev = dyn.n_requests, dyn.device
+        self.static_cursor = static.new_cursors(B) if static is not None else None
+        mk = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+        self.out_type, self.match_dyn, self.match_static = mk(B), mk(B), mk(B)
+        self.index_dyn, self.index_static, self.draft_len = mk(B), mk(B), mk(B)
+        self.draft = mk(B, self.n_predicts)
+        self._args = K.StepArgs()
+
+    def reset(self, mask: Optional[torch.Tensor] = None):
+        """DraftModel.reset (draft.py:47-50)."""
+        self.dyn.reset(mask)
+        if self.static_cursor is not None:
+            if mask is None:
+                self.static_cursor.zero_()
+            else:
+                self.static_cursor.masked_fill_(mask.bool().unsqueeze(1), 0)
+
+    def step(self, tokens: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
+             start_tok: Optional[torch.Tensor] = None):
+        """update(tokens[:, :counts]) then lookup(start_tok); either half may be omitted."""
+        a = self._args
+        a.dyn = self.dyn.handle
+        a.stat = self.static.handle if self.static is not None else None
+        a.static_cursor_dev = K.ptr(self.static_cursor)
+        if tokens is not None:
+            _i32(tokens)
+            assert tokens.dim() == 2 and tokens.shape[0] == self.dyn.n_requests
+            a.tokens_dev, a.token_stride = tokens.data_ptr(), tokens.shape[1]
+            a.counts_dev = K.ptr(_i32(counts)) if counts is not None else None
+        else:
+            a.tokens_dev, a.token_stride, a.counts_dev = None, 0, None
+        a.start_tok_dev = K.ptr(_i32(start_tok)) if start_tok is not None else None
+        a.flavour, a.n_predicts, a.len_bias, a.len_threshold, a.alpha = \
+            self.flavour, self.n_predicts, self.len_bias, self.len_threshold, self.alpha
+        a.out_type_dev, a.out_match_dyn_dev, a.out_match_static_dev = \
+            self.out_type.data_ptr(), self.match_dyn.data_ptr(), self.match_static.data_ptr()
+        a.out_index_dyn_dev, a.out_index_static_dev = self.index_dyn.data_ptr(), self.index_static.data_ptr()
+        a.out_draft_dev, a.draft_stride, a.out_draft_len_dev = self.draft.data_ptr(), self.n_predicts, self.draft_len.data_ptr()
+        with torch.cuda.device(self.dyn.device):
+            K.check(K.lib().samd_step(C.byref(a), K.stream_ptr()), "samd_step")
+
+    def tree_draft(self, start_tok: torch.Tensor, K_top: int = 8, max_paths: Optional[int] = None):
+        """sam_only static tree for requests whose out_type is DRAFT_STATIC_TREE (after step())."""
+        assert self.static is not None and self.static.with_counts
+        B, dev, n = self.dyn.n_requests, self.dyn.device, self.n_predicts
+        max_paths = max_paths or n
+        if not hasattr(self, "tree_tokens"):
+            mk = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+            self.tree_tokens, self.tree_parents, self.tree_depth = mk(B, n), mk(B, n), mk(B, n)
+            self.tree_n, self.tree_shape = mk(B), mk(B, 2)
+            self.tree_retrieve = mk(B, max_paths, n)
+        with torch.cuda.device(dev):
+            K.check(K.lib().samd_static_tree_draft(
+                self.static.handle, B, self.out_type.data_ptr(), self.index_static.data_ptr(), self.match_static.data_ptr(),
+                _i32(start_tok).data_ptr(), n, self.alpha, int(K_top), self.len_bias, self.tree_tokens.data_ptr(),
+                self.tree_parents.data_ptr(), self.tree_depth.data_ptr(), self.tree_n.data_ptr(),
+                self.tree_retrieve.data_ptr(), self.tree_retrieve.shape[1], self.tree_retrieve.shape[2],
+                self.tree_shape.data_ptr(), K.stream_ptr()), "samd_static_tree_draft")
+
+
+class Verifier:
+    """Fused greedy verification + KV compaction (samd/utils.py:127-141, samd/samd_model.py:159-211,
+    samd/cache.py:118-133) for a batch of requests: one persistent launch."""
+
+    def __init__(self, max_batch: int, max_nodes: int, device: Optional[torch.device] = None):
+        K.require_device()
+        self.device = torch.device(device if device is not None else "cuda")
+        self._h = K.vp()
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_verify_create(int(max_batch), int(max_nodes), C.byref(self._h)), "samd_verify_create")
+        self._args = K.VerifyArgs()
+        self._kv_key = None
+        self._kv_ptrs = None
+
+    def bind_kv(self, kv_tensors: Optional[List[torch.Tensor]]):
+        """Register the 2L cache tensors [B, H, max_len, Dh] (key_cache + value_cache order)."""
+        if kv_tensors is None:
+            self._kv_key, self._kv_ptrs, self._kv_meta = None, None, None
+            return
+        key = tuple(t.data_ptr() for t in kv_tensors)
+        if key == self._kv_key:
+            return
+        t0 = kv_tensors[0]
+        assert t0.dim() == 4 and t0.stride(3) == 1
+        es = t0.element_size()
+        for t in kv_tensors:
+            assert t.shape == t0.shape and t.stride() == t0.stride() and t.dtype == t0.dtype and t.device == t0.device
+        self._kv_ptrs = torch.tensor(list(key), dtype=torch.int64, device=self.device)
+        self._kv_meta = dict(n_kv=len(kv_tensors), n_heads=t0.shape[1], row_bytes=t0.shape[3] * es,
+                             batch_stride=t0.stride(0) * es, head_stride=t0.stride(1) * es, pos_stride=t0.stride(2) * es)
+        self._kv_key = key
+
+    def verify(self, logits: torch.Tensor, tree_tokens: torch.Tensor, retrieve: Optional[torch.Tensor],
+               cache_len: Optional[torch.Tensor] = None, move_kv: bool = True, n_nodes: Optional[torch.Tensor] = None,
+               n_paths: Optional[torch.Tensor] = None, out: Optional[dict] = None, want_argmax: bool = False) -> dict:
+        assert logits.is_cuda and logits.dim() == 3 and logits.stride(2) == 1
+        B, T, V = logits.shape
+        dt = {torch.bfloat16: K.DTYPE_BF16, torch.float16: K.DTYPE_FP16}.get(logits.dtype)
+        if dt is None:
+            raise K.SamdError(f"unsupported logits dtype {logits.dtype} (bf16 / fp16 only)")
+        _i32(tree_tokens)
+        assert tree_tokens.shape == (B, T)
+        a = self._args
+        a.logits_dev, a.dtype, a.batch, a.n_nodes, a.vocab = logits.data_ptr(), dt, B, T, V
+        a.batch_stride, a.row_stride = logits.stride(0), logits.stride(1)
+        a.tree_tokens_dev = tree_tokens.data_ptr()
+        a.n_nodes_dev = K.ptr(_i32(n_nodes)) if n_nodes is not None else None
+        if retrieve is not None:
+            _i32(retrieve)
+            if retrieve.dim() == 2:
+                a.n_paths, a.depth, a.retrieve_batch_stride = retrieve.shape[0], retrieve.shape[1], 0
+            else:
+                assert retrieve.shape[0] == B
+                a.n_paths, a.depth, a.retrieve_batch_stride = retrieve.shape[1], retrieve.shape[2], retrieve.stride(0)
+            a.retrieve_dev = retrieve.data_ptr()
+            width = a.depth
+        else:
+            a.retrieve_dev, a.n_paths, a.depth, a.retrieve_batch_stride = None, 1, T, 0
+            width = T
+        a.n_paths_dev = K.ptr(_i32(n_paths)) if n_paths is not None else None
+        if self._kv_ptrs is not None and move_kv and retrieve is not None:
+            m = self._kv_meta
+            a.kv_ptrs_dev, a.n_kv, a.n_heads, a.row_bytes = self._kv_ptrs.data_ptr(), m["n_kv"], m["n_heads"], m["row_bytes"]
+            a.kv_batch_stride, a.kv_head_stride, a.kv_pos_stride = m["batch_stride"], m["head_stride"], m["pos_stride"]
+            a.move_kv = 1
+        else:
+            a.kv_ptrs_dev, a.n_kv, a.move_kv = None, 0, 0
+        a.cache_len_dev = K.ptr(_i32(cache_len)) if cache_len is not None else None
+        if out is None or out["tokens"].shape != (B, width):
+            mk = lambda *s: torch.empty(*s, dtype=torch.int32, device=logits.device)
+            out = dict(best=mk(B), accept_len=mk(B), next_token=mk(B), tokens=mk(B, width), indices=mk(B, width))
+        if want_argmax and "node_argmax" not in out:
+            out["node_argmax"] = torch.empty(B, T, dtype=torch.int32, device=logits.device)
+        a.out_best_dev, a.out_accept_len_dev, a.out_next_token_dev = \
+            out["best"].data_ptr(), out["accept_len"].data_ptr(), out["next_token"].data_ptr()
+        a.out_tokens_dev, a.out_indices_dev = out["tokens"].data_ptr(), out["indices"].data_ptr()
+        a.out_node_argmax_dev = out["node_argmax"].data_ptr() if want_argmax else None
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_verify_compact(self._h, C.byref(a), K.stream_ptr()), "samd_verify_compact")
+        return out
+
+    def close(self):
+        if self._h:
+            K.lib().samd_verify_destroy(self._h)
+            self._h = K.vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def launch_count() -> int:
+    return int(K.lib().samd_launch_count())

@@ -1,0 +1,393 @@
+"""GPU parity tests: the CUDA path (through the C ABI, libsamd_b200.so) against the golden
+fixtures produced by the reference's own classes, and against the CPU oracle on seeded
+inputs.  Bit-exact: all results are integers / token ids / byte moves."""
+import numpy as np
+import pytest
+import torch
+
+import samd_oracle as O
+from helpers import load, unragged, docs_of
+
+pytestmark = pytest.mark.gpu
+
+BIG = 1 << 20
+
+
+def _engine_mod():
+    from samd_b200 import engine, _cabi
+    return engine, _cabi
+
+
+def _dev_i32(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.int32).cuda()
+
+
+# --------------------------------------------------------------------------------------
+def test_dyn_sam_golden():
+    """DynSAM add_tokens / lookup / gen_draft (both flavours) on the reference's golden streams,
+    all seven streams as one batch with ragged per-step counts."""
+    E, K = _engine_mod()
+    z = load("dyn_sam.npz")
+    names = [str(n) for n in z["names"]]
+    B = len(names)
+    streams = [z[f"{n}/stream"] for n in names]
+    cuts = [z[f"{n}/cuts"].tolist() for n in names]
+    n_steps = max(len(c) for c in cuts)
+    dyn = E.DynSamBatch(B, 8192)
+    e16 = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=16, len_bias=0, len_threshold=-BIG)
+    e40 = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=40, len_bias=0, len_threshold=-BIG)
+    eso = E.DraftEngine(dyn, None, K.FLAVOUR_SAM_ONLY, n_predicts=40, len_bias=0, alpha=4.0)
+    so_ref = [unragged(z[f"{n}/draft_so_flat"], z[f"{n}/draft_so_offs"]) for n in names]
+    for s in range(n_steps):
+        lo = [0 if s == 0 else (cuts[r][s - 1] if s - 1 < len(cuts[r]) else None) for r in range(B)]
+        hi = [cuts[r][s] if s < len(cuts[r]) else None for r in range(B)]
+        width = max((h - l) for l, h in zip(lo, hi) if h is not None)
+        tok = np.zeros((B, width), dtype=np.int32)
+        cnt = np.zeros(B, dtype=np.int32)
+        start = np.zeros(B, dtype=np.int32)
+        for r in range(B):
+            if hi[r] is None:
+                continue
+            cnt[r] = hi[r] - lo[r]
+            tok[r, :cnt[r]] = streams[r][lo[r]:hi[r]]
+            start[r] = streams[r][hi[r]]
+        st = _dev_i32(start)
+        e16.step(_dev_i32(tok), _dev_i32(cnt), st)
+        e40.step(None, None, st)
+        eso.step(None, None, st)
+        torch.cuda.synchronize()
+        for r, n in enumerate(names):
+            if hi[r] is None:
+                continue
+            assert e16.index_dyn[r].item() == z[f"{n}/index"][s], (n, s)
+            assert e16.match_dyn[r].item() == z[f"{n}/match"][s], (n, s)
+            assert e16.out_type[r].item() == K.DRAFT_DYN_SEQ
+            assert e16.draft[r].tolist() == z[f"{n}/draft16"][s].tolist(), (n, s)
+            assert e40.draft[r].tolist() == z[f"{n}/draft40"][s].tolist(), (n, s)
+            k = eso.draft_len[r].item()
+            assert eso.draft[r, :k].tolist() == so_ref[r][s], (n, s)
+    for r, n in enumerate(names):
+        ex = dyn.export(r)
+        assert ex["overflow"] == 0
+        assert np.array_equal(ex["link"], z[f"{n}/link"])
+        assert np.array_equal(ex["length"], z[f"{n}/length"])
+        assert np.array_equal(ex["min_endpos"], z[f"{n}/min_endpos"])
+        assert [ex["cur_index"], ex["cur_length"]] == z[f"{n}/cursor"].tolist()
+        assert np.array_equal(ex["text"][1:], streams[r][:cuts[r][-1]])
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tiny", "small", "mid"])
+def test_static_sam_golden(name, tmp_path):
+    """StaticSAM build (state numbering, counts, top-k), transfer_tokens, lookup, gen_draft
+    (sequence + sam_only tree) against the reference's golden outputs; save/load round trip."""
+    E, K = _engine_mod()
+    z = load("static_sam.npz")
+    docs = docs_of(z, name)
+    st = E.StaticSamDevice.build(docs, int(z[f"{name}/eos"]), with_counts=True)
+    ex = st.export()
+    assert np.array_equal(ex["link"], z[f"{name}/link"])
+    assert np.array_equal(ex["length"], z[f"{name}/length"])
+    assert np.array_equal(ex["min_endpos"], z[f"{name}/min_endpos"])
+    assert np.array_equal(ex["cnt_endpos"], z[f"{name}/cnt_endpos"])
+    assert np.array_equal(ex["topk"][:, :, 0], z[f"{name}/topk_tok"])
+    assert np.array_equal(ex["topk"][:, :, 1], z[f"{name}/topk_idx"])
+    path = str(tmp_path / "sam.bin")
+    st.save(path)
+    st2 = E.StaticSamDevice.load(path)
+    assert (st2.n_states, st2.n_edges, st2.n_tokens) == (st.n_states, st.n_edges, st.n_tokens)
+
+    q = z[f"{name}/queries"]
+    steps = z[f"{name}/steps"]
+    nq = q.shape[0]
+    per_q = [[] for _ in range(nq)]
+    for k, (qi, p) in enumerate(steps):
+        per_q[qi].append((int(p), k))
+    trees = unragged(z[f"{name}/tree_tok_flat"], z[f"{name}/tree_offs"])
+    rets = unragged(z[f"{name}/tree_ret_flat"], z[f"{name}/tree_ret_offs"])
+    for sam in (st, st2):
+        dyn = E.DynSamBatch(nq, 256)
+        # len_bias = -BIG makes the static automaton win every selection -> static sequence draft
+        eng = E.DraftEngine(dyn, sam, K.FLAVOUR_SAMD, n_predicts=16, len_bias=-BIG, len_threshold=-BIG)
+        pos = [0] * nq
+        for s in range(max(len(x) for x in per_q)):
+            tok = np.zeros((nq, 8), dtype=np.int32)
+            cnt = np.zeros(nq, dtype=np.int32)
+            start = np.zeros(nq, dtype=np.int32)
+            live = []
+            for qi in range(nq):
+                if s >= len(per_q[qi]):
+                    continue
+                p, k = per_q[qi][s]
+                cnt[qi] = p - pos[qi]
+                tok[qi, :cnt[qi]] = q[qi, pos[qi]:p]
+                start[qi] = q[qi, p]
+                pos[qi] = p
+                live.append((qi, k))
+            st_dev = _dev_i32(start)
+            eng.step(_dev_i32(tok), _dev_i32(cnt), st_dev)
+            # tree draft with the fixture's budget rule: match = max(l - 2, 0), bias 0
+            m = torch.clamp(eng.match_static - 2, min=0)
+            n, mp = 40, 40
+            mk = lambda *sh: torch.zeros(*sh, dtype=torch.int32, device="cuda")
+            t_tok, t_par, t_dep, t_n, t_shape, t_ret = mk(nq, n), mk(nq, n), mk(nq, n), mk(nq), mk(nq, 2), mk(nq, mp, n)
+            K.check(K.lib().samd_static_tree_draft(
+                sam.handle, nq, None, eng.index_static.data_ptr(), m.data_ptr(), st_dev.data_ptr(), n, 4.0, 8, 0,
+                t_tok.data_ptr(), t_par.data_ptr(), t_dep.data_ptr(), t_n.data_ptr(), t_ret.data_ptr(), mp, n,
+                t_shape.data_ptr(), K.stream_ptr()))
+            torch.cuda.synchronize()
+            for qi, k in live:
+                assert eng.index_static[qi].item() == z[f"{name}/index"][k]
+                assert eng.match_static[qi].item() == z[f"{name}/match"][k]
+                assert eng.out_type[qi].item() == K.DRAFT_STATIC_SEQ
+                assert eng.draft[qi].tolist() == z[f"{name}/draft16"][k].tolist()
+                nn = t_n[qi].item()
+                assert t_tok[qi, :nn].tolist() == trees[k]
+                off = z[f"{name}/tree_offs"][k]
+                assert t_dep[qi, :nn].tolist() == z[f"{name}/tree_depth_flat"][off:off + nn].tolist()
+                shape = tuple(t_shape[qi].tolist())
+                assert shape == tuple(z[f"{name}/tree_ret_shape"][k])
+                assert t_ret[qi, :shape[0], :shape[1]].reshape(-1).tolist() == rets[k]
+
+
+# --------------------------------------------------------------------------------------
+def test_draft_selection_golden():
+    """DraftModel.lookup / update of both packages, six requests as one batch."""
+    E, K = _engine_mod()
+    z = load("draft_select.npz")
+    docs = docs_of(z)
+    st = E.StaticSamDevice.build(docs, 2, with_counts=True)
+    streams = z["streams"]
+    B = streams.shape[0]
+    cuts = unragged(z["cuts_flat"], z["cuts_offs"])
+    so_tok = unragged(z["so_tok_flat"], z["so_tok_offs"])
+    so_ret = unragged(z["so_ret_flat"], z["so_ret_offs"])
+    base = np.cumsum([0] + [len(c) for c in cuts])
+    dyn_a, dyn_b = E.DynSamBatch(B, 1024), E.DynSamBatch(B, 1024)
+    ea = E.DraftEngine(dyn_a, st, K.FLAVOUR_SAMD, n_predicts=16, len_bias=5, len_threshold=5)
+    eb = E.DraftEngine(dyn_b, st, K.FLAVOUR_SAM_ONLY, n_predicts=40, len_bias=5, alpha=4.0)
+    n_steps = max(len(c) for c in cuts)
+    for s in range(n_steps):
+        width = max(cuts[r][s] - (cuts[r][s - 1] if s else 0) for r in range(B) if s < len(cuts[r]))
+        tok = np.zeros((B, width), dtype=np.int32)
+        cnt = np.zeros(B, dtype=np.int32)
+        start = np.zeros(B, dtype=np.int32)
+        for r in range(B):
+            if s >= len(cuts[r]):
+                continue
+            lo, hi = (cuts[r][s - 1] if s else 0), cuts[r][s]
+            cnt[r] = hi - lo
+            tok[r, :cnt[r]] = streams[r][lo:hi]
+            start[r] = streams[r][hi]
+        t, c, sd = _dev_i32(tok), _dev_i32(cnt), _dev_i32(start)
+        ea.step(t, c, sd)
+        eb.step(t, c, sd)
+        eb.tree_draft(sd)
+        torch.cuda.synchronize()
+        for r in range(B):
+            if s >= len(cuts[r]):
+                continue
+            k = base[r] + s
+            src = z["samd_source"][k]
+            assert ea.out_type[r].item() == {0: K.DRAFT_DYN_SEQ, 1: K.DRAFT_STATIC_SEQ, 2: K.DRAFT_TREE_MODEL}[int(src)]
+            if src != 2:
+                assert ea.draft[r].tolist() == z["samd_seq"][k].tolist()
+            if z["so_type"][k] == 0:
+                assert eb.out_type[r].item() == K.DRAFT_DYN_SEQ
+                assert eb.draft[r, :eb.draft_len[r].item()].tolist() == so_tok[k]
+            else:
+                assert eb.out_type[r].item() == K.DRAFT_STATIC_TREE
+                nn = eb.tree_n[r].item()
+                assert eb.tree_tokens[r, :nn].tolist() == so_tok[k]
+                shp = eb.tree_shape[r].tolist()
+                assert eb.tree_retrieve[r, :shp[0], :shp[1]].reshape(-1).tolist() == so_ret[k]
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+def test_verify_golden(dt):
+    """gather + eval_posterior + update_state slices against the reference (ties, NaN, +-0, pads)."""
+    E, K = _engine_mod()
+    z = load("verify.npz")
+    bits = torch.from_numpy(z["bf16/logits_bits"]).view(torch.bfloat16)
+    lg = (bits if dt == "bf16" else bits.float().to(torch.float16)).cuda()
+    B, T, V = lg.shape
+    ri = _dev_i32(z["retrieve"])
+    ver = E.Verifier(B, T)
+    cache_len = torch.full((B,), 100, dtype=torch.int32, device="cuda")
+    out = ver.verify(lg, _dev_i32(z["tree_tokens"]), ri, cache_len=cache_len, want_argmax=True)
+    # second launch on the same scratch must give the same answer (self re-arming counters)
+    out2 = ver.verify(lg, _dev_i32(z["tree_tokens"]), ri, cache_len=None, want_argmax=True)
+    torch.cuda.synchronize()
+    for o in (out, out2):
+        assert np.array_equal(o["node_argmax"].cpu().numpy(), z[f"{dt}/node_argmax"])
+        assert np.array_equal(o["best"].cpu().numpy(), z[f"{dt}/best"])
+        assert np.array_equal(o["accept_len"].cpu().numpy(), z[f"{dt}/accept_len"])
+        assert np.array_equal(o["next_token"].cpu().numpy(), z[f"{dt}/next_token"])
+        tk, ix = o["tokens"].cpu().numpy(), o["indices"].cpu().numpy()
+        for b in range(B):
+            n = z[f"{dt}/accept_len"][b]
+            assert tk[b, :n].tolist() == z[f"{dt}/tokens"][b][:n].tolist()
+            assert ix[b, :n].tolist() == z[f"{dt}/indices"][b][:n].tolist()
+    assert np.array_equal(cache_len.cpu().numpy(), 100 + z[f"{dt}/accept_len"])
+
+
+def test_verify_sequence_golden():
+    E, K = _engine_mod()
+    z = load("verify.npz")
+    lg = torch.from_numpy(z["seq/logits_bits"]).view(torch.bfloat16).cuda()
+    B, T, V = lg.shape
+    ver = E.Verifier(B, T)
+    out = ver.verify(lg, _dev_i32(z["seq/tokens"]), None)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["accept_len"].cpu().numpy(), z["seq/accept_len"])
+    assert np.array_equal(out["next_token"].cpu().numpy(), z["seq/next_token"])
+    assert (out["best"] == 0).all()
+
+
+def test_kv_compaction_golden():
+    """select_indices through the fused kernel: the fixture's 16 cases as one batch of 16 requests."""
+    E, K = _engine_mod()
+    z = load("verify.npz")
+    init = torch.from_numpy(z["kv/init_bits"]).view(torch.bfloat16)            # [2L, 1, H, ML, DH]
+    cases = z["kv/cases"]
+    n_case = len(cases)
+    bits = torch.from_numpy(z["bf16/logits_bits"]).view(torch.bfloat16)
+    sel = [int(b) for b, _ in cases]
+    lg = bits[sel].contiguous().cuda()
+    tok = _dev_i32(z["tree_tokens"][sel])
+    kv = [init[i].repeat(n_case, 1, 1, 1).contiguous().cuda() for i in range(init.shape[0])]
+    cache_len = _dev_i32(np.array([s for _, s in cases]))
+    ver = E.Verifier(n_case, lg.shape[1])
+    ver.bind_kv(kv)
+    out = ver.verify(lg, tok, _dev_i32(z["retrieve"]), cache_len=cache_len, move_kv=True)
+    torch.cuda.synchronize()
+    after = z["kv/after_bits"]                                                 # [case, 2L, 1, H, ML, DH]
+    for c in range(n_case):
+        got = torch.stack([t[c] for t in kv]).view(torch.int16).cpu().numpy()
+        assert np.array_equal(got, after[c][:, 0]), c
+        assert cache_len[c].item() == cases[c][1] + z["bf16/accept_len"][sel[c]]
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_decode_loop_golden(name):
+    """prefill update -> {lookup -> fake-LM logits -> fused verify -> update}* entirely through
+    the C ABI; token stream and accept lengths must equal the reference's loop."""
+    E, K = _engine_mod()
+    z = load("decode_loop.npz")
+    full = z[f"{name}/full"]
+    plen = int(z[f"{name}/plen"])
+    vocab = int(z["vocab"])
+    ref_tokens = z[f"{name}/new_tokens"].tolist()
+    ref_acc = z[f"{name}/accepts"].tolist()
+    dyn = E.DynSamBatch(1, 4096)
+    eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAM_ONLY, n_predicts=40, len_bias=5, alpha=4.0)
+    ver = E.Verifier(1, 40)
+    eng.step(_dev_i32(full[None, :plen]), None, None)
+    pos = plen
+    start = _dev_i32([full[pos]])
+    out_tokens, accepts = [], []
+    for _ in range(len(ref_acc)):
+        eng.step(None, None, start)
+        n = eng.draft_len[0].item()
+        logits = torch.zeros(1, 40, vocab, dtype=torch.bfloat16, device="cuda")
+        idx = torch.as_tensor(full[pos + 1:pos + 1 + n].astype(np.int64)).cuda()
+        logits[0, torch.arange(n, device="cuda"), idx] = 1.0
+        res = ver.verify(logits, eng.draft, None, n_nodes=eng.draft_len)
+        al = res["accept_len"][0].item()
+        acc = res["tokens"][0, :al].tolist()
+        eng.step(res["tokens"], res["accept_len"], None)          # device-to-device, no host round trip needed
+        start = res["next_token"]
+        out_tokens.extend(acc)
+        accepts.append(al)
+        pos += al
+    assert accepts == ref_acc
+    assert out_tokens[:len(ref_tokens)] == ref_tokens
+
+
+# --------------------------------------------------------------------------------------
+def test_dyn_batch_vs_oracle_8k():
+    """Config-2 shape at reduced batch: 32 requests x 8192-token prompts, 24 decode steps of 1-8
+    appended tokens, both flavours, against the CPU oracle (clone-heavy and clone-light streams)."""
+    E, K = _engine_mod()
+    from samd_b200 import synth
+    B, N, steps = 32, 8192, 24
+    total = N + 8 * steps + 1
+    streams = [synth.copy_mix(total, 32000, 2000 + r, uniform_fresh=(r % 2 == 1)) for r in range(B)]
+    rng = np.random.default_rng(9)
+    dyn = E.DynSamBatch(B, N + 8 * steps + 8)
+    e16 = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=16, len_bias=5, len_threshold=5)
+    eso = E.DraftEngine(dyn, None, K.FLAVOUR_SAM_ONLY, n_predicts=40, len_bias=5, alpha=4.0)
+    oracles = [O.Automaton() for _ in range(B)]
+    prompt = np.stack([s[:N] for s in streams]).astype(np.int32)
+    e16.step(_dev_i32(prompt), None, None)
+    for r in range(B):
+        oracles[r].extend(streams[r][:N])
+    pos = [N] * B
+    for s in range(steps):
+        cnt = rng.integers(1, 9, size=B).astype(np.int32)
+        tok = np.zeros((B, 8), dtype=np.int32)
+        start = np.zeros(B, dtype=np.int32)
+        for r in range(B):
+            tok[r, :cnt[r]] = streams[r][pos[r]:pos[r] + cnt[r]]
+            oracles[r].extend(streams[r][pos[r]:pos[r] + cnt[r]])
+            pos[r] += cnt[r]
+            start[r] = streams[r][pos[r]]
+        sd = _dev_i32(start)
+        e16.step(_dev_i32(tok), _dev_i32(cnt), sd)
+        eso.step(None, None, sd)
+        torch.cuda.synchronize()
+        for r in range(B):
+            typ, seq, info = O.select_samd(oracles[r], None, int(start[r]), 16, 5, 5)
+            assert e16.match_dyn[r].item() == info["match_dyn"] and e16.index_dyn[r].item() == info["index_dyn"]
+            if typ == "sequence":
+                assert e16.out_type[r].item() == K.DRAFT_DYN_SEQ
+                assert e16.draft[r].tolist() == seq
+            else:
+                assert e16.out_type[r].item() == K.DRAFT_TREE_MODEL
+            want = O.dyn_draft_sam_only(oracles[r], info["index_dyn"], info["match_dyn"], int(start[r]), 40, 4.0)
+            assert eso.draft[r, :eso.draft_len[r].item()].tolist() == want
+    for r in (0, 1, B - 1):
+        ex = dyn.export(r, with_text=False)
+        assert ex["n_states"] == oracles[r].n_states and ex["n_edges"] == oracles[r].n_edges
+        assert np.array_equal(ex["link"], np.array(oracles[r].link))
+        assert np.array_equal(ex["min_endpos"], np.array(oracles[r].first_end))
+
+
+def test_verify_full_size_properties():
+    """Config-4 shape (B=64, T=61, V=32000, bf16): node argmax equals torch.argmax, outputs equal
+    the oracle walk, and the compacted KV rows equal an index_select reference."""
+    E, K = _engine_mod()
+    from samd_b200 import synth
+    B, T, V = 64, 61, 32000
+    ri_np = synth.tree_retrieve_indices(synth.token_recycle_tree())
+    rng = np.random.default_rng(4000)
+    tree_tokens = rng.integers(3, V, size=(B, T)).astype(np.int32)
+    logits, _ = synth.planted_logits(B, T, V, tree_tokens, ri_np, seed=4000, device="cuda")
+    L, H, ML, DH = 4, 8, 256, 128
+    kv = [torch.randn(B, H, ML, DH, device="cuda").to(torch.bfloat16) for _ in range(2 * L)]
+    kv_ref = [t.clone() for t in kv]
+    cache_len = torch.randint(16, 150, (B,), dtype=torch.int32, device="cuda")
+    start = cache_len.clone()
+    ver = E.Verifier(B, T)
+    ver.bind_kv(kv)
+    out = ver.verify(logits, _dev_i32(tree_tokens), _dev_i32(ri_np), cache_len=cache_len, want_argmax=True)
+    torch.cuda.synchronize()
+    am = torch.argmax(logits, dim=-1)
+    assert torch.equal(out["node_argmax"].long(), am)
+    am_np = am.cpu().numpy()
+    for b in range(B):
+        r = O.verify_greedy(am_np[b], tree_tokens[b], ri_np.astype(np.int64))
+        al = r["accept_len"]
+        assert out["best"][b].item() == r["best"] and out["accept_len"][b].item() == al
+        assert out["next_token"][b].item() == r["next_token"]
+        assert out["tokens"][b, :al].tolist() == r["tokens"].tolist()
+        assert out["indices"][b, :al].tolist() == r["indices"].tolist()
+        s0 = start[b].item()
+        src = torch.as_tensor(s0 + r["indices"], device="cuda")
+        for t, t_ref in zip(kv, kv_ref):
+            want = t_ref[b].clone()
+            want[:, s0:s0 + al] = t_ref[b].index_select(1, src)
+            assert torch.equal(t[b], want)
+        assert cache_len[b].item() == s0 + al
