@@ -63,14 +63,31 @@ int samd_dyn_destroy(samd_dyn_t h);
 int samd_dyn_reset(samd_dyn_t h, const uint8_t *mask_dev, void *stream);
 /* device bytes held by the arenas */
 int64_t samd_dyn_bytes(samd_dyn_t h);
+/* Snapshot / restore: copy every arena of `src` into `dst` (same n_requests, max_tokens). */
+int samd_dyn_copy(samd_dyn_t dst, samd_dyn_t src, void *stream);
+/* Capacity growth: a new batch with max_tokens = new_max_tokens holding the same automata (state
+ * numbering, cursors and histories preserved; the edge tables are re-hashed).  Synchronises; the
+ * old handle stays valid and must still be destroyed by the caller. */
+int samd_dyn_grow(samd_dyn_t old_handle, int new_max_tokens, samd_dyn_t *out);
+/* Sums over requests (synchronises): out[8] = {n_states, tokens, n_edges, n_clones, transition
+ * probes spent in add_tokens, probes spent in lookups, overflowed requests, 0}. */
+int samd_dyn_stats(samd_dyn_t h, int64_t *out_host);
 /* Copy one request's automaton to the host (synchronises): meta[8] = {n_states, last,
  * max_length, cur_index, cur_length, n_edges, overflow, n_clones}; link/length/min_endpos
  * arrays of n_states entries (pass NULL to skip) and the token history text[0..max_length]. */
 int samd_dyn_export(samd_dyn_t h, int request, int32_t *meta_host, int32_t *link_host, int32_t *length_host,
                     int32_t *endpos_host, int32_t *text_host, int64_t capacity);
 
+/* Edges of one request as (state, token, target) triples, per state oldest-first (synchronises). */
+int samd_dyn_export_edges(samd_dyn_t h, int request, int32_t *edges_host, int64_t capacity);
+/* DynSAM.gen_draft for arbitrary state indices (samd/sam/dyn_sam.py:107-113 with to_anc;
+ * samd_sam_only/sam/dyn_sam.py:116-121 when flavour = SAM_ONLY, which also needs match_dev). */
+int samd_dyn_gen_draft(samd_dyn_t h, const int32_t *index_dev, const int32_t *match_dev, const int32_t *start_tok_dev,
+                       int32_t flavour, int32_t n_predicts, double alpha, int32_t *out_draft_dev, int32_t draft_stride,
+                       int32_t *out_len_dev, void *stream);
+
 /* ----------------------------------------------------------------------------------------
- * Static suffix automaton over a corpus                (samd/sam/static_sam.py:8-137,
+ * Static suffix automaton over a corpus               (samd/sam/static_sam.py:8-137,
  *                                                       samd_sam_only/sam/static_sam.py:22-215)
  * -------------------------------------------------------------------------------------- */
 /* StaticSAM.build (static_sam.py:38-46; build_sam, samd/sam/utils.py:10-18): host-side online
@@ -91,6 +108,20 @@ int samd_static_info(samd_static_t h, int64_t *info_host);
  * as (token,target) pairs, -1 padded.  NULL skips an array. */
 int samd_static_export(samd_static_t h, int32_t *link_host, int32_t *length_host, int32_t *endpos_host,
                        int32_t *count_host, int32_t *topk_host);
+/* Converter for automata built elsewhere - the object graph of a reference pickle
+ * (load_sam, samd/sam/utils.py:24-37): state arrays [n_states] (endpos_host = min_endpos for the
+ * samd flavour, count_host = cnt_endpos for samd_sam_only; either may be NULL) and the edges as
+ * (state, token, target) triples, per state in dict insertion order.  text_host[0..n_tokens] is the
+ * 1-based token array (NULL for samd_sam_only, which keeps none).  Host only; call
+ * samd_static_upload afterwards. */
+int samd_static_from_arrays(int64_t n_states, const int32_t *link_host, const int32_t *length_host,
+                            const int32_t *endpos_host, const int32_t *count_host, int64_t n_edges,
+                            const int32_t *edges_host, int64_t n_tokens, const int32_t *text_host, samd_static_t *out);
+/* The inverse: edges [n_edges][3] per state oldest-first, text [n_tokens+1].  NULL skips. */
+int samd_static_export_edges(samd_static_t h, int32_t *edges_host, int32_t *text_host);
+/* StaticSAM.gen_draft (samd/sam/static_sam.py:119-125) for arbitrary state indices. */
+int samd_static_gen_draft(samd_static_t h, const int32_t *index_dev, const int32_t *start_tok_dev, int n_requests,
+                          int32_t n_predicts, int32_t *out_draft_dev, int32_t draft_stride, void *stream);
 /* dump_sam / load_sam (samd/sam/utils.py:20-37) in a flat, mmap-able format. */
 int samd_static_save(samd_static_t h, const char *path);
 int samd_static_load(const char *path, samd_static_t *out);
@@ -133,6 +164,14 @@ typedef struct samd_step_args {
 } samd_step_args;
 
 int samd_step(const samd_step_args *args, void *stream);
+
+/* Cursor-only walks.  samd_static_walk = StaticSAM.transfer_tokens (static_sam.py:102-104) when
+ * tokens_dev != NULL, then StaticSAM.lookup (:106-109) when peek_tok_dev != NULL (non-mutating).
+ * samd_dyn_transfer = DynSAM.transfer_tokens (dyn_sam.py:90-92): moves the cursor, appends nothing. */
+int samd_static_walk(samd_static_t h, int32_t *static_cursor_dev, const int32_t *tokens_dev, int32_t token_stride,
+                     const int32_t *counts_dev, const int32_t *peek_tok_dev, int n_requests, int32_t *out_index_dev,
+                     int32_t *out_len_dev, void *stream);
+int samd_dyn_transfer(samd_dyn_t h, const int32_t *tokens_dev, int32_t token_stride, const int32_t *counts_dev, void *stream);
 
 /* sam_only static tree drafter (samd_sam_only/sam/static_sam.py:148-215): best-first search
  * over occurrence-count ratios with CPython-heapq tie order, for the requests whose
@@ -198,6 +237,12 @@ typedef struct samd_verify_args {
 int samd_verify_compact(samd_verify_t h, const samd_verify_args *args, void *stream);
 /* tuning hook: logits elements per phase-1 work item (0 = default) */
 void samd_verify_set_chunk(int elements);
+/* Stand-alone SamdStaticCache.select_indices (samd/cache.py:118-133): rows cache_len+indices[b][j] ->
+ * cache_len+j for j < accept_len[b] in every KV tensor, then cache_len[b] += accept_len[b].
+ * indices_dev NULL = sequence draft (only the length bump, cache.py:123-126,133). */
+int samd_kv_compact(void *const *kv_ptrs_dev, int32_t n_kv, int32_t n_heads, int32_t row_bytes, int64_t kv_batch_stride,
+                    int64_t kv_head_stride, int64_t kv_pos_stride, const int32_t *indices_dev, int32_t depth,
+                    const int32_t *accept_len_dev, int32_t *cache_len_dev, int32_t batch, void *stream);
 /* number of kernel launches the library has issued (for bench.py's gpu_launches) */
 int64_t samd_launch_count(void);
 

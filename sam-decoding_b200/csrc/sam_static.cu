@@ -226,6 +226,78 @@ extern "C" int samd_static_build(const int32_t *docs, const int64_t *offs, int64
     return 0;
 }
 
+// Converter for automata built elsewhere (reference pickles, samd/sam/utils.py:24-37): explicit
+// state arrays plus edges as (state, token, target) triples, per state in dict insertion order.
+extern "C" int samd_static_from_arrays(int64_t n_states, const int32_t *link, const int32_t *length, const int32_t *endpos,
+                                       const int32_t *count, int64_t n_edges, const int32_t *edges, int64_t n_tokens,
+                                       const int32_t *text, samd_static_t *out) {
+    SAMD_REQUIRE(n_states > 0 && link && length && n_edges >= 0 && (n_edges == 0 || edges) && out,
+                 "samd_static_from_arrays: bad arguments");
+    SAMD_REQUIRE(endpos || count, "samd_static_from_arrays: need min_endpos (samd) or cnt_endpos (samd_sam_only)");
+    samd_static_s *h = new samd_static_s();
+    memset(h, 0, sizeof(*h));
+    const uint64_t h_cap = std::max<uint64_t>(samd_table_slots((uint64_t)n_tokens), samd_next_pow2(2 * (uint64_t)n_edges + 64));
+    HostSam b;
+    b.h_cap = h_cap;
+    b.bmask = (uint32_t)(h_cap / SAMD_BUCKET - 1);
+    b.states = (int4 *)malloc((size_t)n_states * sizeof(int4));
+    b.slots = (uint4 *)malloc(h_cap * sizeof(uint4));
+    b.text = (int32_t *)calloc((size_t)n_tokens + 1, sizeof(int32_t));
+    SAMD_REQUIRE(b.states && b.slots && b.text, "samd_static_from_arrays: host allocation failed");
+    memset(b.slots, 0xFF, h_cap * sizeof(uint4));
+    for (int64_t v = 0; v < n_states; ++v) b.states[v] = make_int4(link[v], length[v], endpos ? endpos[v] : 0, (int)SAMD_NIL);
+    b.text[0] = -1;
+    if (text)
+        for (int64_t i = 1; i <= n_tokens; ++i) b.text[i] = text[i];
+    for (int64_t e = 0; e < n_edges; ++e) b.add_edge(edges[3 * e], edges[3 * e + 1], edges[3 * e + 2]);
+    h->h_states = b.states;
+    h->h_slots = b.slots;
+    h->h_text = b.text;
+    h->n_edges = n_edges;
+    h->with_counts = count != nullptr;
+    h->dev.n_states = n_states;
+    h->dev.n_slots = (int64_t)h_cap;
+    h->dev.n_tokens = n_tokens;
+    h->dev.bmask = b.bmask;
+    if (count) {
+        h->h_occ = (int32_t *)malloc((size_t)n_states * sizeof(int32_t));
+        memcpy(h->h_occ, count, (size_t)n_states * sizeof(int32_t));
+        h->h_topk = (int2 *)malloc((size_t)n_states * 8 * sizeof(int2));
+        std::vector<int2> ed;
+        for (int64_t v = 0; v < n_states; ++v) {
+            ed.clear();
+            for (uint32_t e = (uint32_t)h->h_states[v].w; e != SAMD_NIL; e = h->h_slots[e].w)
+                ed.push_back(make_int2((int)h->h_slots[e].y, (int)h->h_slots[e].z));
+            std::reverse(ed.begin(), ed.end());
+            std::stable_sort(ed.begin(), ed.end(), [&](const int2 &x, const int2 &y) { return h->h_occ[x.y] > h->h_occ[y.y]; });
+            for (int j = 0; j < 8; ++j) h->h_topk[(size_t)v * 8 + j] = j < (int)ed.size() ? ed[(size_t)j] : make_int2(-1, -1);
+        }
+    }
+    *out = h;
+    return 0;
+}
+
+// edges as (state, token, target) triples, per state oldest-first; text[0..n_tokens]
+extern "C" int samd_static_export_edges(samd_static_t h, int32_t *edges_host, int32_t *text_host) {
+    SAMD_REQUIRE(h && h->h_states, "samd_static_export_edges: no host mirror");
+    if (edges_host) {
+        int64_t k = 0;
+        for (int64_t v = 0; v < h->dev.n_states; ++v) {
+            const int64_t first = k;
+            for (uint32_t e = (uint32_t)h->h_states[v].w; e != SAMD_NIL; e = h->h_slots[e].w) {
+                edges_host[3 * k] = (int32_t)v;
+                edges_host[3 * k + 1] = (int32_t)h->h_slots[e].y;
+                edges_host[3 * k + 2] = (int32_t)h->h_slots[e].z;
+                k++;
+            }
+            for (int64_t i = first, j = k - 1; i < j; ++i, --j)
+                for (int c = 0; c < 3; ++c) std::swap(edges_host[3 * i + c], edges_host[3 * j + c]);
+        }
+    }
+    if (text_host) memcpy(text_host, h->h_text, (size_t)(h->dev.n_tokens + 1) * sizeof(int32_t));
+    return 0;
+}
+
 extern "C" int samd_static_destroy(samd_static_t h) {
     free_handle(h);
     return 0;

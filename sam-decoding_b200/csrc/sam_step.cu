@@ -3,6 +3,10 @@
 #include "samd_common.cuh"
 #include "../../include/samd_b200.h"
 
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
 // ---------------------------------------------------------------------------------------
 // arena management
 // ---------------------------------------------------------------------------------------
@@ -23,8 +27,7 @@ __global__ void dyn_reset_kernel(DynArena a, const uint8_t *mask) {
         m[META_CUR] = 0;
         m[META_CURLEN] = 0;
         m[META_NEDGES] = 0;
-        m[META_OVERFLOW] = 0;
-        m[META_NCLONES] = 0;
+        for (int i = META_OVERFLOW; i < META_WORDS; ++i) m[i] = 0;
     }
 }
 
@@ -65,6 +68,41 @@ extern "C" int samd_dyn_destroy(samd_dyn_t h) {
 
 extern "C" int64_t samd_dyn_bytes(samd_dyn_t h) { return h ? h->bytes : 0; }
 
+extern "C" int samd_dyn_copy(samd_dyn_t dst, samd_dyn_t src, void *stream) {
+    SAMD_REQUIRE(dst && src && dst->a.n_requests == src->a.n_requests && dst->a.max_tokens == src->a.max_tokens,
+                 "samd_dyn_copy: handles must have the same shape");
+    const DynArena &s = src->a;
+    const DynArena &d = dst->a;
+    cudaStream_t st = (cudaStream_t)stream;
+    SAMD_CUDA(cudaMemcpyAsync(d.states, s.states, (size_t)s.n_requests * s.s_cap * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+    SAMD_CUDA(cudaMemcpyAsync(d.slots, s.slots, (size_t)s.n_requests * s.h_cap * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
+    SAMD_CUDA(cudaMemcpyAsync(d.text, s.text, (size_t)s.n_requests * s.t_cap * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    SAMD_CUDA(cudaMemcpyAsync(d.meta, s.meta, (size_t)s.n_requests * META_WORDS * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int samd_dyn_stats(samd_dyn_t h, int64_t *out) {
+    // out[8] = sums over requests of {n_states, max_length, n_edges, n_clones, extend probes, lookup probes, overflow, 0}
+    SAMD_REQUIRE(h && out, "samd_dyn_stats: bad arguments");
+    SAMD_CUDA(cudaDeviceSynchronize());
+    const size_t n = (size_t)h->a.n_requests * META_WORDS;
+    int32_t *m = (int32_t *)malloc(n * sizeof(int32_t));
+    SAMD_CUDA(cudaMemcpy(m, h->a.meta, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    for (int r = 0; r < h->a.n_requests; ++r) {
+        const int32_t *q = m + (size_t)r * META_WORDS;
+        out[0] += q[META_NSTATES];
+        out[1] += q[META_N];
+        out[2] += q[META_NEDGES];
+        out[3] += q[META_NCLONES];
+        out[4] += q[META_HOPS];
+        out[5] += q[META_PROBES];
+        out[6] += q[META_OVERFLOW];
+    }
+    free(m);
+    return 0;
+}
+
 extern "C" int samd_dyn_reset(samd_dyn_t h, const uint8_t *mask_dev, void *stream) {
     SAMD_REQUIRE(h, "samd_dyn_reset: null handle");
     dyn_reset_kernel<<<h->a.n_requests, 256, 0, (cudaStream_t)stream>>>(h->a, mask_dev);
@@ -80,7 +118,7 @@ extern "C" int samd_dyn_export(samd_dyn_t h, int request, int32_t *meta_host, in
     int32_t meta[META_WORDS];
     SAMD_CUDA(cudaMemcpy(meta, h->a.meta + (size_t)request * META_WORDS, sizeof(meta), cudaMemcpyDeviceToHost));
     if (meta_host)
-        for (int i = 0; i < META_WORDS; ++i) meta_host[i] = meta[i];
+        for (int i = 0; i < 8; ++i) meta_host[i] = meta[i];
     int ns = meta[META_NSTATES];
     if (link_host || length_host || endpos_host) {
         SAMD_REQUIRE(capacity >= ns, "samd_dyn_export: capacity too small");
@@ -106,7 +144,7 @@ extern "C" int samd_dyn_export(samd_dyn_t h, int request, int32_t *meta_host, in
 // online append with clone-on-split (dyn_sam.py:41-67); registers are warp-uniform
 // ---------------------------------------------------------------------------------------
 struct DynRegs {
-    int n_states, last, n, cur, cur_len, n_edges, n_clones;
+    int n_states, last, n, cur, cur_len, n_edges, n_clones, hops;
 };
 
 __device__ __forceinline__ void dyn_append(int4 *states, uint4 *slots, int32_t *text, uint32_t bmask, DynRegs &g, int tok,
@@ -145,6 +183,7 @@ __device__ __forceinline__ void dyn_append(int4 *states, uint4 *slots, int32_t *
             uint32_t e = (uint32_t)rq.w;
             while (e != SAMD_NIL) {
                 const uint4 se = slots[e];
+                if (lane == 0 && se.w != SAMD_NIL) asm volatile("prefetch.global.L1 [%0];" ::"l"(slots + se.w));
                 Probe pi = warp_probe<false, false>(slots, bmask, states, (uint32_t)clone, se.y, lane);
                 if (lane == 0) slots[pi.slot] = make_uint4((uint32_t)clone, se.y, se.z, head_c);
                 head_c = pi.slot;
@@ -201,6 +240,7 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
     DynRegs g;
     {
         int m = (lane < META_WORDS) ? meta[lane] : 0;
+        g.hops = __shfl_sync(SAMD_FULL, m, META_HOPS);
         g.n_states = __shfl_sync(SAMD_FULL, m, META_NSTATES);
         g.last = __shfl_sync(SAMD_FULL, m, META_LAST);
         g.n = __shfl_sync(SAMD_FULL, m, META_N);
@@ -209,7 +249,7 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
         g.n_edges = __shfl_sync(SAMD_FULL, m, META_NEDGES);
         g.n_clones = __shfl_sync(SAMD_FULL, m, META_NCLONES);
     }
-    int s_idx = 0, s_len = 0;
+    int s_idx = 0, s_len = 0, s_hops = 0;
     if (P.has_static) {
         s_idx = P.static_cursor[2 * r];
         s_len = P.static_cursor[2 * r + 1];
@@ -220,20 +260,36 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
         const int k = P.counts ? P.counts[r] : P.token_stride;
         const int32_t *tk = P.tokens + (size_t)r * P.token_stride;
         bool overflow = false;
+        const int peek = P.start_tok ? P.start_tok[r] : -1;
         for (int i = 0; i < k; i += 32) {
             const int mine = (i + lane < k) ? tk[i + lane] : 0;     // coalesced token fetch
             const int lim = min(32, k - i);
+            if (i == 0) {                                           // first token: warm its cursor / tail probes
+                const int t0 = __shfl_sync(SAMD_FULL, mine, 0);
+                prefetch_probe(slots, bmask, states, (uint32_t)g.cur, (uint32_t)t0, lane);
+                prefetch_probe(slots, bmask, nullptr, (uint32_t)g.last, (uint32_t)t0, lane);
+                if (P.has_static) prefetch_probe(P.st.slots, P.st.bmask, P.st.states, (uint32_t)s_idx, (uint32_t)t0, lane);
+            }
             for (int j = 0; j < lim; ++j) {
                 const int tok = __shfl_sync(SAMD_FULL, mine, j);
+                const int nxt_in = __shfl_sync(SAMD_FULL, mine, (j + 1) & 31);
+                const int nxt = (j + 1 < lim) ? nxt_in : ((i + lim >= k) ? peek : -1);
                 if (g.n >= P.dyn.max_tokens) {
                     overflow = true;
                     break;
                 }
-                // add_tokens: match first, then append (dyn_sam.py:84-88)
-                warp_transfer<false>(slots, bmask, states, g.cur, g.cur_len, tok, lane);
+                // add_tokens: match first, then append (dyn_sam.py:84-88); StaticSAM.transfer_tokens
+                // (static_sam.py:102-104) walks an independent structure, so it goes first too
+                warp_transfer<false>(slots, bmask, states, g.cur, g.cur_len, tok, lane, g.hops);
+                if (P.has_static) warp_transfer<true>(P.st.slots, P.st.bmask, P.st.states, s_idx, s_len, tok, lane, s_hops);
+                if (nxt >= 0) {
+                    // the next token's probes are known now: (cursor, nxt), (new tail = state about to be
+                    // created, nxt) and the static cursor's - fetch them while this token is appended
+                    prefetch_probe(slots, bmask, states, (uint32_t)g.cur, (uint32_t)nxt, lane);
+                    prefetch_probe(slots, bmask, nullptr, (uint32_t)g.n_states, (uint32_t)nxt, lane);
+                    if (P.has_static) prefetch_probe(P.st.slots, P.st.bmask, P.st.states, (uint32_t)s_idx, (uint32_t)nxt, lane);
+                }
                 dyn_append(states, slots, text, bmask, g, tok, lane);
-                // StaticSAM.transfer_tokens (static_sam.py:102-104)
-                if (P.has_static) warp_transfer<true>(P.st.slots, P.st.bmask, P.st.states, s_idx, s_len, tok, lane);
             }
             if (overflow) break;
         }
@@ -245,6 +301,7 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
             meta[META_CURLEN] = g.cur_len;
             meta[META_NEDGES] = g.n_edges;
             meta[META_NCLONES] = g.n_clones;
+            meta[META_HOPS] = g.hops;
             if (overflow) meta[META_OVERFLOW] = 1;
             if (P.has_static) {
                 P.static_cursor[2 * r] = s_idx;
@@ -257,12 +314,13 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
     // ---- phase 2: DraftModel.lookup (draft.py:52-63 / samd_sam_only/draft.py:49-59) -------
     const int tok = P.start_tok[r];
     int d_idx = g.cur, d_len = g.cur_len;
-    warp_transfer<false>(slots, bmask, states, d_idx, d_len, tok, lane);
+    int q_hops = 0;
+    warp_transfer<false>(slots, bmask, states, d_idx, d_len, tok, lane, q_hops);
     int t_idx = 0, t_len = 0;
     if (P.has_static) {
         t_idx = s_idx;
         t_len = s_len;
-        warp_transfer<true>(P.st.slots, P.st.bmask, P.st.states, t_idx, t_len, tok, lane);
+        warp_transfer<true>(P.st.slots, P.st.bmask, P.st.states, t_idx, t_len, tok, lane, s_hops);
     }
     const int t_biased = t_len - P.len_bias;
     int type, n_out, endpos = 0, text_n = 0;
@@ -330,6 +388,7 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
         if (P.out_index_dyn) P.out_index_dyn[r] = d_idx;
         if (P.out_index_static) P.out_index_static[r] = t_idx;
         if (P.out_draft_len) P.out_draft_len[r] = n_out;
+        meta[META_PROBES] += q_hops;          // probes spent in lookups (the extend-side count is META_HOPS)
     }
 }
 
@@ -378,7 +437,8 @@ __global__ void __launch_bounds__(32) static_keys_kernel(StaticDev st, const int
     const int lane = threadIdx.x;
     if (r >= n) return;
     int idx = cursor[2 * r], len = cursor[2 * r + 1];
-    warp_transfer<true>(st.slots, st.bmask, st.states, idx, len, start_tok[r], lane);
+    int hops = 0;
+    warp_transfer<true>(st.slots, st.bmask, st.states, idx, len, start_tok[r], lane, hops);
     if (lane == 0) {
         long long key = 0;
         if (len > 0) {
@@ -435,5 +495,240 @@ extern "C" int samd_draft_from_keys(const int64_t *keys_dev, const int32_t *corp
         out_match_dev, out_draft_dev, draft_stride);
     samd_count_launch();
     SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// stand-alone gen_draft entry points (the drop-in DynSAM.gen_draft / StaticSAM.gen_draft may be
+// called with any state index, not only the one the last lookup returned)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) dyn_gen_draft_kernel(DynArena a, const int32_t *index, const int32_t *match,
+                                                           const int32_t *start_tok, int flavour, int n_predicts, double alpha,
+                                                           int32_t *out_draft, int stride, int32_t *out_len) {
+    const int r = blockIdx.x, lane = threadIdx.x;
+    if (r >= a.n_requests) return;
+    const int4 *states = a.states + (size_t)r * a.s_cap;
+    const int32_t *text = a.text + (size_t)r * a.t_cap;
+    const int n = a.meta[(size_t)r * META_WORDS + META_N];
+    int idx = index[r];
+    int4 rec = states[idx];
+    int n_out;
+    if (flavour == SAMD_FLAVOUR_SAMD) {
+        if (idx != 0) {                                      // to_anc (dyn_sam.py:99-105)
+            while (rec.x != 0 && n_predicts > n - rec.z) {
+                idx = rec.x;
+                rec = states[idx];
+            }
+        }
+        n_out = n_predicts;
+    } else {
+        const int budget = min(n_predicts, 1 + (int)((double)match[r] * alpha));
+        n_out = 1 + max(0, min(rec.z + budget, n + 1) - (rec.z + 1));
+    }
+    for (int j = lane; j < stride; j += 32) {
+        int v = 0;
+        if (j < n_out) v = j == 0 ? start_tok[r] : (rec.z + j <= n ? text[rec.z + j] : 0);
+        out_draft[(size_t)r * stride + j] = v;
+    }
+    if (lane == 0 && out_len) out_len[r] = n_out;
+}
+
+extern "C" int samd_dyn_gen_draft(samd_dyn_t h, const int32_t *index_dev, const int32_t *match_dev, const int32_t *start_tok_dev,
+                                  int32_t flavour, int32_t n_predicts, double alpha, int32_t *out_draft_dev, int32_t draft_stride,
+                                  int32_t *out_len_dev, void *stream) {
+    SAMD_REQUIRE(h && index_dev && start_tok_dev && out_draft_dev && draft_stride >= n_predicts, "samd_dyn_gen_draft: bad arguments");
+    SAMD_REQUIRE(flavour == SAMD_FLAVOUR_SAMD || match_dev, "samd_dyn_gen_draft: sam_only flavour needs match lengths");
+    dyn_gen_draft_kernel<<<h->a.n_requests, 32, 0, (cudaStream_t)stream>>>(h->a, index_dev, match_dev, start_tok_dev, flavour,
+                                                                             n_predicts, alpha, out_draft_dev, draft_stride, out_len_dev);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void static_gen_draft_kernel(StaticDev st, const int32_t *index, const int32_t *start_tok, int n, int n_predicts,
+                                        int32_t *out_draft, int stride) {
+    const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const int e = __ldg(st.states + index[r]).z;             // static_sam.py:119-125 (no to_anc)
+    for (int j = lane; j < stride; j += 32) {
+        int v = 0;
+        if (j < n_predicts) v = j == 0 ? start_tok[r] : ((long long)e + j <= st.n_tokens ? st.text[e + j] : 0);
+        out_draft[(size_t)r * stride + j] = v;
+    }
+}
+
+extern "C" int samd_static_gen_draft(samd_static_t h, const int32_t *index_dev, const int32_t *start_tok_dev, int n_requests,
+                                     int32_t n_predicts, int32_t *out_draft_dev, int32_t draft_stride, void *stream) {
+    SAMD_REQUIRE(h && h->dev.states && index_dev && start_tok_dev && out_draft_dev && n_requests > 0 && draft_stride >= n_predicts,
+                 "samd_static_gen_draft: bad arguments");
+    static_gen_draft_kernel<<<(n_requests + 7) / 8, 256, 0, (cudaStream_t)stream>>>(h->dev, index_dev, start_tok_dev, n_requests,
+                                                                                    n_predicts, out_draft_dev, draft_stride);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// edges of one request as (state, token, target) triples, per state in insertion order (oldest first)
+extern "C" int samd_dyn_export_edges(samd_dyn_t h, int request, int32_t *edges_host, int64_t capacity) {
+    SAMD_REQUIRE(h && request >= 0 && request < h->a.n_requests && edges_host, "samd_dyn_export_edges: bad arguments");
+    SAMD_CUDA(cudaDeviceSynchronize());
+    int32_t meta[META_WORDS];
+    SAMD_CUDA(cudaMemcpy(meta, h->a.meta + (size_t)request * META_WORDS, sizeof(meta), cudaMemcpyDeviceToHost));
+    SAMD_REQUIRE(capacity >= meta[META_NEDGES], "samd_dyn_export_edges: capacity too small");
+    const int ns = meta[META_NSTATES];
+    int4 *st = (int4 *)malloc((size_t)ns * sizeof(int4));
+    uint4 *sl = (uint4 *)malloc((size_t)h->a.h_cap * sizeof(uint4));
+    SAMD_CUDA(cudaMemcpy(st, h->a.states + (size_t)request * h->a.s_cap, (size_t)ns * sizeof(int4), cudaMemcpyDeviceToHost));
+    SAMD_CUDA(cudaMemcpy(sl, h->a.slots + (size_t)request * h->a.h_cap, (size_t)h->a.h_cap * sizeof(uint4), cudaMemcpyDeviceToHost));
+    int64_t k = 0;
+    for (int v = 0; v < ns; ++v) {
+        int64_t first = k;
+        for (uint32_t e = (uint32_t)st[v].w; e != SAMD_NIL; e = sl[e].w) {
+            edges_host[3 * k] = v;
+            edges_host[3 * k + 1] = (int32_t)sl[e].y;
+            edges_host[3 * k + 2] = (int32_t)sl[e].z;
+            k++;
+        }
+        for (int64_t i = first, j = k - 1; i < j; ++i, --j)       // list is newest-first: reverse
+            for (int c = 0; c < 3; ++c) {
+                int32_t t = edges_host[3 * i + c];
+                edges_host[3 * i + c] = edges_host[3 * j + c];
+                edges_host[3 * j + c] = t;
+            }
+    }
+    free(st);
+    free(sl);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// cursor-only walks: DynSAM.transfer_tokens (dyn_sam.py:90-92), StaticSAM.transfer_tokens
+// (static_sam.py:102-104) and the stand-alone StaticSAM.lookup / DynSAM.lookup (:94-97, :106-109)
+// ---------------------------------------------------------------------------------------
+template <bool kReadOnly>
+__device__ __forceinline__ void cursor_walk(const uint4 *slots, uint32_t bmask, const int4 *states, int &idx, int &len,
+                                            const int32_t *tk, int k, int lane) {
+    int hops = 0;
+    for (int i = 0; i < k; i += 32) {
+        const int mine = (i + lane < k) ? tk[i + lane] : 0;
+        const int lim = min(32, k - i);
+        for (int j = 0; j < lim; ++j)
+            warp_transfer<kReadOnly>(slots, bmask, states, idx, len, __shfl_sync(SAMD_FULL, mine, j), lane, hops);
+    }
+}
+
+__global__ void __launch_bounds__(32) static_walk_kernel(StaticDev st, int32_t *cursor, const int32_t *tokens, int stride,
+                                                         const int32_t *counts, const int32_t *peek_tok, int n,
+                                                         int32_t *out_index, int32_t *out_len) {
+    const int r = blockIdx.x, lane = threadIdx.x;
+    if (r >= n) return;
+    int idx = cursor[2 * r], len = cursor[2 * r + 1];
+    if (tokens) {
+        cursor_walk<true>(st.slots, st.bmask, st.states, idx, len, tokens + (size_t)r * stride, counts ? counts[r] : stride, lane);
+        if (lane == 0) {
+            cursor[2 * r] = idx;
+            cursor[2 * r + 1] = len;
+        }
+    }
+    if (peek_tok) {
+        int hops = 0;
+        warp_transfer<true>(st.slots, st.bmask, st.states, idx, len, peek_tok[r], lane, hops);
+        if (lane == 0) {
+            out_index[r] = idx;
+            out_len[r] = len;
+        }
+    }
+}
+
+extern "C" int samd_static_walk(samd_static_t h, int32_t *static_cursor_dev, const int32_t *tokens_dev, int32_t token_stride,
+                                const int32_t *counts_dev, const int32_t *peek_tok_dev, int n_requests, int32_t *out_index_dev,
+                                int32_t *out_len_dev, void *stream) {
+    SAMD_REQUIRE(h && h->dev.states && static_cursor_dev && n_requests > 0, "samd_static_walk: bad arguments");
+    SAMD_REQUIRE(!peek_tok_dev || (out_index_dev && out_len_dev), "samd_static_walk: peek needs output arrays");
+    static_walk_kernel<<<n_requests, 32, 0, (cudaStream_t)stream>>>(h->dev, static_cursor_dev, tokens_dev, token_stride, counts_dev,
+                                                                     peek_tok_dev, n_requests, out_index_dev, out_len_dev);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void __launch_bounds__(32) dyn_walk_kernel(DynArena a, const int32_t *tokens, int stride, const int32_t *counts) {
+    const int r = blockIdx.x, lane = threadIdx.x;
+    if (r >= a.n_requests) return;
+    int32_t *meta = a.meta + (size_t)r * META_WORDS;
+    int idx = meta[META_CUR], len = meta[META_CURLEN];
+    cursor_walk<false>(a.slots + (size_t)r * a.h_cap, a.bmask, a.states + (size_t)r * a.s_cap, idx, len,
+                       tokens + (size_t)r * stride, counts ? counts[r] : stride, lane);
+    if (lane == 0) {
+        meta[META_CUR] = idx;
+        meta[META_CURLEN] = len;
+    }
+}
+
+extern "C" int samd_dyn_transfer(samd_dyn_t h, const int32_t *tokens_dev, int32_t token_stride, const int32_t *counts_dev,
+                                 void *stream) {
+    SAMD_REQUIRE(h && tokens_dev && token_stride > 0, "samd_dyn_transfer: bad arguments");
+    dyn_walk_kernel<<<h->a.n_requests, 32, 0, (cudaStream_t)stream>>>(h->a, tokens_dev, token_stride, counts_dev);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Capacity growth: a new batch with a larger max_tokens holding the same automata (same state
+// numbering, cursor and history).  State records / text / meta are copied; the edge table is
+// re-hashed on the host for the new capacity, keeping every state's edge order.  Rare.
+// ---------------------------------------------------------------------------------------
+extern "C" int samd_dyn_grow(samd_dyn_t old, int new_max_tokens, samd_dyn_t *out) {
+    SAMD_REQUIRE(old && out && new_max_tokens > old->a.max_tokens, "samd_dyn_grow: new capacity must be larger");
+    samd_dyn_s *nw = nullptr;
+    int rc = samd_dyn_create(old->a.n_requests, new_max_tokens, &nw);
+    if (rc) return rc;
+    SAMD_CUDA(cudaDeviceSynchronize());
+    const DynArena &o = old->a;
+    const DynArena &n = nw->a;
+    int4 *st = (int4 *)malloc((size_t)o.s_cap * sizeof(int4));
+    uint4 *sl = (uint4 *)malloc((size_t)o.h_cap * sizeof(uint4));
+    uint4 *nsl = (uint4 *)malloc((size_t)n.h_cap * sizeof(uint4));
+    int32_t meta[META_WORDS];
+    SAMD_REQUIRE(st && sl && nsl, "samd_dyn_grow: host allocation failed");
+    std::vector<uint32_t> chain;
+    for (int r = 0; r < o.n_requests; ++r) {
+        SAMD_CUDA(cudaMemcpy(meta, o.meta + (size_t)r * META_WORDS, sizeof(meta), cudaMemcpyDeviceToHost));
+        const int ns = meta[META_NSTATES];
+        SAMD_CUDA(cudaMemcpy(st, o.states + (size_t)r * o.s_cap, (size_t)ns * sizeof(int4), cudaMemcpyDeviceToHost));
+        SAMD_CUDA(cudaMemcpy(sl, o.slots + (size_t)r * o.h_cap, (size_t)o.h_cap * sizeof(uint4), cudaMemcpyDeviceToHost));
+        memset(nsl, 0xFF, (size_t)n.h_cap * sizeof(uint4));
+        for (int v = 0; v < ns; ++v) {
+            chain.clear();
+            for (uint32_t e = (uint32_t)st[v].w; e != SAMD_NIL; e = sl[e].w) chain.push_back(e);
+            uint32_t head = SAMD_NIL;
+            for (size_t i = chain.size(); i-- > 0;) {                 // oldest first
+                const uint4 ed = sl[chain[i]];
+                uint32_t b = samd_hash((uint32_t)v, ed.y) & n.bmask;
+                uint32_t slot = 0;
+                for (bool placed = false; !placed; b = (b + 1) & n.bmask)
+                    for (int l = 0; l < SAMD_BUCKET && !placed; ++l)
+                        if (nsl[(size_t)b * SAMD_BUCKET + l].x == SAMD_EMPTY) {
+                            slot = b * SAMD_BUCKET + l;
+                            placed = true;
+                        }
+                nsl[slot] = make_uint4((uint32_t)v, ed.y, ed.z, head);
+                head = slot;
+            }
+            st[v].w = (int)head;
+        }
+        SAMD_CUDA(cudaMemcpy(n.states + (size_t)r * n.s_cap, st, (size_t)ns * sizeof(int4), cudaMemcpyHostToDevice));
+        SAMD_CUDA(cudaMemcpy(n.slots + (size_t)r * n.h_cap, nsl, (size_t)n.h_cap * sizeof(uint4), cudaMemcpyHostToDevice));
+        SAMD_CUDA(cudaMemcpy(n.text + (size_t)r * n.t_cap, o.text + (size_t)r * o.t_cap, (size_t)(meta[META_N] + 1) * sizeof(int32_t),
+                             cudaMemcpyDeviceToDevice));
+        meta[META_OVERFLOW] = 0;
+        SAMD_CUDA(cudaMemcpy(n.meta + (size_t)r * META_WORDS, meta, sizeof(meta), cudaMemcpyHostToDevice));
+    }
+    free(st);
+    free(sl);
+    free(nsl);
+    *out = nw;
     return 0;
 }

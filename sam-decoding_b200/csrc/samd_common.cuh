@@ -18,7 +18,7 @@
 #define SAMD_BUCKET 8
 
 enum { META_NSTATES = 0, META_LAST = 1, META_N = 2, META_CUR = 3, META_CURLEN = 4, META_NEDGES = 5,
-       META_OVERFLOW = 6, META_NCLONES = 7, META_WORDS = 8 };
+       META_OVERFLOW = 6, META_NCLONES = 7, META_HOPS = 8, META_PROBES = 9, META_WORDS = 16 };
 
 __host__ __device__ __forceinline__ uint32_t samd_hash(uint32_t state, uint32_t tok) {
     uint32_t h = state * 0x9E3779B1u + tok * 0x85EBCA77u;
@@ -150,13 +150,27 @@ __device__ __forceinline__ Probe warp_probe(const uint4 *slots, uint32_t bmask, 
     return r;
 }
 
+// Prefetch hint for a probe whose key is already known (next token's cursor / tail probes): the
+// four sectors of the bucket and the state record are pulled towards the SM while the warp is
+// still busy with the current token, turning a DRAM round trip into a cache hit.
+__device__ __forceinline__ void prefetch_probe(const uint4 *slots, uint32_t bmask, const int4 *states, uint32_t state,
+                                               uint32_t tok, int lane) {
+    if (lane < 4) {
+        const char *p = reinterpret_cast<const char *>(slots + (size_t)(samd_hash(state, tok) & bmask) * SAMD_BUCKET) + lane * 32;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    } else if (lane == 4 && states) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(states + state));
+    }
+}
+
 // Longest-suffix-match step (dyn_sam.py:69-78): one memory round trip per suffix-link hop.
 template <bool kReadOnly>
 __device__ __forceinline__ void warp_transfer(const uint4 *slots, uint32_t bmask, const int4 *states, int &index,
-                                              int &length, int tok, int lane) {
+                                              int &length, int tok, int lane, int &hops) {
     bool first = true;
     while (true) {
         Probe pr = warp_probe<true, kReadOnly>(slots, bmask, states, (uint32_t)index, (uint32_t)tok, lane);
+        hops++;
         if (!first) length = pr.rec.y;           // length = states[index].length after a link hop
         if (pr.found) {
             index = (int)pr.target;

@@ -1,12 +1,18 @@
 // Fused greedy tree verification + KV-cache compaction, one persistent launch (sm_100a).
-//   phase 1  stream logits [B,T,V] once: per (request,row,chunk) work item a CTA computes the
-//            chunk argmax (torch.argmax rule: lowest index among equal maxima, NaN is the
-//            maximum, +0 == -0) and folds it into a packed 64-bit key per row with atomicMax.
-//            The CTA that completes a request's last item walks the P x D path table
-//            (samd/utils.py:127-141), writes the outputs, snapshots + bumps cache_len and
-//            publishes the request as ready.
-//   phase 2  KV work items (request, tensor): rows cache_len+indices[j] -> cache_len+j
-//            (samd/cache.py:118-133), all heads, 16-byte columns, loads before stores.
+//
+// Work is warp-granular and statically strided over a grid that is fully resident:
+//   phase 1  item = (request, tree row, chunk).  A warp streams its slice of the logits row with
+//            128-bit no-allocate loads (8 in flight per lane), keeps a running (key, index) maximum
+//            under torch.argmax's rule (lowest index among equal maxima, NaN is the maximum,
+//            +0 == -0) and reduces it with shuffles - no block barrier, no shared memory.  Rows
+//            split into several chunks are combined with a 64-bit atomicMax.  The warp that
+//            completes a request's last item walks the P x D path table (samd/utils.py:127-141),
+//            writes best / accept_len / next_token / accepted tokens + indices, snapshots and bumps
+//            cache_len and publishes the request as ready.
+//   phase 2  item = (request, KV tensor).  The warp waits for the request's walk, then moves rows
+//            cache_len+indices[j] -> cache_len+j (samd/cache.py:118-133) for all heads in 16-byte
+//            columns, loads of a row group before its stores (the reference gathers into a
+//            temporary first; ascending j with indices[j] >= j makes that order equivalent).
 #include "samd_common.cuh"
 #include "../../include/samd_b200.h"
 
@@ -15,23 +21,26 @@
 
 #include <algorithm>
 
-#define VT 256                 // threads per CTA
+#define VT 256                 // threads per CTA (8 warps)
+#define VW (VT / 32)
+#define UNROLL 8               // 128-bit loads in flight per lane
 #define KV_GROUP 8             // accepted rows staged in registers per pass
 
 struct samd_verify_s {
     unsigned long long *node_key;   // [max_batch][max_nodes]
     int *done;                      // [max_batch]
-    int *ready;                     // [max_batch] epoch of the last finished walk
+    int *active;                    // [2][max_batch] requests with rows to move (double-buffered by epoch parity)
+    int *counters;                  // {n_active[0], n_active[1], finished walks (monotonic), epoch whose walks are all done}
+    long long finished_total;
     int *kv_start;                  // [max_batch] cache_len before the bump
-    int *work;                      // [4] {phase-1 counter, phase-2 counter, exit counter, unused}
     int max_batch, max_nodes, epoch, device, n_sms;
 };
 
 struct VerifyParams {
     samd_verify_args a;
     unsigned long long *node_key;
-    int *done, *ready, *kv_start, *work;
-    int max_nodes, epoch;
+    int *done, *active, *counters, *kv_start;
+    int max_nodes, max_batch, epoch, finished_target;
     int chunk, chunks_per_row, n_items1, n_items2, vec_ok;
 };
 
@@ -63,6 +72,30 @@ __device__ __forceinline__ uint32_t vec_max_bits(const uint4 &x) {
     }
 }
 
+// NaN-propagating packed maximum of two 16-bit pairs held as raw bits (HMNMX2 on sm_100a)
+template <int kDtype>
+__device__ __forceinline__ uint32_t hmax2_bits(uint32_t a, uint32_t b) {
+    if (kDtype == SAMD_DTYPE_BF16) {
+        const __nv_bfloat162 r = __hmax2_nan(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+        return *reinterpret_cast<const uint32_t *>(&r);
+    } else {
+        const __half2 r = __hmax2_nan(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b));
+        return *reinterpret_cast<const uint32_t *>(&r);
+    }
+}
+
+template <int kDtype>
+__device__ __forceinline__ uint32_t vec_pair_max(const uint4 &x) {
+    return hmax2_bits<kDtype>(hmax2_bits<kDtype>(x.x, x.y), hmax2_bits<kDtype>(x.z, x.w));
+}
+
+// orderable key of the larger half of a packed pair
+template <int kDtype>
+__device__ __forceinline__ uint32_t pair_key(uint32_t m) {
+    const uint32_t a = orderable16<kDtype>(m & 0xFFFFu), b = orderable16<kDtype>(m >> 16);
+    return a > b ? a : b;
+}
+
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -87,6 +120,48 @@ __device__ __forceinline__ void fold_vec(const uint4 &x, uint32_t elem, uint32_t
     }
 }
 
+template <int G>
+__device__ __forceinline__ void load_group(uint4 (&x)[G], const uint4 *v4, int v0, int nvec, int lane, uint32_t ninf) {
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        const int vi = v0 + u * 32 + lane;
+        x[u] = vi < nvec ? ld_stream(v4 + vi) : make_uint4(ninf, ninf, ninf, ninf);
+    }
+}
+
+// Fold one group of 32 x G vectors into the WARP-uniform running maximum (best_key, best_idx).
+template <int kDtype, int G>
+__device__ __forceinline__ void fold_group(const uint4 (&x)[G], int v0, int nvec, int lane, int e0, uint32_t &best_key,
+                                           uint32_t &best_idx) {
+    uint32_t m = vec_pair_max<kDtype>(x[0]);
+#pragma unroll
+    for (int u = 1; u < G; ++u) m = hmax2_bits<kDtype>(m, vec_pair_max<kDtype>(x[u]));
+    const uint32_t wk = __reduce_max_sync(SAMD_FULL, pair_key<kDtype>(m));
+    if (wk <= best_key) return;                                // warp-uniform; taken ~ln(#groups) times per row
+    best_key = wk;
+    bool found = false;
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        if (found) continue;
+        const int vi = v0 + u * 32 + lane;
+        const unsigned bal = __ballot_sync(SAMD_FULL, vi < nvec && pair_key<kDtype>(vec_pair_max<kDtype>(x[u])) == wk);
+        if (bal) {                                             // lowest u, then lowest lane = lowest index
+            found = true;
+            const int src = __ffs(bal) - 1;
+            int e_first = 0;
+            if (lane == src) {
+                const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                e_first = 7;
+#pragma unroll
+                for (int e = 7; e >= 0; --e)
+                    if (orderable16<kDtype>((w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu) == wk) e_first = e;
+            }
+            e_first = __shfl_sync(SAMD_FULL, e_first, src);
+            best_idx = (uint32_t)(e0 + (v0 + u * 32 + src) * 8 + e_first);
+        }
+    }
+}
+
 __device__ __forceinline__ int ri_at(const VerifyParams &P, int b, int p, int j) {
     if (!P.a.retrieve_dev) return j;                          // sequence: identity path
     return P.a.retrieve_dev[(size_t)b * P.a.retrieve_batch_stride + (size_t)p * P.a.depth + j];
@@ -94,24 +169,18 @@ __device__ __forceinline__ int ri_at(const VerifyParams &P, int b, int p, int j)
 
 template <int kDtype>
 __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
-    __shared__ int s_item;
-    __shared__ unsigned long long s_red[VT / 32];
-    __shared__ int s_flag;
-    __shared__ unsigned int s_best;
-    extern __shared__ int s_am[];                              // [n_nodes] node argmax of one request
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ int s_am_all[];                          // [VW][n_nodes] node argmax, one slab per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gwarp = warp * gridDim.x + blockIdx.x;          // warp-major: consecutive items land on different SMs
+    const int n_warps = gridDim.x * VW;
     const samd_verify_args &A = P.a;
     const int T = A.n_nodes;
     const int C = P.chunks_per_row;
+    int *s_am = s_am_all + warp * T;
     const uint16_t *logits = reinterpret_cast<const uint16_t *>(A.logits_dev);
 
     // ------------------------------ phase 1: argmax + path walk ---------------------------
-    while (true) {
-        if (tid == 0) s_item = atomicAdd(&P.work[0], 1);
-        __syncthreads();
-        const int item = s_item;
-        __syncthreads();
-        if (item >= P.n_items1) break;
+    for (int item = gwarp; item < P.n_items1; item += n_warps) {
         const int c = item % C;
         const int t = (item / C) % T;
         const int b = item / (C * T);
@@ -122,28 +191,37 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
             const uint16_t *row = logits + (size_t)b * A.batch_stride + (size_t)t * A.row_stride + e0;
             uint32_t best_key = 0, best_idx = 0;
             if (P.vec_ok) {
+                // The running maximum is WARP-uniform: a group of 32 x UNROLL vectors is reduced to one
+                // key per lane with packed max instructions, then across lanes with redux.sync; only when
+                // the group beats the running maximum (about ln(#groups) times per row) is the first
+                // maximal element located, from the registers that still hold the group.
                 const uint4 *v4 = reinterpret_cast<const uint4 *>(row);
                 const int nvec = len >> 3;
-                for (int v = tid; v < nvec; v += 4 * VT) {
-                    uint4 x[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (v + u * VT < nvec) x[u] = ld_stream(v4 + v + u * VT);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (v + u * VT < nvec) fold_vec<kDtype>(x[u], (uint32_t)(e0 + (v + u * VT) * 8), best_key, best_idx);
+                const uint32_t ninf = kDtype == SAMD_DTYPE_BF16 ? 0xFF80FF80u : 0xFC00FC00u;
+                // software pipeline: the loads of the next half-group are in flight while this one is folded
+                constexpr int G = UNROLL / 2;
+                uint4 xa[G], xb[G];
+                load_group<G>(xa, v4, 0, nvec, lane, ninf);
+                for (int v0 = 0; v0 < nvec; v0 += 64 * G) {
+                    const int v1 = v0 + 32 * G;
+                    if (v1 < nvec) load_group<G>(xb, v4, v1, nvec, lane, ninf);
+                    fold_group<kDtype, G>(xa, v0, nvec, lane, e0, best_key, best_idx);
+                    if (v1 < nvec) {
+                        if (v1 + 32 * G < nvec) load_group<G>(xa, v4, v1 + 32 * G, nvec, lane, ninf);
+                        fold_group<kDtype, G>(xb, v1, nvec, lane, e0, best_key, best_idx);
+                    }
                 }
                 const int tail = nvec << 3;
-                if (tid < len - tail) {                        // < 8 trailing elements
-                    const uint32_t ke = orderable16<kDtype>(row[tail + tid]);
-                    // a tail element can only beat this thread's vector maxima, never tie with an earlier index
-                    if (ke > best_key) {
-                        best_key = ke;
-                        best_idx = (uint32_t)(e0 + tail + tid);
+                if (len - tail > 0) {                          // < 8 trailing elements, all later than the vectors
+                    const uint32_t ke = lane < len - tail ? orderable16<kDtype>(row[tail + lane]) : 0u;
+                    const uint32_t wk = __reduce_max_sync(SAMD_FULL, ke);
+                    if (wk > best_key) {
+                        best_key = wk;
+                        best_idx = (uint32_t)(e0 + tail + __ffs(__ballot_sync(SAMD_FULL, ke == wk)) - 1);
                     }
                 }
             } else {
-                for (int e = tid; e < len; e += VT) {
+                for (int e = lane; e < len; e += 32) {
                     const uint32_t ke = orderable16<kDtype>(row[e]);
                     if (ke > best_key) {
                         best_key = ke;
@@ -151,47 +229,43 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
                     }
                 }
             }
-            unsigned long long pk = ((unsigned long long)best_key << 32) | (unsigned long long)(0xFFFFFFFFu - best_idx);
-            if (best_key == 0) pk = 0;
+            unsigned long long pk = best_key ? (((unsigned long long)best_key << 32) | (unsigned long long)(0xFFFFFFFFu - best_idx)) : 0ull;
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 const unsigned long long other = __shfl_xor_sync(SAMD_FULL, pk, o);
                 pk = other > pk ? other : pk;
             }
-            if (lane == 0) s_red[warp] = pk;
-            __syncthreads();
-            if (tid == 0) {
-                for (int w = 1; w < VT / 32; ++w) pk = s_red[w] > pk ? s_red[w] : pk;
-                atomicMax(&P.node_key[(size_t)b * P.max_nodes + t], pk);
+            if (lane == 0) {
+                unsigned long long *kp = &P.node_key[(size_t)b * P.max_nodes + t];
+                if (C == 1) *reinterpret_cast<volatile unsigned long long *>(kp) = pk;
+                else atomicMax(kp, pk);
             }
         }
-        if (tid == 0) {
+        int fin = 0;
+        if (lane == 0) {
             __threadfence();
-            const int prev = atomicAdd(&P.done[b], 1);
-            s_flag = (prev == T * C - 1);
+            fin = atomicAdd(&P.done[b], 1) == T * C - 1;
         }
-        __syncthreads();
-        if (!s_flag) continue;
+        fin = __shfl_sync(SAMD_FULL, fin, 0);
+        if (!fin) continue;
 
-        // ---- this CTA finished request b: path walk (samd/utils.py:127-141) -------------------
+        // ---- this warp finished request b: path walk (samd/utils.py:127-141) ------------------
         __threadfence();
-        if (tid == 0) {
-            P.done[b] = 0;
-            s_best = 0;
-        }
-        for (int i = tid; i < T; i += VT) {
+        if (lane == 0) P.done[b] = 0;
+        for (int i = lane; i < T; i += 32) {
             unsigned long long *kp = &P.node_key[(size_t)b * P.max_nodes + i];
-            const unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(kp);
+            const unsigned long long k = __ldcg(kp);
             const int am = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
             s_am[i] = am;
             *kp = 0;                                            // re-arm for the next launch
             if (A.out_node_argmax_dev && i < n_rows) A.out_node_argmax_dev[(size_t)b * T + i] = am;
         }
-        __syncthreads();
+        __syncwarp();
         const int32_t *tok = A.tree_tokens_dev + (size_t)b * T;
         const int n_paths = A.retrieve_dev ? (A.n_paths_dev ? A.n_paths_dev[b] : A.n_paths) : 1;
         const int depth = A.retrieve_dev ? A.depth : n_rows;
-        for (int p = tid; p < n_paths; p += VT) {
+        unsigned int bestpk = 0;
+        for (int p = lane; p < n_paths; p += 32) {
             int acc = 0;
             int prev = ri_at(P, b, p, 0);
             for (int j = 0; j + 1 < depth; ++j) {
@@ -202,13 +276,14 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
                 acc++;
                 prev = nxt;
             }
-            atomicMax(&s_best, ((unsigned)acc << 16) | (unsigned)(0xFFFF - p));   // max accept, first path
+            bestpk = max(bestpk, ((unsigned)acc << 16) | (unsigned)(0xFFFF - p));   // max accept, first path
         }
-        __syncthreads();
-        const int acc = (int)(s_best >> 16);
-        const int best = acc == 0 ? 0 : (int)(0xFFFF - (s_best & 0xFFFF));
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bestpk = max(bestpk, __shfl_xor_sync(SAMD_FULL, bestpk, o));
+        const int acc = (int)(bestpk >> 16);
+        const int best = acc == 0 ? 0 : (int)(0xFFFF - (bestpk & 0xFFFF));
         const int out_stride = A.retrieve_dev ? A.depth : T;
-        for (int j = tid; j < out_stride; j += VT) {
+        for (int j = lane; j < out_stride; j += 32) {
             int tk = -1, ix = -1;
             if (j <= acc) {
                 ix = ri_at(P, b, best, j);
@@ -217,7 +292,7 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
             if (A.out_tokens_dev) A.out_tokens_dev[(size_t)b * out_stride + j] = tk;
             if (A.out_indices_dev) A.out_indices_dev[(size_t)b * out_stride + j] = ix;
         }
-        if (tid == 0) {
+        if (lane == 0) {
             const int last = ri_at(P, b, best, acc);
             if (A.out_best_dev) A.out_best_dev[b] = best;
             if (A.out_accept_len_dev) A.out_accept_len_dev[b] = acc + 1;
@@ -229,63 +304,70 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
             }
             P.kv_start[b] = start;
         }
-        __syncthreads();
-        if (tid == 0) {
+        // publish: requests that really move rows join the compact active list of phase 2
+        int moved = 0;
+        for (int j = lane; j <= acc; j += 32) moved += ri_at(P, b, best, j) != j;
+        moved = __reduce_add_sync(SAMD_FULL, moved);
+        __syncwarp();
+        if (lane == 0) {
+            if (moved > 0 && P.n_items2 > 0) P.active[(P.epoch & 1) * P.max_batch + atomicAdd(&P.counters[P.epoch & 1], 1)] = b;
             __threadfence();
-            atomicExch(&P.ready[b], P.epoch);
+            // monotonic count of finished walks; whoever completes the batch raises the (write-once,
+            // read-many) flag the phase-2 pollers watch, so polling never contends with this atomic
+            if ((unsigned)(atomicAdd(&P.counters[2], 1) + 1) == (unsigned)P.finished_target) {
+                __threadfence();
+                *reinterpret_cast<volatile int *>(&P.counters[3]) = P.epoch;
+            }
         }
+        __syncwarp();
     }
 
     // ------------------------------ phase 2: KV row moves ---------------------------------
+    // All walks are awaited (phase 1 is a single wave, so they end together), then the moved rows of
+    // the active requests are flattened into 16-byte units and strided over every lane of the grid.
     if (P.n_items2 > 0) {
+        if (gwarp == 0 && lane == 0) P.counters[(P.epoch + 1) & 1] = 0;      // re-arm the other list
+        __syncthreads();
+        if (threadIdx.x == 0) {                                 // one poller per CTA, plain loads, backoff
+            while (*reinterpret_cast<volatile int *>(&P.counters[3]) != P.epoch) __nanosleep(400);
+            __threadfence();
+        }
+        __syncthreads();
+        const int n_active = __ldcg(&P.counters[P.epoch & 1]);
+        const int *active = P.active + (P.epoch & 1) * P.max_batch;
         const int cols = A.row_bytes >> 4;                      // 16-byte columns per (head,row)
         const int per_tensor = A.n_heads * cols;
-        while (true) {
-            if (tid == 0) s_item = atomicAdd(&P.work[1], 1);
-            __syncthreads();
-            const int item = s_item;
-            __syncthreads();
-            if (item >= P.n_items2) break;
-            const int b = item / A.n_kv;
-            const int kv = item % A.n_kv;
-            if (tid == 0) {
-                while (atomicAdd(&P.ready[b], 0) != P.epoch) __nanosleep(64);
-                __threadfence();
+        const long long per_req = (long long)A.n_kv * per_tensor;
+        const long long total = per_req * n_active;
+        int cur_a = -1, acc1 = 0, start = 0;
+        const int32_t *idx = nullptr;
+        for (long long g = (long long)gwarp * 32 + lane; g < total; g += (long long)n_warps * 32) {
+            const int a_i = (int)(g / per_req);
+            const int unit = (int)(g - (long long)a_i * per_req);
+            const int b = __ldcg(active + a_i);
+            if (a_i != cur_a) {
+                cur_a = a_i;
+                acc1 = __ldcg(A.out_accept_len_dev + b);
+                start = __ldcg(P.kv_start + b);
+                idx = A.out_indices_dev + (size_t)b * A.depth;
             }
-            __syncthreads();
-            const int acc1 = __ldcg(A.out_accept_len_dev + b);
-            const int start = __ldcg(P.kv_start + b);
-            const int32_t *idx = A.out_indices_dev + (size_t)b * A.depth;
-            char *base = reinterpret_cast<char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.kv_ptrs_dev) + kv)) +
-                         (size_t)b * A.kv_batch_stride;
+            const int kv = unit / per_tensor;
+            const int w = unit - kv * per_tensor;
+            const int hd = w / cols, col = w - hd * cols;
+            char *hb = reinterpret_cast<char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.kv_ptrs_dev) + kv)) +
+                       (size_t)b * A.kv_batch_stride + (size_t)hd * A.kv_head_stride + ((size_t)col << 4);
             for (int j0 = 0; j0 < acc1; j0 += KV_GROUP) {
                 int src[KV_GROUP];
+                uint4 val[KV_GROUP];
 #pragma unroll
                 for (int u = 0; u < KV_GROUP; ++u) src[u] = (j0 + u < acc1) ? __ldcg(idx + j0 + u) : j0 + u;
-                for (int w = tid; w < per_tensor; w += VT) {
-                    const int hd = w / cols, col = w - hd * cols;
-                    char *hb = base + (size_t)hd * A.kv_head_stride + ((size_t)col << 4);
-                    uint4 val[KV_GROUP];
 #pragma unroll
-                    for (int u = 0; u < KV_GROUP; ++u)
-                        if (j0 + u < acc1 && src[u] != j0 + u)
-                            val[u] = *reinterpret_cast<const uint4 *>(hb + (size_t)(start + src[u]) * A.kv_pos_stride);
+                for (int u = 0; u < KV_GROUP; ++u)
+                    if (src[u] != j0 + u) val[u] = *reinterpret_cast<const uint4 *>(hb + (size_t)(start + src[u]) * A.kv_pos_stride);
 #pragma unroll
-                    for (int u = 0; u < KV_GROUP; ++u)
-                        if (j0 + u < acc1 && src[u] != j0 + u)
-                            *reinterpret_cast<uint4 *>(hb + (size_t)(start + j0 + u) * A.kv_pos_stride) = val[u];
-                }
+                for (int u = 0; u < KV_GROUP; ++u)
+                    if (src[u] != j0 + u) *reinterpret_cast<uint4 *>(hb + (size_t)(start + j0 + u) * A.kv_pos_stride) = val[u];
             }
-        }
-    }
-    // last CTA out re-arms the work counters for the next launch
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(&P.work[2], 1) == (int)gridDim.x - 1) {
-            P.work[0] = 0;
-            P.work[1] = 0;
-            P.work[2] = 0;
         }
     }
 }
@@ -300,14 +382,15 @@ extern "C" int samd_verify_create(int max_batch, int max_nodes, samd_verify_t *o
     SAMD_CUDA(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, h->device));
     SAMD_CUDA(cudaMalloc(&h->node_key, (size_t)max_batch * max_nodes * sizeof(unsigned long long)));
     SAMD_CUDA(cudaMalloc(&h->done, (size_t)max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMalloc(&h->ready, (size_t)max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMalloc(&h->active, (size_t)2 * max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMalloc(&h->counters, 4 * sizeof(int)));
+    h->finished_total = 0;
     SAMD_CUDA(cudaMalloc(&h->kv_start, (size_t)max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMalloc(&h->work, 4 * sizeof(int)));
     SAMD_CUDA(cudaMemset(h->node_key, 0, (size_t)max_batch * max_nodes * sizeof(unsigned long long)));
     SAMD_CUDA(cudaMemset(h->done, 0, (size_t)max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMemset(h->ready, 0, (size_t)max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMemset(h->active, 0, (size_t)2 * max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMemset(h->counters, 0, 4 * sizeof(int)));
     SAMD_CUDA(cudaMemset(h->kv_start, 0, (size_t)max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMemset(h->work, 0, 4 * sizeof(int)));
     SAMD_CUDA(cudaDeviceSynchronize());
     *out = h;
     return 0;
@@ -317,9 +400,9 @@ extern "C" int samd_verify_destroy(samd_verify_t h) {
     if (!h) return 0;
     cudaFree(h->node_key);
     cudaFree(h->done);
-    cudaFree(h->ready);
+    cudaFree(h->active);
+    cudaFree(h->counters);
     cudaFree(h->kv_start);
-    cudaFree(h->work);
     delete h;
     return 0;
 }
@@ -334,7 +417,7 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     SAMD_REQUIRE(a->n_nodes > 0 && a->n_nodes <= h->max_nodes, "samd_verify_compact: n_nodes exceeds scratch capacity");
     SAMD_REQUIRE(a->vocab > 0, "samd_verify_compact: bad vocab");
     SAMD_REQUIRE(a->dtype == SAMD_DTYPE_BF16 || a->dtype == SAMD_DTYPE_FP16, "samd_verify_compact: bad dtype");
-    SAMD_REQUIRE(!a->retrieve_dev || (a->n_paths > 0 && a->n_paths < 65535 && a->depth > 0),
+    SAMD_REQUIRE(!a->retrieve_dev || (a->n_paths > 0 && a->n_paths < 65535 && a->depth > 0 && a->depth < 65535),
                  "samd_verify_compact: bad retrieve table shape");
     const bool move = a->move_kv && a->kv_ptrs_dev && a->retrieve_dev;
     if (move) {
@@ -348,29 +431,110 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     P.a = *a;
     P.node_key = h->node_key;
     P.done = h->done;
-    P.ready = h->ready;
+    P.active = h->active;
+    P.counters = h->counters;
+    P.max_batch = h->max_batch;
+    h->finished_total += a->batch;
+    P.finished_target = (int)(uint32_t)h->finished_total;     // device counter wraps mod 2^32 as well
     P.kv_start = h->kv_start;
-    P.work = h->work;
     P.max_nodes = h->max_nodes;
     P.epoch = ++h->epoch;
-    int chunk = g_chunk_override > 0 ? g_chunk_override : 8192;
-    chunk = (chunk + 7) & ~7;
-    if (chunk > a->vocab) chunk = (a->vocab + 7) & ~7;
+    const size_t smem = (size_t)VW * a->n_nodes * sizeof(int);
+    auto kern = a->dtype == SAMD_DTYPE_BF16 ? verify_compact_kernel<SAMD_DTYPE_BF16> : verify_compact_kernel<SAMD_DTYPE_FP16>;
+    int per_sm = 0;
+    SAMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, VT, smem));
+    SAMD_REQUIRE(per_sm > 0, "samd_verify_compact: kernel does not fit on an SM");
+    const long long resident_warps = (long long)h->n_sms * per_sm * VW;
+    // split rows into chunks only when whole rows would leave most of the machine idle
+    const long long rows = (long long)a->batch * a->n_nodes;
+    int chunks = 1;
+    if (g_chunk_override > 0) chunks = (a->vocab + g_chunk_override - 1) / g_chunk_override;
+    else
+        while (rows * chunks * 2 <= resident_warps && a->vocab / (chunks * 2) >= 2048) chunks *= 2;
+    int chunk = ((a->vocab + chunks - 1) / chunks + 7) & ~7;
     P.chunk = chunk;
     P.chunks_per_row = (a->vocab + chunk - 1) / chunk;
     P.n_items1 = a->batch * a->n_nodes * P.chunks_per_row;
     P.n_items2 = move ? a->batch * a->n_kv : 0;
     P.vec_ok = ((uintptr_t)a->logits_dev % 16 == 0) && (a->batch_stride % 8 == 0) && (a->row_stride % 8 == 0);
-    const size_t smem = (size_t)a->n_nodes * sizeof(int);
-    auto kern = a->dtype == SAMD_DTYPE_BF16 ? verify_compact_kernel<SAMD_DTYPE_BF16> : verify_compact_kernel<SAMD_DTYPE_FP16>;
-    int per_sm = 0;
-    SAMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, VT, smem));
-    SAMD_REQUIRE(per_sm > 0, "samd_verify_compact: kernel does not fit on an SM");
     // persistent grid: every CTA must be resident (phase 2 spins on phase-1 results)
-    long long want = (long long)P.n_items1 + P.n_items2;
-    int grid = (int)std::min<long long>((long long)h->n_sms * per_sm, want);
+    const long long want_warps = std::max<long long>(P.n_items1, P.n_items2);
+    long long grid = std::min<long long>((long long)h->n_sms * per_sm, (want_warps + VW - 1) / VW);
+    if (move) grid = (long long)h->n_sms * per_sm;             // phase 2 strides its units over the whole machine
     if (grid < 1) grid = 1;
-    kern<<<grid, VT, smem, (cudaStream_t)stream>>>(P);
+    kern<<<(int)grid, VT, smem, (cudaStream_t)stream>>>(P);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stand-alone SamdStaticCache.select_indices (samd/cache.py:118-133) for callers that verify
+// elsewhere: same row moves as phase 2 above, indices / accept lengths given by the caller.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VT) kv_compact_kernel(void *const *kv_ptrs, int n_kv, int n_heads, int row_bytes,
+                                                        long long batch_stride, long long head_stride, long long pos_stride,
+                                                        const int32_t *indices, int depth, const int32_t *accept_len,
+                                                        int32_t *cache_len, int batch, int bump) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * VT + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * VT) >> 5;
+    const int cols = row_bytes >> 4;
+    const int per_tensor = n_heads * cols;
+    for (int item = gwarp; item < batch * n_kv; item += n_warps) {
+        const int b = item / n_kv, kv = item % n_kv;
+        const int acc1 = accept_len[b];
+        const int start = cache_len[b];
+        const int32_t *idx = indices + (size_t)b * depth;
+        char *base = reinterpret_cast<char *>(kv_ptrs[kv]) + (size_t)b * batch_stride;
+        for (int j0 = 0; j0 < acc1; j0 += KV_GROUP) {
+            int src[KV_GROUP];
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < KV_GROUP; ++u) {
+                src[u] = (j0 + u < acc1) ? idx[j0 + u] : j0 + u;
+                any |= src[u] != j0 + u;
+            }
+            if (!any) continue;
+            for (int w = lane; w < per_tensor; w += 32) {
+                const int hd = w / cols, col = w - hd * cols;
+                char *hb = base + (size_t)hd * head_stride + ((size_t)col << 4);
+                uint4 val[KV_GROUP];
+#pragma unroll
+                for (int u = 0; u < KV_GROUP; ++u)
+                    if (src[u] != j0 + u) val[u] = *reinterpret_cast<const uint4 *>(hb + (size_t)(start + src[u]) * pos_stride);
+#pragma unroll
+                for (int u = 0; u < KV_GROUP; ++u)
+                    if (src[u] != j0 + u) *reinterpret_cast<uint4 *>(hb + (size_t)(start + j0 + u) * pos_stride) = val[u];
+            }
+        }
+    }
+    (void)bump;
+}
+
+__global__ void kv_bump_kernel(int32_t *cache_len, const int32_t *accept_len, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) cache_len[b] += accept_len[b];
+}
+
+extern "C" int samd_kv_compact(void *const *kv_ptrs_dev, int32_t n_kv, int32_t n_heads, int32_t row_bytes, int64_t kv_batch_stride,
+                               int64_t kv_head_stride, int64_t kv_pos_stride, const int32_t *indices_dev, int32_t depth,
+                               const int32_t *accept_len_dev, int32_t *cache_len_dev, int32_t batch, void *stream) {
+    SAMD_REQUIRE(accept_len_dev && cache_len_dev && batch > 0, "samd_kv_compact: bad arguments");
+    if (indices_dev) {                                          // indices NULL = sequence draft: only the length bump
+        SAMD_REQUIRE(kv_ptrs_dev && n_kv > 0 && n_heads > 0 && depth > 0, "samd_kv_compact: bad KV shape");
+        SAMD_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0 && kv_pos_stride % 16 == 0 && kv_head_stride % 16 == 0 &&
+                         kv_batch_stride % 16 == 0,
+                     "samd_kv_compact: KV rows must be 16-byte aligned");
+        const int items = batch * n_kv;
+        const int grid = std::min((items + VW - 1) / VW, 148 * 8);
+        kv_compact_kernel<<<grid, VT, 0, (cudaStream_t)stream>>>(kv_ptrs_dev, n_kv, n_heads, row_bytes, kv_batch_stride,
+                                                                 kv_head_stride, kv_pos_stride, indices_dev, depth, accept_len_dev,
+                                                                 cache_len_dev, batch, 0);
+        samd_count_launch();
+        SAMD_CUDA(cudaGetLastError());
+    }
+    kv_bump_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cache_len_dev, accept_len_dev, batch);
     samd_count_launch();
     SAMD_CUDA(cudaGetLastError());
     return 0;

@@ -1,1 +1,6 @@
-"""samd drop-in package (filled in below)."""
+"""Drop-in for the reference's `samd` package (samd/__init__.py:1-5): same names, CUDA inside."""
+from .samd_config import SamdConfig
+from .samd_model import SamdModel
+from .utils import SamdGenerationConfig
+from .sam import build_sam, load_sam, dump_sam
+from .draft import DraftModel

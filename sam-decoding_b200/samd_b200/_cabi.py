@@ -59,7 +59,16 @@ SYMBOLS = {
     "samd_dyn_destroy": (C.c_int, [vp]),
     "samd_dyn_reset": (C.c_int, [vp, vp, vp]),
     "samd_dyn_bytes": (C.c_int64, [vp]),
+    "samd_dyn_copy": (C.c_int, [vp, vp, vp]),
+    "samd_dyn_grow": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "samd_dyn_stats": (C.c_int, [vp, c_i64p]),
     "samd_dyn_export": (C.c_int, [vp, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int64]),
+    "samd_dyn_export_edges": (C.c_int, [vp, C.c_int, c_i32p, C.c_int64]),
+    "samd_dyn_gen_draft": (C.c_int, [vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_double, vp, C.c_int32, vp, vp]),
+    "samd_static_from_arrays": (C.c_int, [C.c_int64, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int64, c_i32p, C.c_int64, c_i32p,
+                                          C.POINTER(vp)]),
+    "samd_static_export_edges": (C.c_int, [vp, c_i32p, c_i32p]),
+    "samd_static_gen_draft": (C.c_int, [vp, vp, vp, C.c_int, C.c_int32, vp, C.c_int32, vp]),
     "samd_static_build": (C.c_int, [c_i32p, c_i64p, C.c_int64, C.c_int32, C.c_int, C.POINTER(vp)]),
     "samd_static_build_host": (C.c_int, [c_i32p, c_i64p, C.c_int64, C.c_int32, C.c_int, C.POINTER(vp)]),
     "samd_static_upload": (C.c_int, [vp]),
@@ -75,6 +84,10 @@ SYMBOLS = {
                                          vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "samd_static_lookup_keys": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, vp, vp]),
     "samd_draft_from_keys": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, C.c_int32, vp, vp, C.c_int32, vp]),
+    "samd_static_walk": (C.c_int, [vp, vp, vp, C.c_int32, vp, vp, C.c_int, vp, vp, vp]),
+    "samd_dyn_transfer": (C.c_int, [vp, vp, C.c_int32, vp, vp]),
+    "samd_kv_compact": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32,
+                                  vp, vp, C.c_int32, vp]),
     "samd_verify_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
     "samd_verify_destroy": (C.c_int, [vp]),
     "samd_verify_compact": (C.c_int, [vp, C.POINTER(VerifyArgs), vp]),

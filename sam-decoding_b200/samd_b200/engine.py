@@ -64,6 +64,27 @@ class DynSamBatch:
                     n_edges=int(meta[5]), overflow=int(meta[6]), n_clones=int(meta[7]), link=link[:ns], length=length[:ns],
                     min_endpos=endpos[:ns], text=text[:n + 1])
 
+    def grown(self, new_max_tokens: int) -> "DynSamBatch":
+        """A new batch with a larger capacity holding the same automata (samd_dyn_grow)."""
+        new = DynSamBatch.__new__(DynSamBatch)
+        new.device, new.n_requests, new.max_tokens = self.device, self.n_requests, int(new_max_tokens)
+        new._h = K.vp()
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_dyn_grow(self._h, int(new_max_tokens), C.byref(new._h)), "samd_dyn_grow")
+        return new
+
+    def copy_from(self, other: "DynSamBatch"):
+        """Snapshot / restore of all arenas (device-to-device, stream ordered)."""
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_dyn_copy(self._h, other.handle, K.stream_ptr()), "samd_dyn_copy")
+
+    def stats(self) -> dict:
+        out = np.zeros(8, dtype=np.int64)
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_dyn_stats(self._h, out.ctypes.data_as(K.c_i64p)), "samd_dyn_stats")
+        keys = ("n_states", "tokens", "n_edges", "n_clones", "extend_probes", "lookup_probes", "overflowed")
+        return {k: int(v) for k, v in zip(keys, out)}
+
     def close(self):
         if self._h:
             K.lib().samd_dyn_destroy(self._h)
