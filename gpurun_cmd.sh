@@ -1,4 +1,1 @@
-mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q -k "verify or kv" 2>&1 | tail -5
-python bench.py --only-verify > gpurun_out/verify_c.json 2> gpurun_out/verify_c.err; echo "rc=$?"; tail -c 400 gpurun_out/verify_c.err
-python bench.py --only-verify --verify-vocab 128256 --kv-len 512 > gpurun_out/verify_c5.json 2>> gpurun_out/verify_c.err; echo "rc=$?"
+python -m pytest tests/test_gpu_dropin.py -m gpu -x -q 2>&1 | tail -40

@@ -40,6 +40,7 @@ extern "C" {
 /* logits dtypes */
 #define SAMD_DTYPE_BF16 0
 #define SAMD_DTYPE_FP16 1
+#define SAMD_DTYPE_FP32 2
 
 typedef struct samd_dyn_s    *samd_dyn_t;     /* batch of per-request dynamic automata        */
 typedef struct samd_static_s *samd_static_t;  /* read-only static automaton over a corpus     */

@@ -405,14 +405,33 @@ def loop_fixture(ns):
     print("decode_loop.npz", {n: (len(out[f'{n}/accepts']), float(out[f'{n}/accepts'].mean())) for n in names})
 
 
+def pickle_fixture(ns):
+    """Pickles written by the reference's own dump_sam (samd/sam/utils.py:20-22), to check that this
+    framework's load_sam reads them (module path / class names / attribute layout)."""
+    z = np.load(os.path.join(OUT, "static_sam.npz"))
+    flat, offs = z["small/docs_flat"], z["small/docs_offs"]
+    docs = [flat[offs[i]:offs[i + 1]].tolist() for i in range(len(offs) - 1)]
+    sa = ns.samd_sam.StaticSAM.build(docs, int(z["small/eos"]), verbose=False)
+    ns.samd_sam.dump_sam(os.path.join(OUT, "ref_static_samd.pkl"), sa)
+    with quiet():
+        sb = ns.so_sam.StaticSAM.build(docs, int(z["small/eos"]), verbose=False)
+    ns.so_sam.dump_sam(os.path.join(OUT, "ref_static_sam_only.pkl"), sb)
+    print("pickles", os.path.getsize(os.path.join(OUT, "ref_static_samd.pkl")),
+          os.path.getsize(os.path.join(OUT, "ref_static_sam_only.pkl")))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "pickles":
+        pickle_fixture(ns)
+        return
     dyn_fixture(ns)
     static_fixture(ns)
     select_fixture(ns)
     verify_fixture(ns)
     loop_fixture(ns)
+    pickle_fixture(ns)
 
 
 if __name__ == "__main__":

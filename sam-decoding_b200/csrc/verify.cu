@@ -72,6 +72,13 @@ __device__ __forceinline__ uint32_t vec_max_bits(const uint4 &x) {
     }
 }
 
+__device__ __forceinline__ uint32_t orderable32(uint32_t b) {
+    const uint32_t a = b & 0x7FFFFFFFu;
+    if (a > 0x7F800000u) return 0xFFFFFFFFu;      // NaN is the maximum
+    if (a == 0) return 0x80000000u;               // +0 == -0
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 // NaN-propagating packed maximum of two 16-bit pairs held as raw bits (HMNMX2 on sm_100a)
 template <int kDtype>
 __device__ __forceinline__ uint32_t hmax2_bits(uint32_t a, uint32_t b) {
@@ -190,7 +197,19 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
             const int len = min(P.chunk, A.vocab - e0);
             const uint16_t *row = logits + (size_t)b * A.batch_stride + (size_t)t * A.row_stride + e0;
             uint32_t best_key = 0, best_idx = 0;
-            if (P.vec_ok) {
+            if constexpr (kDtype == SAMD_DTYPE_FP32) {
+                // fp32 logits (the reference's --dtype float32 runs): coalesced scalar loads, per-lane maxima
+                const uint32_t *row32 = reinterpret_cast<const uint32_t *>(A.logits_dev) + (size_t)b * A.batch_stride +
+                                        (size_t)t * A.row_stride + e0;
+#pragma unroll 4
+                for (int e = lane; e < len; e += 32) {
+                    const uint32_t ke = orderable32(__ldg(row32 + e));
+                    if (ke > best_key) {
+                        best_key = ke;
+                        best_idx = (uint32_t)(e0 + e);
+                    }
+                }
+            } else if (P.vec_ok) {
                 // The running maximum is WARP-uniform: a group of 32 x UNROLL vectors is reduced to one
                 // key per lane with packed max instructions, then across lanes with redux.sync; only when
                 // the group beats the running maximum (about ln(#groups) times per row) is the first
@@ -416,7 +435,8 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     SAMD_REQUIRE(a->batch > 0 && a->batch <= h->max_batch, "samd_verify_compact: batch exceeds scratch capacity");
     SAMD_REQUIRE(a->n_nodes > 0 && a->n_nodes <= h->max_nodes, "samd_verify_compact: n_nodes exceeds scratch capacity");
     SAMD_REQUIRE(a->vocab > 0, "samd_verify_compact: bad vocab");
-    SAMD_REQUIRE(a->dtype == SAMD_DTYPE_BF16 || a->dtype == SAMD_DTYPE_FP16, "samd_verify_compact: bad dtype");
+    SAMD_REQUIRE(a->dtype == SAMD_DTYPE_BF16 || a->dtype == SAMD_DTYPE_FP16 || a->dtype == SAMD_DTYPE_FP32,
+                 "samd_verify_compact: bad dtype");
     SAMD_REQUIRE(!a->retrieve_dev || (a->n_paths > 0 && a->n_paths < 65535 && a->depth > 0 && a->depth < 65535),
                  "samd_verify_compact: bad retrieve table shape");
     const bool move = a->move_kv && a->kv_ptrs_dev && a->retrieve_dev;
@@ -440,7 +460,9 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     P.max_nodes = h->max_nodes;
     P.epoch = ++h->epoch;
     const size_t smem = (size_t)VW * a->n_nodes * sizeof(int);
-    auto kern = a->dtype == SAMD_DTYPE_BF16 ? verify_compact_kernel<SAMD_DTYPE_BF16> : verify_compact_kernel<SAMD_DTYPE_FP16>;
+    auto kern = a->dtype == SAMD_DTYPE_BF16   ? verify_compact_kernel<SAMD_DTYPE_BF16>
+                : a->dtype == SAMD_DTYPE_FP16 ? verify_compact_kernel<SAMD_DTYPE_FP16>
+                                              : verify_compact_kernel<SAMD_DTYPE_FP32>;
     int per_sm = 0;
     SAMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, VT, smem));
     SAMD_REQUIRE(per_sm > 0, "samd_verify_compact: kernel does not fit on an SM");

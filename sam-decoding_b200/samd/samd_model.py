@@ -122,9 +122,12 @@ class SamdModel(nn.Module):
         packed = torch.cat([out["accept_len"], out["tokens"][0]]).tolist()        # the step's one D2H copy
         k = packed[0]
         new_tokens = packed[1:1 + k]
-        self.draft.update(tokens=out["tokens"][0, :k], tree_tokens=tree_tokens.squeeze(0), tree_logits=tree_logits.squeeze(0))
+        self._draft_update(out["tokens"][0, :k], tree_tokens.squeeze(0), tree_logits.squeeze(0))
         self.cache.cache_length += k
         return sample_p, new_tokens
+
+    def _draft_update(self, tokens, tree_tokens, tree_logits):
+        self.draft.update(tokens=tokens, tree_tokens=tree_tokens, tree_logits=tree_logits)
 
     def set_cache(self, generation_config: SamdGenerationConfig):
         if self.samd_config.cache_type == "dynamic":

@@ -20,6 +20,7 @@ DRAFT_TREE_MODEL = 2
 DRAFT_STATIC_TREE = 3
 DTYPE_BF16 = 0
 DTYPE_FP16 = 1
+DTYPE_FP32 = 2
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)

@@ -306,9 +306,9 @@ class Verifier:
                n_paths: Optional[torch.Tensor] = None, out: Optional[dict] = None, want_argmax: bool = False) -> dict:
         assert logits.is_cuda and logits.dim() == 3 and logits.stride(2) == 1
         B, T, V = logits.shape
-        dt = {torch.bfloat16: K.DTYPE_BF16, torch.float16: K.DTYPE_FP16}.get(logits.dtype)
+        dt = {torch.bfloat16: K.DTYPE_BF16, torch.float16: K.DTYPE_FP16, torch.float32: K.DTYPE_FP32}.get(logits.dtype)
         if dt is None:
-            raise K.SamdError(f"unsupported logits dtype {logits.dtype} (bf16 / fp16 only)")
+            raise K.SamdError(f"unsupported logits dtype {logits.dtype} (bf16 / fp16 / fp32)")
         _i32(tree_tokens)
         assert tree_tokens.shape == (B, T)
         a = self._args
