@@ -10,21 +10,24 @@
 
 // ---------------------------------------------------------------------------------------
 // host builder (StaticSAM.build, samd/sam/static_sam.py:32-79; counts/top-k of
-// samd_sam_only/sam/static_sam.py:94-96,137-146)
+// samd_sam_only/sam/static_sam.py:94-96,137-146) - same record / overflow layout as the device
 // ---------------------------------------------------------------------------------------
 namespace {
 
 struct HostSam {
-    int4 *states = nullptr;
+    int32_t *recs = nullptr;
     uint4 *slots = nullptr;
     int32_t *text = nullptr;
     uint64_t s_cap = 0, h_cap = 0;
     uint32_t bmask = 0;
-    int64_t n_states = 1, n = 0, n_edges = 0, n_clones = 0;
+    int64_t n_states = 1, n = 0, n_edges = 0, n_clones = 0, n_ovf = 0;
     int last = 0;
     std::vector<uint8_t> is_clone;
 
-    bool probe(uint32_t state, uint32_t tok, uint32_t &slot) const {
+    int32_t *rec(int64_t v) const { return recs + (size_t)v * SAMD_REC; }
+
+    // overflow table: found -> slot of the edge; else slot = first free slot of the probe sequence
+    bool ovf_find(uint32_t state, uint32_t tok, uint32_t &slot) const {
         uint32_t b = samd_hash(state, tok) & bmask;
         for (;;) {
             const uint4 *bk = slots + (size_t)b * SAMD_BUCKET;
@@ -41,55 +44,72 @@ struct HostSam {
             b = (b + 1) & bmask;
         }
     }
-    void add_edge(int state, int tok, int target) {
+    // pointer to the target word of edge (state, tok), or nullptr
+    int32_t *find(int state, int tok) const {
+        int32_t *r = rec(state);
+        for (int i = 0; i < SAMD_INLINE; ++i) {
+            if (r[R_TOK + i] == tok) return r + R_TGT + i;
+            if ((uint32_t)r[R_TOK + i] == SAMD_EMPTY) return nullptr;     // inline fills in order, overflow only after
+        }
+        if ((uint32_t)r[R_OHEAD] == SAMD_NIL) return nullptr;
         uint32_t slot;
-        probe((uint32_t)state, (uint32_t)tok, slot);
-        slots[slot] = make_uint4((uint32_t)state, (uint32_t)tok, (uint32_t)target, (uint32_t)states[state].w);
-        states[state].w = (int)slot;
+        if (!ovf_find((uint32_t)state, (uint32_t)tok, slot)) return nullptr;
+        return reinterpret_cast<int32_t *>(&slots[slot].z);
+    }
+    void add_edge(int state, int tok, int target) {
+        int32_t *r = rec(state);
         n_edges++;
+        for (int i = 0; i < SAMD_INLINE; ++i)
+            if ((uint32_t)r[R_TOK + i] == SAMD_EMPTY) {
+                r[R_TOK + i] = tok;
+                r[R_TGT + i] = target;
+                return;
+            }
+        uint32_t slot;
+        ovf_find((uint32_t)state, (uint32_t)tok, slot);
+        slots[slot] = make_uint4((uint32_t)state, (uint32_t)tok, (uint32_t)target, SAMD_NIL);
+        if ((uint32_t)r[R_OTAIL] != SAMD_NIL) slots[(uint32_t)r[R_OTAIL]].w = slot;
+        else r[R_OHEAD] = (int32_t)slot;
+        r[R_OTAIL] = (int32_t)slot;
+        n_ovf++;
+    }
+    template <class F>
+    void for_each_edge(int64_t v, F f) const {
+        const int32_t *r = rec(v);
+        for (int i = 0; i < SAMD_INLINE && (uint32_t)r[R_TOK + i] != SAMD_EMPTY; ++i) f(r[R_TOK + i], r[R_TGT + i]);
+        for (uint32_t e = (uint32_t)r[R_OHEAD]; e != SAMD_NIL; e = slots[e].w) f((int32_t)slots[e].y, (int32_t)slots[e].z);
     }
     void append(int tok) {
         n += 1;
         const int cur = (int)n_states++;
-        states[cur] = make_int4(-1, (int)n, (int)n, (int)SAMD_NIL);
+        samd_init_rec(rec(cur), -1, (int)n, (int)n);
         is_clone.push_back(0);
         text[n] = tok;
         int p = last;
-        uint32_t slot = 0;
-        while (p != -1 && !probe((uint32_t)p, (uint32_t)tok, slot)) {
-            slots[slot] = make_uint4((uint32_t)p, (uint32_t)tok, (uint32_t)cur, (uint32_t)states[p].w);
-            states[p].w = (int)slot;
-            n_edges++;
-            p = states[p].x;
+        int32_t *hit = nullptr;
+        while (p != -1 && !(hit = find(p, tok))) {
+            add_edge(p, tok, cur);
+            p = rec(p)[R_LINK];
         }
         if (p == -1) {
-            states[cur].x = 0;
+            rec(cur)[R_LINK] = 0;
         } else {
-            const int q = (int)slots[slot].z;
-            if (states[p].y + 1 == states[q].y) {
-                states[cur].x = q;
+            const int q = *hit;
+            if (rec(p)[R_LEN] + 1 == rec(q)[R_LEN]) {
+                rec(cur)[R_LINK] = q;
             } else {
                 const int clone = (int)n_states++;
                 n_clones++;
                 is_clone.push_back(1);
-                states[clone] = make_int4(states[q].x, states[p].y + 1, states[q].z, (int)SAMD_NIL);
-                // copy q's edges oldest-first so that the clone keeps q's insertion order
-                uint32_t chain[64];
-                std::vector<uint32_t> big;
-                int cnt = 0;
-                for (uint32_t e = (uint32_t)states[q].w; e != SAMD_NIL; e = slots[e].w) {
-                    if (cnt < 64) chain[cnt] = e;
-                    else big.push_back(e);
-                    cnt++;
+                // the clone keeps q's link, min_endpos and edges (in q's insertion order)
+                samd_init_rec(rec(clone), rec(q)[R_LINK], rec(p)[R_LEN] + 1, rec(q)[R_END]);
+                for_each_edge(q, [&](int32_t t, int32_t g) { add_edge(clone, t, g); });
+                while (p != -1 && (hit = find(p, tok)) && *hit == q) {
+                    *hit = clone;
+                    p = rec(p)[R_LINK];
                 }
-                for (int i = (int)big.size() - 1; i >= 0; --i) add_edge(clone, (int)slots[big[i]].y, (int)slots[big[i]].z);
-                for (int i = std::min(cnt, 64) - 1; i >= 0; --i) add_edge(clone, (int)slots[chain[i]].y, (int)slots[chain[i]].z);
-                while (p != -1 && probe((uint32_t)p, (uint32_t)tok, slot) && (int)slots[slot].z == q) {
-                    slots[slot].z = (uint32_t)clone;
-                    p = states[p].x;
-                }
-                states[q].x = clone;
-                states[cur].x = clone;
+                rec(q)[R_LINK] = clone;
+                rec(cur)[R_LINK] = clone;
             }
         }
         last = cur;
@@ -98,12 +118,12 @@ struct HostSam {
 
 void free_handle(samd_static_s *h) {
     if (!h) return;
-    cudaFree((void *)h->dev.states);
+    cudaFree((void *)h->dev.recs);
     cudaFree((void *)h->dev.slots);
     cudaFree((void *)h->dev.text);
     cudaFree((void *)h->dev.occ);
     cudaFree((void *)h->dev.topk);
-    free(h->h_states);
+    free(h->h_recs);
     free(h->h_slots);
     free(h->h_text);
     free(h->h_occ);
@@ -115,9 +135,9 @@ int upload(samd_static_s *h) {
     StaticDev &d = h->dev;
     SAMD_CUDA(cudaGetDevice(&h->device));
     void *p = nullptr;
-    SAMD_CUDA(cudaMalloc(&p, (size_t)d.n_states * sizeof(int4)));
-    d.states = (const int4 *)p;
-    SAMD_CUDA(cudaMemcpy(p, h->h_states, (size_t)d.n_states * sizeof(int4), cudaMemcpyHostToDevice));
+    SAMD_CUDA(cudaMalloc(&p, (size_t)d.n_states * SAMD_REC * sizeof(int32_t)));
+    d.recs = (const int32_t *)p;
+    SAMD_CUDA(cudaMemcpy(p, h->h_recs, (size_t)d.n_states * SAMD_REC * sizeof(int32_t), cudaMemcpyHostToDevice));
     SAMD_CUDA(cudaMalloc(&p, (size_t)d.n_slots * sizeof(uint4)));
     d.slots = (const uint4 *)p;
     SAMD_CUDA(cudaMemcpy(p, h->h_slots, (size_t)d.n_slots * sizeof(uint4), cudaMemcpyHostToDevice));
@@ -135,6 +155,98 @@ int upload(samd_static_s *h) {
     return 0;
 }
 
+// Move a finished HostSam into a handle: records trimmed, overflow table re-hashed to its final
+// (small) power-of-two size, optional top-k table from the counts.
+samd_static_s *finish(HostSam &b, const int32_t *counts, bool with_counts) {
+    samd_static_s *h = new samd_static_s();
+    memset(h, 0, sizeof(*h));
+    const int64_t ns = b.n_states;
+    uint64_t cap = samd_next_pow2(2 * (uint64_t)b.n_ovf + 64);
+    uint4 *nsl = (uint4 *)malloc(cap * sizeof(uint4));
+    memset(nsl, 0xFF, cap * sizeof(uint4));
+    const uint32_t nmask = (uint32_t)(cap / SAMD_BUCKET - 1);
+    for (int64_t v = 0; v < ns; ++v) {
+        int32_t *r = b.rec(v);
+        uint32_t head = SAMD_NIL, tail = SAMD_NIL;
+        for (uint32_t e = (uint32_t)r[R_OHEAD]; e != SAMD_NIL; e = b.slots[e].w) {
+            const uint4 ed = b.slots[e];
+            uint32_t bk = samd_hash((uint32_t)v, ed.y) & nmask, slot = 0;
+            for (bool placed = false; !placed; bk = (bk + 1) & nmask)
+                for (int l = 0; l < SAMD_BUCKET && !placed; ++l)
+                    if (nsl[(size_t)bk * SAMD_BUCKET + l].x == SAMD_EMPTY) {
+                        slot = bk * SAMD_BUCKET + l;
+                        placed = true;
+                    }
+            nsl[slot] = make_uint4((uint32_t)v, ed.y, ed.z, SAMD_NIL);
+            if (tail != SAMD_NIL) nsl[tail].w = slot;
+            else head = slot;
+            tail = slot;
+        }
+        r[R_OHEAD] = (int32_t)head;
+        r[R_OTAIL] = (int32_t)tail;
+    }
+    free(b.slots);
+    b.slots = nsl;
+    b.h_cap = cap;
+    b.bmask = nmask;
+    h->h_recs = (int32_t *)realloc(b.recs, (size_t)ns * SAMD_REC * sizeof(int32_t));
+    b.recs = h->h_recs;
+    h->h_slots = nsl;
+    h->h_text = b.text;
+    h->n_edges = b.n_edges;
+    h->n_clones = b.n_clones;
+    h->n_ovf = b.n_ovf;
+    h->with_counts = with_counts;
+    h->dev.n_states = ns;
+    h->dev.n_slots = (int64_t)cap;
+    h->dev.n_tokens = b.n;
+    h->dev.bmask = nmask;
+    if (with_counts) {
+        h->h_occ = (int32_t *)calloc((size_t)ns, sizeof(int32_t));
+        if (counts) {
+            memcpy(h->h_occ, counts, (size_t)ns * sizeof(int32_t));
+        } else {
+            // |endpos| by accumulation up the link tree in decreasing-length order (counting sort); equals the
+            // reference's running count (clone inherits q's count, then every state on the new suffix path +1)
+            std::vector<int32_t> order((size_t)ns), bucket((size_t)b.n + 2, 0);
+            for (int64_t v = 0; v < ns; ++v) bucket[(size_t)b.rec(v)[R_LEN] + 1]++;
+            for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
+            for (int64_t v = 0; v < ns; ++v) order[(size_t)bucket[(size_t)b.rec(v)[R_LEN]]++] = (int32_t)v;
+            for (int64_t v = 1; v < ns; ++v) h->h_occ[v] = b.is_clone[(size_t)v] ? 0 : 1;
+            for (int64_t i = ns - 1; i > 0; --i) {
+                const int v = order[(size_t)i];
+                const int l = b.rec(v)[R_LINK];
+                if (l > 0) h->h_occ[l] += h->h_occ[v];
+            }
+        }
+        h->h_topk = (int2 *)malloc((size_t)ns * 8 * sizeof(int2));
+        std::vector<int2> edges;
+        for (int64_t v = 0; v < ns; ++v) {
+            edges.clear();
+            b.for_each_edge(v, [&](int32_t t, int32_t g) { edges.push_back(make_int2(t, g)); });   // dict insertion order
+            std::stable_sort(edges.begin(), edges.end(),
+                             [&](const int2 &x, const int2 &y) { return h->h_occ[x.y] > h->h_occ[y.y]; });
+            for (int j = 0; j < 8; ++j)
+                h->h_topk[(size_t)v * 8 + j] = j < (int)edges.size() ? edges[(size_t)j] : make_int2(-1, -1);
+        }
+    }
+    return h;
+}
+
+int alloc_host(HostSam &b, uint64_t n_states_cap, uint64_t n_tokens, uint64_t ovf_cap) {
+    b.s_cap = n_states_cap;
+    b.h_cap = ovf_cap;
+    b.bmask = (uint32_t)(b.h_cap / SAMD_BUCKET - 1);
+    b.recs = (int32_t *)malloc(b.s_cap * SAMD_REC * sizeof(int32_t));
+    b.slots = (uint4 *)malloc(b.h_cap * sizeof(uint4));
+    b.text = (int32_t *)calloc((size_t)n_tokens + 1, sizeof(int32_t));
+    SAMD_REQUIRE(b.recs && b.slots && b.text, "static SAM: host allocation failed");
+    memset(b.slots, 0xFF, b.h_cap * sizeof(uint4));
+    samd_init_rec(b.rec(0), -1, 0, 0);
+    b.text[0] = -1;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" int samd_static_build_host(const int32_t *docs, const int64_t *offs, int64_t n_docs, int32_t eos, int with_counts,
@@ -148,68 +260,27 @@ extern "C" int samd_static_build_host(const int32_t *docs, const int64_t *offs, 
     }
     SAMD_REQUIRE(total < (int64_t)1 << 30, "samd_static_build: corpus too large for one shard (>= 2^30 tokens)");
     HostSam b;
-    b.s_cap = 2 * (uint64_t)total + 2;
-    b.h_cap = samd_table_slots((uint64_t)total);
-    b.bmask = (uint32_t)(b.h_cap / SAMD_BUCKET - 1);
-    b.states = (int4 *)malloc(b.s_cap * sizeof(int4));
-    b.slots = (uint4 *)malloc(b.h_cap * sizeof(uint4));
-    b.text = (int32_t *)malloc((size_t)(total + 1) * sizeof(int32_t));
-    SAMD_REQUIRE(b.states && b.slots && b.text, "samd_static_build: host allocation failed");
-    memset(b.slots, 0xFF, b.h_cap * sizeof(uint4));
-    b.states[0] = make_int4(-1, 0, 0, (int)SAMD_NIL);
-    b.text[0] = -1;
+    // overflow edges are rare (only states with > 5 out-edges): start at n/2 slots... but never re-hash
+    // mid-build, so size for the worst case the corpus allows: edges <= 3n, all of them could overflow
+    // only in adversarial inputs; n slots (load <= ~0.5 in practice) with a hard check below.
+    int rc = alloc_host(b, 2 * (uint64_t)total + 2, (uint64_t)total, samd_table_slots((uint64_t)total));
+    if (rc) return rc;
     b.is_clone.reserve(b.s_cap);
     b.is_clone.push_back(0);
     for (int64_t d = 0; d < n_docs; ++d) {
-        for (int64_t i = offs[d]; i < offs[d + 1]; ++i) b.append(docs[i]);
+        for (int64_t i = offs[d]; i < offs[d + 1]; ++i) {
+            SAMD_REQUIRE(docs[i] >= 0, "samd_static_build: token ids must be non-negative");
+            b.append(docs[i]);
+        }
         if (docs[offs[d + 1] - 1] != eos) b.append(eos);
     }
-    samd_static_s *h = new samd_static_s();
-    memset(h, 0, sizeof(*h));
-    h->h_states = (int4 *)realloc(b.states, (size_t)b.n_states * sizeof(int4));
-    h->h_slots = b.slots;
-    h->h_text = b.text;
-    h->n_edges = b.n_edges;
-    h->n_clones = b.n_clones;
-    h->with_counts = with_counts != 0;
-    h->dev.n_states = b.n_states;
-    h->dev.n_slots = (int64_t)b.h_cap;
-    h->dev.n_tokens = b.n;
-    h->dev.bmask = b.bmask;
-    if (with_counts) {
-        const int64_t ns = b.n_states;
-        h->h_occ = (int32_t *)calloc((size_t)ns, sizeof(int32_t));
-        // |endpos| by accumulation up the link tree in decreasing-length order (counting sort)
-        std::vector<int32_t> order((size_t)ns), bucket((size_t)b.n + 2, 0);
-        for (int64_t v = 0; v < ns; ++v) bucket[(size_t)h->h_states[v].y + 1]++;
-        for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
-        for (int64_t v = 0; v < ns; ++v) order[(size_t)bucket[(size_t)h->h_states[v].y]++] = (int32_t)v;
-        for (int64_t v = 1; v < ns; ++v) h->h_occ[v] = b.is_clone[(size_t)v] ? 0 : 1;
-        for (int64_t i = ns - 1; i > 0; --i) {
-            const int v = order[(size_t)i];
-            const int l = h->h_states[v].x;
-            if (l > 0) h->h_occ[l] += h->h_occ[v];
-        }
-        h->h_topk = (int2 *)malloc((size_t)ns * 8 * sizeof(int2));
-        std::vector<int2> edges;
-        for (int64_t v = 0; v < ns; ++v) {
-            edges.clear();
-            for (uint32_t e = (uint32_t)h->h_states[v].w; e != SAMD_NIL; e = h->h_slots[e].w)
-                edges.push_back(make_int2((int)h->h_slots[e].y, (int)h->h_slots[e].z));
-            std::reverse(edges.begin(), edges.end());                 // oldest first = dict insertion order
-            std::stable_sort(edges.begin(), edges.end(),
-                             [&](const int2 &x, const int2 &y) { return h->h_occ[x.y] > h->h_occ[y.y]; });
-            for (int j = 0; j < 8; ++j)
-                h->h_topk[(size_t)v * 8 + j] = j < (int)edges.size() ? edges[(size_t)j] : make_int2(-1, -1);
-        }
-    }
-    *out = h;
+    *out = finish(b, nullptr, with_counts != 0);
     return 0;
 }
 
 extern "C" int samd_static_upload(samd_static_t h) {
-    SAMD_REQUIRE(h && h->h_states, "samd_static_upload: no host automaton");
-    SAMD_REQUIRE(!h->dev.states, "samd_static_upload: already on the device");
+    SAMD_REQUIRE(h && h->h_recs, "samd_static_upload: no host automaton");
+    SAMD_REQUIRE(!h->dev.recs, "samd_static_upload: already on the device");
     return upload(h);
 }
 
@@ -234,65 +305,34 @@ extern "C" int samd_static_from_arrays(int64_t n_states, const int32_t *link, co
     SAMD_REQUIRE(n_states > 0 && link && length && n_edges >= 0 && (n_edges == 0 || edges) && out,
                  "samd_static_from_arrays: bad arguments");
     SAMD_REQUIRE(endpos || count, "samd_static_from_arrays: need min_endpos (samd) or cnt_endpos (samd_sam_only)");
-    samd_static_s *h = new samd_static_s();
-    memset(h, 0, sizeof(*h));
-    const uint64_t h_cap = std::max<uint64_t>(samd_table_slots((uint64_t)n_tokens), samd_next_pow2(2 * (uint64_t)n_edges + 64));
     HostSam b;
-    b.h_cap = h_cap;
-    b.bmask = (uint32_t)(h_cap / SAMD_BUCKET - 1);
-    b.states = (int4 *)malloc((size_t)n_states * sizeof(int4));
-    b.slots = (uint4 *)malloc(h_cap * sizeof(uint4));
-    b.text = (int32_t *)calloc((size_t)n_tokens + 1, sizeof(int32_t));
-    SAMD_REQUIRE(b.states && b.slots && b.text, "samd_static_from_arrays: host allocation failed");
-    memset(b.slots, 0xFF, h_cap * sizeof(uint4));
-    for (int64_t v = 0; v < n_states; ++v) b.states[v] = make_int4(link[v], length[v], endpos ? endpos[v] : 0, (int)SAMD_NIL);
-    b.text[0] = -1;
+    int rc = alloc_host(b, (uint64_t)n_states, (uint64_t)n_tokens, samd_next_pow2(2 * (uint64_t)n_edges + 64));
+    if (rc) return rc;
+    for (int64_t v = 0; v < n_states; ++v) samd_init_rec(b.rec(v), link[v], length[v], endpos ? endpos[v] : 0);
     if (text)
         for (int64_t i = 1; i <= n_tokens; ++i) b.text[i] = text[i];
     for (int64_t e = 0; e < n_edges; ++e) b.add_edge(edges[3 * e], edges[3 * e + 1], edges[3 * e + 2]);
-    h->h_states = b.states;
-    h->h_slots = b.slots;
-    h->h_text = b.text;
-    h->n_edges = n_edges;
-    h->with_counts = count != nullptr;
-    h->dev.n_states = n_states;
-    h->dev.n_slots = (int64_t)h_cap;
-    h->dev.n_tokens = n_tokens;
-    h->dev.bmask = b.bmask;
-    if (count) {
-        h->h_occ = (int32_t *)malloc((size_t)n_states * sizeof(int32_t));
-        memcpy(h->h_occ, count, (size_t)n_states * sizeof(int32_t));
-        h->h_topk = (int2 *)malloc((size_t)n_states * 8 * sizeof(int2));
-        std::vector<int2> ed;
-        for (int64_t v = 0; v < n_states; ++v) {
-            ed.clear();
-            for (uint32_t e = (uint32_t)h->h_states[v].w; e != SAMD_NIL; e = h->h_slots[e].w)
-                ed.push_back(make_int2((int)h->h_slots[e].y, (int)h->h_slots[e].z));
-            std::reverse(ed.begin(), ed.end());
-            std::stable_sort(ed.begin(), ed.end(), [&](const int2 &x, const int2 &y) { return h->h_occ[x.y] > h->h_occ[y.y]; });
-            for (int j = 0; j < 8; ++j) h->h_topk[(size_t)v * 8 + j] = j < (int)ed.size() ? ed[(size_t)j] : make_int2(-1, -1);
-        }
-    }
-    *out = h;
+    b.n_states = n_states;
+    b.n = n_tokens;
+    *out = finish(b, count, count != nullptr);
     return 0;
 }
 
 // edges as (state, token, target) triples, per state oldest-first; text[0..n_tokens]
 extern "C" int samd_static_export_edges(samd_static_t h, int32_t *edges_host, int32_t *text_host) {
-    SAMD_REQUIRE(h && h->h_states, "samd_static_export_edges: no host mirror");
+    SAMD_REQUIRE(h && h->h_recs, "samd_static_export_edges: no host mirror");
     if (edges_host) {
+        HostSam b;
+        b.recs = h->h_recs;
+        b.slots = h->h_slots;
         int64_t k = 0;
-        for (int64_t v = 0; v < h->dev.n_states; ++v) {
-            const int64_t first = k;
-            for (uint32_t e = (uint32_t)h->h_states[v].w; e != SAMD_NIL; e = h->h_slots[e].w) {
+        for (int64_t v = 0; v < h->dev.n_states; ++v)
+            b.for_each_edge(v, [&](int32_t t, int32_t g) {
                 edges_host[3 * k] = (int32_t)v;
-                edges_host[3 * k + 1] = (int32_t)h->h_slots[e].y;
-                edges_host[3 * k + 2] = (int32_t)h->h_slots[e].z;
+                edges_host[3 * k + 1] = t;
+                edges_host[3 * k + 2] = g;
                 k++;
-            }
-            for (int64_t i = first, j = k - 1; i < j; ++i, --j)
-                for (int c = 0; c < 3; ++c) std::swap(edges_host[3 * i + c], edges_host[3 * j + c]);
-        }
+            });
     }
     if (text_host) memcpy(text_host, h->h_text, (size_t)(h->dev.n_tokens + 1) * sizeof(int32_t));
     return 0;
@@ -309,21 +349,22 @@ extern "C" int samd_static_info(samd_static_t h, int64_t *info) {
     info[1] = h->n_edges;
     info[2] = h->dev.n_tokens;
     info[3] = h->dev.n_slots;
-    info[4] = h->dev.n_states * 16 + h->dev.n_slots * 16 + (h->dev.n_tokens + 1) * 4 +
+    info[4] = h->dev.n_states * 64 + h->dev.n_slots * 16 + (h->dev.n_tokens + 1) * 4 +
               (h->with_counts ? h->dev.n_states * (4 + 64) : 0);
     info[5] = h->with_counts;
     info[6] = h->n_clones;
-    info[7] = 0;
+    info[7] = h->n_ovf;
     return 0;
 }
 
 extern "C" int samd_static_export(samd_static_t h, int32_t *link, int32_t *length, int32_t *endpos, int32_t *count,
                                   int32_t *topk) {
-    SAMD_REQUIRE(h && h->h_states, "samd_static_export: no host mirror");
+    SAMD_REQUIRE(h && h->h_recs, "samd_static_export: no host mirror");
     for (int64_t v = 0; v < h->dev.n_states; ++v) {
-        if (link) link[v] = h->h_states[v].x;
-        if (length) length[v] = h->h_states[v].y;
-        if (endpos) endpos[v] = h->h_states[v].z;
+        const int32_t *r = h->h_recs + (size_t)v * SAMD_REC;
+        if (link) link[v] = r[R_LINK];
+        if (length) length[v] = r[R_LEN];
+        if (endpos) endpos[v] = r[R_END];
     }
     if (count) {
         SAMD_REQUIRE(h->h_occ, "samd_static_export: automaton built without counts");
@@ -336,17 +377,18 @@ extern "C" int samd_static_export(samd_static_t h, int32_t *link, int32_t *lengt
     return 0;
 }
 
-// flat file: header (8 x int64) then states, slots, text, [occ, topk]
+// flat file: header (8 x int64) then records, overflow slots, text, [occ, topk]
 static const int64_t kMagic = 0x30304232444d4153ll;   // "SAMD2B00"
+static const int64_t kFormat = 2;                      // 64-byte records with inline edges
 
 extern "C" int samd_static_save(samd_static_t h, const char *path) {
-    SAMD_REQUIRE(h && path && h->h_states, "samd_static_save: bad arguments");
+    SAMD_REQUIRE(h && path && h->h_recs, "samd_static_save: bad arguments");
     FILE *f = fopen(path, "wb");
     SAMD_REQUIRE(f, "samd_static_save: cannot open file");
-    int64_t hdr[8] = {kMagic, SAMD_ABI_VERSION, h->dev.n_states, h->dev.n_slots, h->dev.n_tokens, h->n_edges,
-                      h->with_counts, h->n_clones};
+    int64_t hdr[8] = {kMagic, kFormat, h->dev.n_states, h->dev.n_slots, h->dev.n_tokens, h->n_edges,
+                      h->with_counts | (h->n_ovf << 8), h->n_clones};
     bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1;
-    ok = ok && fwrite(h->h_states, sizeof(int4), (size_t)h->dev.n_states, f) == (size_t)h->dev.n_states;
+    ok = ok && fwrite(h->h_recs, SAMD_REC * sizeof(int32_t), (size_t)h->dev.n_states, f) == (size_t)h->dev.n_states;
     ok = ok && fwrite(h->h_slots, sizeof(uint4), (size_t)h->dev.n_slots, f) == (size_t)h->dev.n_slots;
     ok = ok && fwrite(h->h_text, sizeof(int32_t), (size_t)h->dev.n_tokens + 1, f) == (size_t)h->dev.n_tokens + 1;
     if (h->with_counts) {
@@ -363,9 +405,9 @@ static int load_impl(const char *path, samd_static_t *out, bool to_device) {
     FILE *f = fopen(path, "rb");
     SAMD_REQUIRE(f, "samd_static_load: cannot open file");
     int64_t hdr[8];
-    if (fread(hdr, sizeof(hdr), 1, f) != 1 || hdr[0] != kMagic || hdr[1] != SAMD_ABI_VERSION) {
+    if (fread(hdr, sizeof(hdr), 1, f) != 1 || hdr[0] != kMagic || hdr[1] != kFormat) {
         fclose(f);
-        samd_set_error("samd_static_load: not a samd_b200 automaton file (or ABI mismatch)");
+        samd_set_error("samd_static_load: not a samd_b200 automaton file (or format mismatch)");
         return 2;
     }
     samd_static_s *h = new samd_static_s();
@@ -374,14 +416,15 @@ static int load_impl(const char *path, samd_static_t *out, bool to_device) {
     h->dev.n_slots = hdr[3];
     h->dev.n_tokens = hdr[4];
     h->n_edges = hdr[5];
-    h->with_counts = (int)hdr[6];
+    h->with_counts = (int)(hdr[6] & 0xFF);
+    h->n_ovf = hdr[6] >> 8;
     h->n_clones = hdr[7];
     h->dev.bmask = (uint32_t)(h->dev.n_slots / SAMD_BUCKET - 1);
-    h->h_states = (int4 *)malloc((size_t)h->dev.n_states * sizeof(int4));
+    h->h_recs = (int32_t *)malloc((size_t)h->dev.n_states * SAMD_REC * sizeof(int32_t));
     h->h_slots = (uint4 *)malloc((size_t)h->dev.n_slots * sizeof(uint4));
     h->h_text = (int32_t *)malloc((size_t)(h->dev.n_tokens + 1) * sizeof(int32_t));
-    bool ok = h->h_states && h->h_slots && h->h_text;
-    ok = ok && fread(h->h_states, sizeof(int4), (size_t)h->dev.n_states, f) == (size_t)h->dev.n_states;
+    bool ok = h->h_recs && h->h_slots && h->h_text;
+    ok = ok && fread(h->h_recs, SAMD_REC * sizeof(int32_t), (size_t)h->dev.n_states, f) == (size_t)h->dev.n_states;
     ok = ok && fread(h->h_slots, sizeof(uint4), (size_t)h->dev.n_slots, f) == (size_t)h->dev.n_slots;
     ok = ok && fread(h->h_text, sizeof(int32_t), (size_t)h->dev.n_tokens + 1, f) == (size_t)h->dev.n_tokens + 1;
     if (ok && h->with_counts) {
@@ -418,14 +461,15 @@ extern "C" int samd_static_set_l2_window(samd_static_t h, void *stream, int64_t 
         SAMD_CUDA(cudaCtxResetPersistingL2Cache());
         return 0;
     }
+    SAMD_REQUIRE(h->dev.recs, "samd_static_set_l2_window: automaton is not on the device");
     cudaDeviceProp prop;
     SAMD_CUDA(cudaGetDeviceProperties(&prop, h->device));
     size_t carve = std::min((size_t)bytes, (size_t)prop.persistingL2CacheMaxSize);
     SAMD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
-    // state records are contiguous and come first in creation (= document) order; the window
-    // covers their prefix.  hitRatio scales the window down to the carve-out.
-    size_t span = std::min((size_t)h->dev.n_states * sizeof(int4), (size_t)prop.accessPolicyMaxWindowSize);
-    attr.accessPolicyWindow.base_ptr = (void *)h->dev.states;
+    // state records are contiguous in creation (= document) order; the window covers their prefix
+    // (root + the states of the first documents).  hitRatio scales the window down to the carve-out.
+    size_t span = std::min((size_t)h->dev.n_states * SAMD_REC * sizeof(int32_t), (size_t)prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.base_ptr = (void *)h->dev.recs;
     attr.accessPolicyWindow.num_bytes = span;
     attr.accessPolicyWindow.hitRatio = span <= carve ? 1.0f : (float)((double)carve / (double)span);
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;

@@ -11,23 +11,25 @@
 // arena management
 // ---------------------------------------------------------------------------------------
 __global__ void dyn_reset_kernel(DynArena a, const uint8_t *mask) {
-    // one CTA per request: clear the edge table (0xFF = free), write the root and the meta block
+    // one CTA per request: clear the overflow table (0xFF = free), write the root and the meta block
     int r = blockIdx.x;
     if (mask && !mask[r]) return;
     uint4 *slots = a.slots + (size_t)r * a.h_cap;
     const uint4 e = make_uint4(SAMD_EMPTY, SAMD_EMPTY, SAMD_EMPTY, SAMD_EMPTY);
     for (uint32_t i = threadIdx.x; i < a.h_cap; i += blockDim.x) slots[i] = e;
+    if (threadIdx.x < SAMD_REC) {
+        // root (dyn_sam.py:19): link -1, length 0, min_endpos 0, no edges
+        const int t = threadIdx.x;
+        int v = 0;
+        if (t == R_LINK || t == R_OHEAD || t == R_OTAIL || (t >= R_TOK && t < R_TOK + SAMD_INLINE)) v = -1;
+        a.recs[(size_t)r * a.s_cap * SAMD_REC + t] = v;
+    }
     if (threadIdx.x == 0) {
-        a.states[(size_t)r * a.s_cap] = make_int4(-1, 0, 0, (int)SAMD_NIL);   // root (dyn_sam.py:19)
         a.text[(size_t)r * a.t_cap] = -1;                                       // sentinel (dyn_sam.py:20)
         int32_t *m = a.meta + (size_t)r * META_WORDS;
+        for (int i = 0; i < META_WORDS; ++i) m[i] = 0;
         m[META_NSTATES] = 1;
-        m[META_LAST] = 0;
-        m[META_N] = 0;
-        m[META_CUR] = 0;
-        m[META_CURLEN] = 0;
-        m[META_NEDGES] = 0;
-        for (int i = META_OVERFLOW; i < META_WORDS; ++i) m[i] = 0;
+        m[META_LASTLINK] = -1;
     }
 }
 
@@ -43,22 +45,22 @@ extern "C" int samd_dyn_create(int n_requests, int max_tokens, samd_dyn_t *out) 
     a.t_cap = ((uint32_t)max_tokens + 1u + 3u) & ~3u;
     a.bmask = a.h_cap / SAMD_BUCKET - 1u;
     SAMD_CUDA(cudaGetDevice(&h->device));
-    size_t b_states = (size_t)n_requests * a.s_cap * sizeof(int4);
+    size_t b_recs = (size_t)n_requests * a.s_cap * SAMD_REC * sizeof(int32_t);
     size_t b_slots = (size_t)n_requests * a.h_cap * sizeof(uint4);
     size_t b_text = (size_t)n_requests * a.t_cap * sizeof(int32_t);
     size_t b_meta = (size_t)n_requests * META_WORDS * sizeof(int32_t);
-    SAMD_CUDA(cudaMalloc(&a.states, b_states));
+    SAMD_CUDA(cudaMalloc(&a.recs, b_recs));
     SAMD_CUDA(cudaMalloc(&a.slots, b_slots));
     SAMD_CUDA(cudaMalloc(&a.text, b_text));
     SAMD_CUDA(cudaMalloc(&a.meta, b_meta));
-    h->bytes = (int64_t)(b_states + b_slots + b_text + b_meta);
+    h->bytes = (int64_t)(b_recs + b_slots + b_text + b_meta);
     *out = h;
     return samd_dyn_reset(h, nullptr, nullptr);
 }
 
 extern "C" int samd_dyn_destroy(samd_dyn_t h) {
     if (!h) return 0;
-    cudaFree(h->a.states);
+    cudaFree(h->a.recs);
     cudaFree(h->a.slots);
     cudaFree(h->a.text);
     cudaFree(h->a.meta);
@@ -74,7 +76,7 @@ extern "C" int samd_dyn_copy(samd_dyn_t dst, samd_dyn_t src, void *stream) {
     const DynArena &s = src->a;
     const DynArena &d = dst->a;
     cudaStream_t st = (cudaStream_t)stream;
-    SAMD_CUDA(cudaMemcpyAsync(d.states, s.states, (size_t)s.n_requests * s.s_cap * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+    SAMD_CUDA(cudaMemcpyAsync(d.recs, s.recs, (size_t)s.n_requests * s.s_cap * SAMD_REC * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     SAMD_CUDA(cudaMemcpyAsync(d.slots, s.slots, (size_t)s.n_requests * s.h_cap * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
     SAMD_CUDA(cudaMemcpyAsync(d.text, s.text, (size_t)s.n_requests * s.t_cap * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     SAMD_CUDA(cudaMemcpyAsync(d.meta, s.meta, (size_t)s.n_requests * META_WORDS * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
@@ -122,13 +124,13 @@ extern "C" int samd_dyn_export(samd_dyn_t h, int request, int32_t *meta_host, in
     int ns = meta[META_NSTATES];
     if (link_host || length_host || endpos_host) {
         SAMD_REQUIRE(capacity >= ns, "samd_dyn_export: capacity too small");
-        int4 *tmp = (int4 *)malloc((size_t)ns * sizeof(int4));
-        SAMD_CUDA(cudaMemcpy(tmp, h->a.states + (size_t)request * h->a.s_cap, (size_t)ns * sizeof(int4),
+        int32_t *tmp = (int32_t *)malloc((size_t)ns * SAMD_REC * sizeof(int32_t));
+        SAMD_CUDA(cudaMemcpy(tmp, h->a.recs + (size_t)request * h->a.s_cap * SAMD_REC, (size_t)ns * SAMD_REC * sizeof(int32_t),
                              cudaMemcpyDeviceToHost));
         for (int i = 0; i < ns; ++i) {
-            if (link_host) link_host[i] = tmp[i].x;
-            if (length_host) length_host[i] = tmp[i].y;
-            if (endpos_host) endpos_host[i] = tmp[i].z;
+            if (link_host) link_host[i] = tmp[(size_t)i * SAMD_REC + R_LINK];
+            if (length_host) length_host[i] = tmp[(size_t)i * SAMD_REC + R_LEN];
+            if (endpos_host) endpos_host[i] = tmp[(size_t)i * SAMD_REC + R_END];
         }
         free(tmp);
     }
@@ -144,72 +146,126 @@ extern "C" int samd_dyn_export(samd_dyn_t h, int request, int32_t *meta_host, in
 // online append with clone-on-split (dyn_sam.py:41-67); registers are warp-uniform
 // ---------------------------------------------------------------------------------------
 struct DynRegs {
-    int n_states, last, n, cur, cur_len, n_edges, n_clones, hops;
+    int n_states, last, last_link, n, cur, cur_len, n_edges, n_clones, hops;
 };
 
-__device__ __forceinline__ void dyn_append(int4 *states, uint4 *slots, int32_t *text, uint32_t bmask, DynRegs &g, int tok,
+// add the out-edge state --tok--> target, given the (failed) look-up `r` of (state, tok)
+__device__ __forceinline__ void add_edge(int32_t *recs, uint4 *slots, uint32_t bmask, int state, int tok, int target, Look &r,
+                                         int lane) {
+    int32_t *rec = recs + (size_t)state * SAMD_REC;
+    const unsigned emp = __ballot_sync(SAMD_FULL, lane >= R_TOK && lane < R_TOK + SAMD_INLINE && (uint32_t)r.w == SAMD_EMPTY);
+    if (emp) {                                              // a free inline edge: two 4-byte stores
+        const int l = __ffs(emp) - 1;
+        if (lane == 0) {
+            rec[l] = tok;
+            rec[l + (R_TGT - R_TOK)] = target;
+        }
+        return;
+    }
+    if (!r.probed) ovf_probe(slots, bmask, (uint32_t)state, (uint32_t)tok, lane, false, r);
+    const uint32_t tail = (uint32_t)rec_word(r, R_OTAIL);
+    if (lane == 0) {
+        slots[r.slot] = make_uint4((uint32_t)state, (uint32_t)tok, (uint32_t)target, SAMD_NIL);
+        if (tail != SAMD_NIL) slots[tail].w = r.slot;     // append: lists run oldest -> newest
+        else rec[R_OHEAD] = (int)r.slot;
+        rec[R_OTAIL] = (int)r.slot;
+    }
+}
+
+__device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t *text, uint32_t bmask, DynRegs &g, int tok,
                                            int lane) {
     g.n += 1;
     const int cur = g.n_states++;
-    if (lane == 0) {
-        states[cur] = make_int4(-1, g.n, g.n, (int)SAMD_NIL);
-        text[g.n] = tok;
+    if (lane < SAMD_REC) {                                  // the new state's record: one 64-byte store
+        int v = 0;
+        if (lane == R_LINK || lane == R_OHEAD || lane == R_OTAIL || (lane >= R_TOK && lane < R_TOK + SAMD_INLINE)) v = -1;
+        if (lane == R_LEN || lane == R_END) v = g.n;
+        recs[(size_t)cur * SAMD_REC + lane] = v;
     }
-    __syncwarp();
+    if (lane == 0) text[g.n] = tok;
     int p = g.last;
     int link_cur = 0;
+    if (p != 0) {
+        // `last` was created by the previous append and has no out-edge yet (edges are only ever added
+        // along the suffix chain of the tail): write its first inline edge without reading anything.
+        if (lane == 0) {
+            recs[(size_t)p * SAMD_REC + R_TOK] = tok;
+            recs[(size_t)p * SAMD_REC + R_TGT] = cur;
+        }
+        g.n_edges++;
+        p = g.last_link;
+    }
+    __syncwarp();
     while (p != -1) {
-        Probe pr = warp_probe<true, false>(slots, bmask, states, (uint32_t)p, (uint32_t)tok, lane);
-        if (!pr.found) {
-            // p has no edge on tok: add p --tok--> cur at the free slot the probe ended on
-            if (lane == 0) {
-                slots[pr.slot] = make_uint4((uint32_t)p, (uint32_t)tok, (uint32_t)cur, (uint32_t)pr.rec.w);
-                reinterpret_cast<int32_t *>(states + p)[3] = (int)pr.slot;
-            }
+        Look r = warp_look<false>(recs, slots, bmask, p, tok, lane);
+        if (!r.found) {
+            add_edge(recs, slots, bmask, p, tok, cur, r, lane);
             g.n_edges++;
             __syncwarp();
-            p = pr.rec.x;
+            p = rec_word(r, R_LINK);
             continue;
         }
-        const int q = (int)pr.target;
-        const int4 rq = states[q];
-        if (pr.rec.y + 1 == rq.y) {
+        const int q = r.target;
+        int qw = 0;
+        if (lane < SAMD_REC) qw = recs[(size_t)q * SAMD_REC + lane];
+        const int len_p = rec_word(r, R_LEN);
+        if (len_p + 1 == __shfl_sync(SAMD_FULL, qw, R_LEN)) {
             link_cur = q;
         } else {
-            // clone-on-split: copy q's edges, link and min_endpos; length = len(p) + 1
+            // clone-on-split: the clone is q's record (inline edges, link, min_endpos) with length
+            // len(p)+1 - one 64-byte copy; q's overflow edges, if any, are re-inserted oldest first
             const int clone = g.n_states++;
             g.n_clones++;
-            uint32_t head_c = SAMD_NIL;
-            uint32_t e = (uint32_t)rq.w;
+            int cw = qw;
+            if (lane == R_LEN) cw = len_p + 1;
+            if (lane == R_OHEAD || lane == R_OTAIL) cw = -1;
+            if (lane < SAMD_REC) recs[(size_t)clone * SAMD_REC + lane] = cw;
+            g.n_edges += __popc(__ballot_sync(SAMD_FULL, lane >= R_TOK && lane < R_TOK + SAMD_INLINE && (uint32_t)qw != SAMD_EMPTY));
+            uint32_t e = (uint32_t)__shfl_sync(SAMD_FULL, qw, R_OHEAD);
+            uint32_t head_c = SAMD_NIL, tail_c = SAMD_NIL;
             while (e != SAMD_NIL) {
                 const uint4 se = slots[e];
                 if (lane == 0 && se.w != SAMD_NIL) asm volatile("prefetch.global.L1 [%0];" ::"l"(slots + se.w));
-                Probe pi = warp_probe<false, false>(slots, bmask, states, (uint32_t)clone, se.y, lane);
-                if (lane == 0) slots[pi.slot] = make_uint4((uint32_t)clone, se.y, se.z, head_c);
-                head_c = pi.slot;
+                Look f;
+                f.found = false;
+                ovf_probe(slots, bmask, (uint32_t)clone, se.y, lane, false, f);
+                if (lane == 0) {
+                    slots[f.slot] = make_uint4((uint32_t)clone, se.y, se.z, SAMD_NIL);
+                    if (tail_c != SAMD_NIL) slots[tail_c].w = f.slot;
+                }
+                if (head_c == SAMD_NIL) head_c = f.slot;
+                tail_c = f.slot;
                 g.n_edges++;
                 __syncwarp();
                 e = se.w;
             }
-            if (lane == 0) states[clone] = make_int4(rq.x, pr.rec.y + 1, rq.z, (int)head_c);
-            // redirect p's suffix chain from q to the clone
-            Probe cp = pr;
-            while (true) {
-                if (lane == 0) slots[cp.slot].z = (uint32_t)clone;
-                __syncwarp();
-                const int pp = cp.rec.x;
-                if (pp == -1) break;
-                cp = warp_probe<true, false>(slots, bmask, states, (uint32_t)pp, (uint32_t)tok, lane);
-                if (!(cp.found && (int)cp.target == q)) break;
+            if (lane == 0 && head_c != SAMD_NIL) {
+                recs[(size_t)clone * SAMD_REC + R_OHEAD] = (int)head_c;
+                recs[(size_t)clone * SAMD_REC + R_OTAIL] = (int)tail_c;
             }
-            if (lane == 0) reinterpret_cast<int32_t *>(states + q)[0] = clone;
+            // redirect p's suffix chain from q to the clone
+            Look cp = r;
+            int pp = p;
+            while (true) {
+                if (lane == 0) {
+                    if (cp.k >= 0) recs[(size_t)pp * SAMD_REC + R_TGT + cp.k] = clone;
+                    else slots[cp.slot].z = (uint32_t)clone;
+                }
+                __syncwarp();
+                pp = rec_word(cp, R_LINK);
+                if (pp == -1) break;
+                cp = warp_look<false>(recs, slots, bmask, pp, tok, lane);
+                if (!(cp.found && cp.target == q)) break;
+            }
+            if (lane == 0) recs[(size_t)q * SAMD_REC + R_LINK] = clone;
             link_cur = clone;
         }
         break;
     }
-    if (lane == 0) reinterpret_cast<int32_t *>(states + cur)[0] = link_cur;
+    if (lane == 0) recs[(size_t)cur * SAMD_REC + R_LINK] = link_cur;
     __syncwarp();
     g.last = cur;
+    g.last_link = link_cur;
 }
 
 struct StepParams {
@@ -231,7 +287,7 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
     const int r = blockIdx.x;
     const int lane = threadIdx.x;
     if (r >= P.dyn.n_requests) return;
-    int4 *states = P.dyn.states + (size_t)r * P.dyn.s_cap;
+    int32_t *recs = P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC;
     uint4 *slots = P.dyn.slots + (size_t)r * P.dyn.h_cap;
     int32_t *text = P.dyn.text + (size_t)r * P.dyn.t_cap;
     int32_t *meta = P.dyn.meta + (size_t)r * META_WORDS;
@@ -240,14 +296,15 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
     DynRegs g;
     {
         int m = (lane < META_WORDS) ? meta[lane] : 0;
-        g.hops = __shfl_sync(SAMD_FULL, m, META_HOPS);
         g.n_states = __shfl_sync(SAMD_FULL, m, META_NSTATES);
         g.last = __shfl_sync(SAMD_FULL, m, META_LAST);
+        g.last_link = __shfl_sync(SAMD_FULL, m, META_LASTLINK);
         g.n = __shfl_sync(SAMD_FULL, m, META_N);
         g.cur = __shfl_sync(SAMD_FULL, m, META_CUR);
         g.cur_len = __shfl_sync(SAMD_FULL, m, META_CURLEN);
         g.n_edges = __shfl_sync(SAMD_FULL, m, META_NEDGES);
         g.n_clones = __shfl_sync(SAMD_FULL, m, META_NCLONES);
+        g.hops = __shfl_sync(SAMD_FULL, m, META_HOPS);
     }
     int s_idx = 0, s_len = 0, s_hops = 0;
     if (P.has_static) {
@@ -260,42 +317,32 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
         const int k = P.counts ? P.counts[r] : P.token_stride;
         const int32_t *tk = P.tokens + (size_t)r * P.token_stride;
         bool overflow = false;
-        const int peek = P.start_tok ? P.start_tok[r] : -1;
+        prefetch_rec(recs, g.cur, lane);
+        if (P.has_static) prefetch_rec(P.st.recs, s_idx, lane);
         for (int i = 0; i < k; i += 32) {
             const int mine = (i + lane < k) ? tk[i + lane] : 0;     // coalesced token fetch
             const int lim = min(32, k - i);
-            if (i == 0) {                                           // first token: warm its cursor / tail probes
-                const int t0 = __shfl_sync(SAMD_FULL, mine, 0);
-                prefetch_probe(slots, bmask, states, (uint32_t)g.cur, (uint32_t)t0, lane);
-                prefetch_probe(slots, bmask, nullptr, (uint32_t)g.last, (uint32_t)t0, lane);
-                if (P.has_static) prefetch_probe(P.st.slots, P.st.bmask, P.st.states, (uint32_t)s_idx, (uint32_t)t0, lane);
-            }
             for (int j = 0; j < lim; ++j) {
                 const int tok = __shfl_sync(SAMD_FULL, mine, j);
-                const int nxt_in = __shfl_sync(SAMD_FULL, mine, (j + 1) & 31);
-                const int nxt = (j + 1 < lim) ? nxt_in : ((i + lim >= k) ? peek : -1);
                 if (g.n >= P.dyn.max_tokens) {
                     overflow = true;
                     break;
                 }
                 // add_tokens: match first, then append (dyn_sam.py:84-88); StaticSAM.transfer_tokens
                 // (static_sam.py:102-104) walks an independent structure, so it goes first too
-                warp_transfer<false>(slots, bmask, states, g.cur, g.cur_len, tok, lane, g.hops);
-                if (P.has_static) warp_transfer<true>(P.st.slots, P.st.bmask, P.st.states, s_idx, s_len, tok, lane, s_hops);
-                if (nxt >= 0) {
-                    // the next token's probes are known now: (cursor, nxt), (new tail = state about to be
-                    // created, nxt) and the static cursor's - fetch them while this token is appended
-                    prefetch_probe(slots, bmask, states, (uint32_t)g.cur, (uint32_t)nxt, lane);
-                    prefetch_probe(slots, bmask, nullptr, (uint32_t)g.n_states, (uint32_t)nxt, lane);
-                    if (P.has_static) prefetch_probe(P.st.slots, P.st.bmask, P.st.states, (uint32_t)s_idx, (uint32_t)nxt, lane);
-                }
-                dyn_append(states, slots, text, bmask, g, tok, lane);
+                warp_transfer<false>(recs, slots, bmask, g.cur, g.cur_len, tok, lane, g.hops);
+                if (P.has_static) warp_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, s_idx, s_len, tok, lane, s_hops);
+                // the records the NEXT token (or the final lookup) starts from are known now
+                prefetch_rec(recs, g.cur, lane);
+                if (P.has_static) prefetch_rec(P.st.recs, s_idx, lane);
+                dyn_append(recs, slots, text, bmask, g, tok, lane);
             }
             if (overflow) break;
         }
         if (lane == 0) {
             meta[META_NSTATES] = g.n_states;
             meta[META_LAST] = g.last;
+            meta[META_LASTLINK] = g.last_link;
             meta[META_N] = g.n;
             meta[META_CUR] = g.cur;
             meta[META_CURLEN] = g.cur_len;
@@ -315,12 +362,12 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
     const int tok = P.start_tok[r];
     int d_idx = g.cur, d_len = g.cur_len;
     int q_hops = 0;
-    warp_transfer<false>(slots, bmask, states, d_idx, d_len, tok, lane, q_hops);
+    warp_transfer<false>(recs, slots, bmask, d_idx, d_len, tok, lane, q_hops);
     int t_idx = 0, t_len = 0;
     if (P.has_static) {
         t_idx = s_idx;
         t_len = s_len;
-        warp_transfer<true>(P.st.slots, P.st.bmask, P.st.states, t_idx, t_len, tok, lane, s_hops);
+        warp_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, t_idx, t_len, tok, lane, s_hops);
     }
     const int t_biased = t_len - P.len_bias;
     int type, n_out, endpos = 0, text_n = 0;
@@ -332,11 +379,11 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
                 type = SAMD_DRAFT_DYN_SEQ;
                 // to_anc (dyn_sam.py:99-105)
                 int idx = d_idx;
-                int4 rec = states[idx];
+                int4 rec = *reinterpret_cast<const int4 *>(recs + (size_t)idx * SAMD_REC);
                 if (idx != 0) {
                     while (rec.x != 0 && P.n_predicts > g.n - rec.z) {
                         idx = rec.x;
-                        rec = states[idx];
+                        rec = *reinterpret_cast<const int4 *>(recs + (size_t)idx * SAMD_REC);
                     }
                 }
                 endpos = rec.z;
@@ -344,7 +391,7 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
                 text_n = g.n;
             } else {
                 type = SAMD_DRAFT_STATIC_SEQ;
-                endpos = __ldg(P.st.states + t_idx).z;
+                endpos = __ldg(P.st.recs + (size_t)t_idx * SAMD_REC + R_END);
                 src = P.st.text;
                 text_n = (int)P.st.n_tokens;
             }
@@ -356,7 +403,7 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
         if (d_len >= t_biased) {
             type = SAMD_DRAFT_DYN_SEQ;
             const int budget = min(P.n_predicts, 1 + (int)((double)d_len * P.alpha));
-            endpos = states[d_idx].z;
+            endpos = recs[(size_t)d_idx * SAMD_REC + R_END];
             src = text;
             text_n = g.n;
             // [start] + text[e+1 : e+n]  (no padding; samd_sam_only/sam/dyn_sam.py:116-119)
@@ -396,6 +443,7 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     SAMD_REQUIRE(a && a->dyn, "samd_step: dyn handle required");
     SAMD_REQUIRE((a->stat == nullptr) == (a->static_cursor_dev == nullptr),
                  "samd_step: static handle and static cursor must be given together");
+    SAMD_REQUIRE(!a->stat || a->stat->dev.recs, "samd_step: static automaton is not on the device");
     StepParams P;
     P.dyn = a->dyn->a;
     P.has_static = a->stat != nullptr;
@@ -438,11 +486,11 @@ __global__ void __launch_bounds__(32) static_keys_kernel(StaticDev st, const int
     if (r >= n) return;
     int idx = cursor[2 * r], len = cursor[2 * r + 1];
     int hops = 0;
-    warp_transfer<true>(st.slots, st.bmask, st.states, idx, len, start_tok[r], lane, hops);
+    warp_transfer<true>(st.recs, st.slots, st.bmask, idx, len, start_tok[r], lane, hops);
     if (lane == 0) {
         long long key = 0;
         if (len > 0) {
-            const long long e = shard_offset + (long long)__ldg(st.states + idx).z;
+            const long long e = shard_offset + (long long)__ldg(st.recs + (size_t)idx * SAMD_REC + R_END);
             key = ((long long)len << 32) | (long long)(0xFFFFFFFFu - (uint32_t)e);
         }
         keys[r] = key;
@@ -451,7 +499,7 @@ __global__ void __launch_bounds__(32) static_keys_kernel(StaticDev st, const int
 
 extern "C" int samd_static_lookup_keys(samd_static_t h, const int32_t *static_cursor_dev, const int32_t *start_tok_dev,
                                        int n_requests, int64_t shard_offset, int64_t *out_keys_dev, void *stream) {
-    SAMD_REQUIRE(h && static_cursor_dev && start_tok_dev && out_keys_dev && n_requests > 0,
+    SAMD_REQUIRE(h && h->dev.recs && static_cursor_dev && start_tok_dev && out_keys_dev && n_requests > 0,
                  "samd_static_lookup_keys: bad arguments");
     static_keys_kernel<<<n_requests, 32, 0, (cudaStream_t)stream>>>(h->dev, static_cursor_dev, start_tok_dev, n_requests,
                                                                      (long long)shard_offset, (long long *)out_keys_dev);
@@ -507,17 +555,17 @@ __global__ void __launch_bounds__(32) dyn_gen_draft_kernel(DynArena a, const int
                                                            int32_t *out_draft, int stride, int32_t *out_len) {
     const int r = blockIdx.x, lane = threadIdx.x;
     if (r >= a.n_requests) return;
-    const int4 *states = a.states + (size_t)r * a.s_cap;
+    const int32_t *recs = a.recs + (size_t)r * a.s_cap * SAMD_REC;
     const int32_t *text = a.text + (size_t)r * a.t_cap;
     const int n = a.meta[(size_t)r * META_WORDS + META_N];
     int idx = index[r];
-    int4 rec = states[idx];
+    int4 rec = *reinterpret_cast<const int4 *>(recs + (size_t)idx * SAMD_REC);
     int n_out;
     if (flavour == SAMD_FLAVOUR_SAMD) {
         if (idx != 0) {                                      // to_anc (dyn_sam.py:99-105)
             while (rec.x != 0 && n_predicts > n - rec.z) {
                 idx = rec.x;
-                rec = states[idx];
+                rec = *reinterpret_cast<const int4 *>(recs + (size_t)idx * SAMD_REC);
             }
         }
         n_out = n_predicts;
@@ -550,7 +598,7 @@ __global__ void static_gen_draft_kernel(StaticDev st, const int32_t *index, cons
     const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (r >= n) return;
-    const int e = __ldg(st.states + index[r]).z;             // static_sam.py:119-125 (no to_anc)
+    const int e = __ldg(st.recs + (size_t)index[r] * SAMD_REC + R_END);   // static_sam.py:119-125 (no to_anc)
     for (int j = lane; j < stride; j += 32) {
         int v = 0;
         if (j < n_predicts) v = j == 0 ? start_tok[r] : ((long long)e + j <= st.n_tokens ? st.text[e + j] : 0);
@@ -560,13 +608,21 @@ __global__ void static_gen_draft_kernel(StaticDev st, const int32_t *index, cons
 
 extern "C" int samd_static_gen_draft(samd_static_t h, const int32_t *index_dev, const int32_t *start_tok_dev, int n_requests,
                                      int32_t n_predicts, int32_t *out_draft_dev, int32_t draft_stride, void *stream) {
-    SAMD_REQUIRE(h && h->dev.states && index_dev && start_tok_dev && out_draft_dev && n_requests > 0 && draft_stride >= n_predicts,
+    SAMD_REQUIRE(h && h->dev.recs && index_dev && start_tok_dev && out_draft_dev && n_requests > 0 && draft_stride >= n_predicts,
                  "samd_static_gen_draft: bad arguments");
     static_gen_draft_kernel<<<(n_requests + 7) / 8, 256, 0, (cudaStream_t)stream>>>(h->dev, index_dev, start_tok_dev, n_requests,
                                                                                     n_predicts, out_draft_dev, draft_stride);
     samd_count_launch();
     SAMD_CUDA(cudaGetLastError());
     return 0;
+}
+
+// out-edges of state v in insertion order: inline edges, then the overflow list (oldest first)
+template <class F>
+static inline void host_for_each_edge(const int32_t *recs, const uint4 *slots, int64_t v, F f) {
+    const int32_t *rec = recs + (size_t)v * SAMD_REC;
+    for (int i = 0; i < SAMD_INLINE && (uint32_t)rec[R_TOK + i] != SAMD_EMPTY; ++i) f(rec[R_TOK + i], rec[R_TGT + i]);
+    for (uint32_t e = (uint32_t)rec[R_OHEAD]; e != SAMD_NIL; e = slots[e].w) f((int32_t)slots[e].y, (int32_t)slots[e].z);
 }
 
 // edges of one request as (state, token, target) triples, per state in insertion order (oldest first)
@@ -577,28 +633,24 @@ extern "C" int samd_dyn_export_edges(samd_dyn_t h, int request, int32_t *edges_h
     SAMD_CUDA(cudaMemcpy(meta, h->a.meta + (size_t)request * META_WORDS, sizeof(meta), cudaMemcpyDeviceToHost));
     SAMD_REQUIRE(capacity >= meta[META_NEDGES], "samd_dyn_export_edges: capacity too small");
     const int ns = meta[META_NSTATES];
-    int4 *st = (int4 *)malloc((size_t)ns * sizeof(int4));
+    int32_t *st = (int32_t *)malloc((size_t)ns * SAMD_REC * sizeof(int32_t));
     uint4 *sl = (uint4 *)malloc((size_t)h->a.h_cap * sizeof(uint4));
-    SAMD_CUDA(cudaMemcpy(st, h->a.states + (size_t)request * h->a.s_cap, (size_t)ns * sizeof(int4), cudaMemcpyDeviceToHost));
+    SAMD_CUDA(cudaMemcpy(st, h->a.recs + (size_t)request * h->a.s_cap * SAMD_REC, (size_t)ns * SAMD_REC * sizeof(int32_t),
+                         cudaMemcpyDeviceToHost));
     SAMD_CUDA(cudaMemcpy(sl, h->a.slots + (size_t)request * h->a.h_cap, (size_t)h->a.h_cap * sizeof(uint4), cudaMemcpyDeviceToHost));
     int64_t k = 0;
-    for (int v = 0; v < ns; ++v) {
-        int64_t first = k;
-        for (uint32_t e = (uint32_t)st[v].w; e != SAMD_NIL; e = sl[e].w) {
-            edges_host[3 * k] = v;
-            edges_host[3 * k + 1] = (int32_t)sl[e].y;
-            edges_host[3 * k + 2] = (int32_t)sl[e].z;
-            k++;
-        }
-        for (int64_t i = first, j = k - 1; i < j; ++i, --j)       // list is newest-first: reverse
-            for (int c = 0; c < 3; ++c) {
-                int32_t t = edges_host[3 * i + c];
-                edges_host[3 * i + c] = edges_host[3 * j + c];
-                edges_host[3 * j + c] = t;
+    for (int v = 0; v < ns; ++v)
+        host_for_each_edge(st, sl, v, [&](int32_t tok, int32_t tgt) {
+            if (k < capacity) {
+                edges_host[3 * k] = v;
+                edges_host[3 * k + 1] = tok;
+                edges_host[3 * k + 2] = tgt;
             }
-    }
+            k++;
+        });
     free(st);
     free(sl);
+    SAMD_REQUIRE(k == meta[META_NEDGES], "samd_dyn_export_edges: edge count mismatch (corrupt arena)");
     return 0;
 }
 
@@ -607,14 +659,14 @@ extern "C" int samd_dyn_export_edges(samd_dyn_t h, int request, int32_t *edges_h
 // (static_sam.py:102-104) and the stand-alone StaticSAM.lookup / DynSAM.lookup (:94-97, :106-109)
 // ---------------------------------------------------------------------------------------
 template <bool kReadOnly>
-__device__ __forceinline__ void cursor_walk(const uint4 *slots, uint32_t bmask, const int4 *states, int &idx, int &len,
+__device__ __forceinline__ void cursor_walk(const int32_t *recs, const uint4 *slots, uint32_t bmask, int &idx, int &len,
                                             const int32_t *tk, int k, int lane) {
     int hops = 0;
     for (int i = 0; i < k; i += 32) {
         const int mine = (i + lane < k) ? tk[i + lane] : 0;
         const int lim = min(32, k - i);
         for (int j = 0; j < lim; ++j)
-            warp_transfer<kReadOnly>(slots, bmask, states, idx, len, __shfl_sync(SAMD_FULL, mine, j), lane, hops);
+            warp_transfer<kReadOnly>(recs, slots, bmask, idx, len, __shfl_sync(SAMD_FULL, mine, j), lane, hops);
     }
 }
 
@@ -625,7 +677,7 @@ __global__ void __launch_bounds__(32) static_walk_kernel(StaticDev st, int32_t *
     if (r >= n) return;
     int idx = cursor[2 * r], len = cursor[2 * r + 1];
     if (tokens) {
-        cursor_walk<true>(st.slots, st.bmask, st.states, idx, len, tokens + (size_t)r * stride, counts ? counts[r] : stride, lane);
+        cursor_walk<true>(st.recs, st.slots, st.bmask, idx, len, tokens + (size_t)r * stride, counts ? counts[r] : stride, lane);
         if (lane == 0) {
             cursor[2 * r] = idx;
             cursor[2 * r + 1] = len;
@@ -633,7 +685,7 @@ __global__ void __launch_bounds__(32) static_walk_kernel(StaticDev st, int32_t *
     }
     if (peek_tok) {
         int hops = 0;
-        warp_transfer<true>(st.slots, st.bmask, st.states, idx, len, peek_tok[r], lane, hops);
+        warp_transfer<true>(st.recs, st.slots, st.bmask, idx, len, peek_tok[r], lane, hops);
         if (lane == 0) {
             out_index[r] = idx;
             out_len[r] = len;
@@ -644,7 +696,7 @@ __global__ void __launch_bounds__(32) static_walk_kernel(StaticDev st, int32_t *
 extern "C" int samd_static_walk(samd_static_t h, int32_t *static_cursor_dev, const int32_t *tokens_dev, int32_t token_stride,
                                 const int32_t *counts_dev, const int32_t *peek_tok_dev, int n_requests, int32_t *out_index_dev,
                                 int32_t *out_len_dev, void *stream) {
-    SAMD_REQUIRE(h && h->dev.states && static_cursor_dev && n_requests > 0, "samd_static_walk: bad arguments");
+    SAMD_REQUIRE(h && h->dev.recs && static_cursor_dev && n_requests > 0, "samd_static_walk: bad arguments");
     SAMD_REQUIRE(!peek_tok_dev || (out_index_dev && out_len_dev), "samd_static_walk: peek needs output arrays");
     static_walk_kernel<<<n_requests, 32, 0, (cudaStream_t)stream>>>(h->dev, static_cursor_dev, tokens_dev, token_stride, counts_dev,
                                                                      peek_tok_dev, n_requests, out_index_dev, out_len_dev);
@@ -658,7 +710,7 @@ __global__ void __launch_bounds__(32) dyn_walk_kernel(DynArena a, const int32_t 
     if (r >= a.n_requests) return;
     int32_t *meta = a.meta + (size_t)r * META_WORDS;
     int idx = meta[META_CUR], len = meta[META_CURLEN];
-    cursor_walk<false>(a.slots + (size_t)r * a.h_cap, a.bmask, a.states + (size_t)r * a.s_cap, idx, len,
+    cursor_walk<false>(a.recs + (size_t)r * a.s_cap * SAMD_REC, a.slots + (size_t)r * a.h_cap, a.bmask, idx, len,
                        tokens + (size_t)r * stride, counts ? counts[r] : stride, lane);
     if (lane == 0) {
         meta[META_CUR] = idx;
@@ -677,7 +729,7 @@ extern "C" int samd_dyn_transfer(samd_dyn_t h, const int32_t *tokens_dev, int32_
 
 // ---------------------------------------------------------------------------------------
 // Capacity growth: a new batch with a larger max_tokens holding the same automata (same state
-// numbering, cursor and history).  State records / text / meta are copied; the edge table is
+// numbering, cursor and history).  Records / text / meta are copied; the overflow table is
 // re-hashed on the host for the new capacity, keeping every state's edge order.  Rare.
 // ---------------------------------------------------------------------------------------
 extern "C" int samd_dyn_grow(samd_dyn_t old, int new_max_tokens, samd_dyn_t *out) {
@@ -688,24 +740,22 @@ extern "C" int samd_dyn_grow(samd_dyn_t old, int new_max_tokens, samd_dyn_t *out
     SAMD_CUDA(cudaDeviceSynchronize());
     const DynArena &o = old->a;
     const DynArena &n = nw->a;
-    int4 *st = (int4 *)malloc((size_t)o.s_cap * sizeof(int4));
+    int32_t *st = (int32_t *)malloc((size_t)o.s_cap * SAMD_REC * sizeof(int32_t));
     uint4 *sl = (uint4 *)malloc((size_t)o.h_cap * sizeof(uint4));
     uint4 *nsl = (uint4 *)malloc((size_t)n.h_cap * sizeof(uint4));
     int32_t meta[META_WORDS];
     SAMD_REQUIRE(st && sl && nsl, "samd_dyn_grow: host allocation failed");
-    std::vector<uint32_t> chain;
     for (int r = 0; r < o.n_requests; ++r) {
         SAMD_CUDA(cudaMemcpy(meta, o.meta + (size_t)r * META_WORDS, sizeof(meta), cudaMemcpyDeviceToHost));
         const int ns = meta[META_NSTATES];
-        SAMD_CUDA(cudaMemcpy(st, o.states + (size_t)r * o.s_cap, (size_t)ns * sizeof(int4), cudaMemcpyDeviceToHost));
+        SAMD_CUDA(cudaMemcpy(st, o.recs + (size_t)r * o.s_cap * SAMD_REC, (size_t)ns * SAMD_REC * sizeof(int32_t), cudaMemcpyDeviceToHost));
         SAMD_CUDA(cudaMemcpy(sl, o.slots + (size_t)r * o.h_cap, (size_t)o.h_cap * sizeof(uint4), cudaMemcpyDeviceToHost));
         memset(nsl, 0xFF, (size_t)n.h_cap * sizeof(uint4));
         for (int v = 0; v < ns; ++v) {
-            chain.clear();
-            for (uint32_t e = (uint32_t)st[v].w; e != SAMD_NIL; e = sl[e].w) chain.push_back(e);
-            uint32_t head = SAMD_NIL;
-            for (size_t i = chain.size(); i-- > 0;) {                 // oldest first
-                const uint4 ed = sl[chain[i]];
+            int32_t *rec = st + (size_t)v * SAMD_REC;
+            uint32_t head = SAMD_NIL, tail = SAMD_NIL;
+            for (uint32_t e = (uint32_t)rec[R_OHEAD]; e != SAMD_NIL; e = sl[e].w) {     // oldest first
+                const uint4 ed = sl[e];
                 uint32_t b = samd_hash((uint32_t)v, ed.y) & n.bmask;
                 uint32_t slot = 0;
                 for (bool placed = false; !placed; b = (b + 1) & n.bmask)
@@ -714,12 +764,15 @@ extern "C" int samd_dyn_grow(samd_dyn_t old, int new_max_tokens, samd_dyn_t *out
                             slot = b * SAMD_BUCKET + l;
                             placed = true;
                         }
-                nsl[slot] = make_uint4((uint32_t)v, ed.y, ed.z, head);
-                head = slot;
+                nsl[slot] = make_uint4((uint32_t)v, ed.y, ed.z, SAMD_NIL);
+                if (tail != SAMD_NIL) nsl[tail].w = slot;
+                else head = slot;
+                tail = slot;
             }
-            st[v].w = (int)head;
+            rec[R_OHEAD] = (int32_t)head;
+            rec[R_OTAIL] = (int32_t)tail;
         }
-        SAMD_CUDA(cudaMemcpy(n.states + (size_t)r * n.s_cap, st, (size_t)ns * sizeof(int4), cudaMemcpyHostToDevice));
+        SAMD_CUDA(cudaMemcpy(n.recs + (size_t)r * n.s_cap * SAMD_REC, st, (size_t)ns * SAMD_REC * sizeof(int32_t), cudaMemcpyHostToDevice));
         SAMD_CUDA(cudaMemcpy(n.slots + (size_t)r * n.h_cap, nsl, (size_t)n.h_cap * sizeof(uint4), cudaMemcpyHostToDevice));
         SAMD_CUDA(cudaMemcpy(n.text + (size_t)r * n.t_cap, o.text + (size_t)r * o.t_cap, (size_t)(meta[META_N] + 1) * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice));

@@ -1,12 +1,21 @@
 // Shared device/host definitions of the flat suffix-automaton layout (sm_100a).
 //
 // Layout (identical for the per-request dynamic arenas and the static automaton):
-//   state record  int4  {link, length, min_endpos, edge_head}          16 B
-//   edge slot     uint4 {state, token, target, next_edge_of_state}     16 B
-//   edge table    open addressing, 8-slot (128 B = one cache line) buckets, linear over
-//                 buckets; a slot is free when .x == SAMD_EMPTY.  Nothing is ever deleted,
-//                 so a probe ends at the first bucket that still has a free slot.
+//   state record  16 x int32 = 64 B, 64-byte aligned (two sectors of one cache line):
+//                   [0] link  [1] length  [2] min_endpos  [3] overflow list head (oldest)
+//                   [4..8] inline edge tokens (SAMD_EMPTY = free)   [9..13] inline edge targets
+//                   [14] overflow list tail (newest)   [15] aux
+//                 The first five out-edges of a state live INSIDE its record, so a transition
+//                 probe, the suffix link, the length and min_endpos all come from ONE 64-byte read,
+//                 and clone-on-split is one 64-byte copy.  (Mean out-degree of non-root states is
+//                 ~1.3)
+//   overflow edge uint4 {state, token, target, next (towards newer)} in an open-addressing table
+//                 keyed (state, token): 8-slot (128 B) buckets, linear over buckets, a slot is free
+//                 when .x == SAMD_EMPTY.  Nothing is ever deleted, so a probe ends at the first
+//                 bucket that still has a free slot.  Per-state lists run oldest -> newest, so edge
+//                 enumeration (clone, export, top-k) sees dict insertion order: inline, then the list.
 //   text          int32, 1-based, text[0] = -1                         (dyn_sam.py:20)
+// Tokens must be non-negative (SAMD_EMPTY = -1 marks free inline edges).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,9 +25,13 @@
 #define SAMD_NIL   0xFFFFFFFFu
 #define SAMD_FULL  0xFFFFFFFFu
 #define SAMD_BUCKET 8
+#define SAMD_REC 16            // int32 words per state record
+#define SAMD_INLINE 5          // inline out-edges per state
+
+enum { R_LINK = 0, R_LEN = 1, R_END = 2, R_OHEAD = 3, R_TOK = 4, R_TGT = 9, R_OTAIL = 14, R_AUX = 15 };
 
 enum { META_NSTATES = 0, META_LAST = 1, META_N = 2, META_CUR = 3, META_CURLEN = 4, META_NEDGES = 5,
-       META_OVERFLOW = 6, META_NCLONES = 7, META_HOPS = 8, META_PROBES = 9, META_WORDS = 16 };
+       META_OVERFLOW = 6, META_NCLONES = 7, META_HOPS = 8, META_PROBES = 9, META_LASTLINK = 10, META_WORDS = 16 };
 
 __host__ __device__ __forceinline__ uint32_t samd_hash(uint32_t state, uint32_t tok) {
     uint32_t h = state * 0x9E3779B1u + tok * 0x85EBCA77u;
@@ -33,15 +46,28 @@ static inline uint64_t samd_next_pow2(uint64_t x) {
     while (p < x) p <<= 1;
     return p;
 }
-// edge-table capacity rule: >= 4 slots per token (edges <= 3n-4), power of two, >= 64
+// overflow-table capacity rule for a growing automaton: >= 4 slots per token (edges <= 3n-4)
 static inline uint64_t samd_table_slots(uint64_t n_tokens) {
     uint64_t c = samd_next_pow2(4 * (n_tokens + 1));
     return c < 64 ? 64 : c;
 }
 
+static inline void samd_init_rec(int32_t *w, int link, int len, int endpos) {
+    w[R_LINK] = link;
+    w[R_LEN] = len;
+    w[R_END] = endpos;
+    w[R_OHEAD] = (int32_t)SAMD_NIL;
+    for (int i = 0; i < SAMD_INLINE; ++i) {
+        w[R_TOK + i] = (int32_t)SAMD_EMPTY;
+        w[R_TGT + i] = 0;
+    }
+    w[R_OTAIL] = (int32_t)SAMD_NIL;
+    w[R_AUX] = 0;
+}
+
 struct DynArena {
-    int4     *states;   // [B][s_cap]
-    uint4    *slots;    // [B][h_cap]
+    int32_t  *recs;     // [B][s_cap][SAMD_REC]
+    uint4    *slots;    // [B][h_cap] overflow edges
     int32_t  *text;     // [B][t_cap]
     int32_t  *meta;     // [B][META_WORDS]
     int32_t   n_requests, max_tokens;
@@ -49,8 +75,8 @@ struct DynArena {
 };
 
 struct StaticDev {
-    const int4    *states;
-    const uint4   *slots;
+    const int32_t *recs;   // [n_states][SAMD_REC]
+    const uint4   *slots;  // [n_slots] overflow edges
     const int32_t *text;
     const int32_t *occ;    // cnt_endpos (count flavour) or NULL
     const int2    *topk;   // [n_states][8] (token,target), -1 padded, or NULL
@@ -61,12 +87,12 @@ struct StaticDev {
 struct samd_static_s {
     StaticDev dev;
     // host mirrors kept for export/save (test + persistence paths)
-    int4     *h_states;
+    int32_t  *h_recs;
     uint4    *h_slots;
     int32_t  *h_text;
     int32_t  *h_occ;
     int2     *h_topk;
-    int64_t   n_edges, n_clones;
+    int64_t   n_edges, n_clones, n_ovf;
     int       with_counts;
     int       device;
 };
@@ -97,83 +123,92 @@ void samd_count_launch(int n = 1);
         }                                                             \
     } while (0)
 
+#ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------
-// Warp-cooperative probe: lanes 0..7 read the eight slots of one bucket (one 128 B line),
-// lane 8 fetches the state record of `state` in the same memory round trip.
+// Warp-cooperative transition probe.  Lanes 0..15 read the sixteen words of the state record (one
+// 64 B request); the inline edges are matched with a ballot.  Only states with more than five
+// out-edges (the root, a few hubs) ever touch the overflow table: lanes 0..7 then read one bucket.
 // ---------------------------------------------------------------------------------------
-struct Probe {
-    uint32_t slot;     // matching slot, or the first free slot of the probe sequence
-    uint32_t target;   // transition target when found
-    int4     rec;      // state record of `state` (when requested)
+struct Look {
+    int      w;        // this lane's word of the record (valid in lanes 0..15)
+    int      target;   // transition target when found
+    uint32_t slot;     // overflow slot of the hit / first free overflow slot (when probed), else NIL
+    int      k;        // inline index of the hit, or -1
     bool     found;
+    bool     probed;   // the overflow table was searched (slot is meaningful)
 };
 
-template <bool kRec, bool kReadOnly>
-__device__ __forceinline__ Probe warp_probe(const uint4 *slots, uint32_t bmask, const int4 *states, uint32_t state,
-                                            uint32_t tok, int lane) {
-    Probe r;
+__device__ __forceinline__ int rec_word(const Look &r, int which) { return __shfl_sync(SAMD_FULL, r.w, which); }
+
+// search the overflow table for (state, tok): found -> slot/target; else slot = first free slot
+__device__ __forceinline__ void ovf_probe(const uint4 *slots, uint32_t bmask, uint32_t state, uint32_t tok, int lane,
+                                          bool ro, Look &r) {
     uint32_t b = samd_hash(state, tok) & bmask;
-    int4 rec = make_int4(0, 0, 0, 0);
-    if (kRec && lane == 8) rec = kReadOnly ? __ldg(states + state) : states[state];
+    r.probed = true;
     while (true) {
         uint4 s = make_uint4(0xFFFFFFFEu, 0, 0, 0);
         if (lane < SAMD_BUCKET) {
             const uint4 *ptr = slots + ((size_t)b * SAMD_BUCKET + lane);
-            s = kReadOnly ? __ldg(ptr) : *ptr;
+            s = ro ? __ldg(ptr) : *ptr;
         }
-        unsigned hit = __ballot_sync(SAMD_FULL, s.x == state && s.y == tok);
-        unsigned emp = __ballot_sync(SAMD_FULL, s.x == SAMD_EMPTY);
+        const unsigned hit = __ballot_sync(SAMD_FULL, s.x == state && s.y == tok);
+        const unsigned emp = __ballot_sync(SAMD_FULL, s.x == SAMD_EMPTY);
         if (hit) {
-            int l = __ffs(hit) - 1;
+            const int l = __ffs(hit) - 1;
             r.found = true;
             r.slot = b * SAMD_BUCKET + l;
-            r.target = __shfl_sync(SAMD_FULL, s.z, l);
-            break;
+            r.target = (int)__shfl_sync(SAMD_FULL, s.z, l);
+            return;
         }
         if (emp) {
-            int l = __ffs(emp) - 1;
             r.found = false;
-            r.slot = b * SAMD_BUCKET + l;
-            r.target = 0;
-            break;
+            r.slot = b * SAMD_BUCKET + (__ffs(emp) - 1);
+            return;
         }
         b = (b + 1) & bmask;
     }
-    if (kRec) {
-        r.rec.x = __shfl_sync(SAMD_FULL, rec.x, 8);
-        r.rec.y = __shfl_sync(SAMD_FULL, rec.y, 8);
-        r.rec.z = __shfl_sync(SAMD_FULL, rec.z, 8);
-        r.rec.w = __shfl_sync(SAMD_FULL, rec.w, 8);
-    } else {
-        r.rec = rec;
+}
+
+template <bool kReadOnly>
+__device__ __forceinline__ Look warp_look(const int32_t *recs, const uint4 *slots, uint32_t bmask, int state, int tok, int lane) {
+    Look r;
+    const int32_t *p = recs + (size_t)state * SAMD_REC;
+    int w = 0;
+    if (lane < SAMD_REC) w = kReadOnly ? __ldg(p + lane) : p[lane];
+    r.w = w;
+    r.slot = SAMD_NIL;
+    r.probed = false;
+    r.target = 0;
+    const unsigned hit = __ballot_sync(SAMD_FULL, lane >= R_TOK && lane < R_TOK + SAMD_INLINE && w == tok);
+    if (hit) {
+        const int l = __ffs(hit) - 1;
+        r.k = l - R_TOK;
+        r.target = __shfl_sync(SAMD_FULL, w, l + (R_TGT - R_TOK));
+        r.found = true;
+        return r;
     }
+    r.k = -1;
+    r.found = false;
+    if ((uint32_t)__shfl_sync(SAMD_FULL, w, R_OHEAD) != SAMD_NIL) ovf_probe(slots, bmask, (uint32_t)state, (uint32_t)tok, lane, kReadOnly, r);
     return r;
 }
 
-// Prefetch hint for a probe whose key is already known (next token's cursor / tail probes): the
-// four sectors of the bucket and the state record are pulled towards the SM while the warp is
-// still busy with the current token, turning a DRAM round trip into a cache hit.
-__device__ __forceinline__ void prefetch_probe(const uint4 *slots, uint32_t bmask, const int4 *states, uint32_t state,
-                                               uint32_t tok, int lane) {
-    if (lane < 4) {
-        const char *p = reinterpret_cast<const char *>(slots + (size_t)(samd_hash(state, tok) & bmask) * SAMD_BUCKET) + lane * 32;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-    } else if (lane == 4 && states) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(states + state));
-    }
+// Hint: pull the 64 B record of `state` towards the SM (both sectors) ahead of its use.
+__device__ __forceinline__ void prefetch_rec(const int32_t *recs, int state, int lane) {
+    if (lane < 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(recs + (size_t)state * SAMD_REC + lane * 8));
 }
 
-// Longest-suffix-match step (dyn_sam.py:69-78): one memory round trip per suffix-link hop.
+// Longest-suffix-match step (dyn_sam.py:69-78): one 64-byte read per suffix-link hop.
 template <bool kReadOnly>
-__device__ __forceinline__ void warp_transfer(const uint4 *slots, uint32_t bmask, const int4 *states, int &index,
-                                              int &length, int tok, int lane, int &hops) {
+__device__ __forceinline__ void warp_transfer(const int32_t *recs, const uint4 *slots, uint32_t bmask, int &index, int &length,
+                                              int tok, int lane, int &hops) {
     bool first = true;
     while (true) {
-        Probe pr = warp_probe<true, kReadOnly>(slots, bmask, states, (uint32_t)index, (uint32_t)tok, lane);
+        const Look r = warp_look<kReadOnly>(recs, slots, bmask, index, tok, lane);
         hops++;
-        if (!first) length = pr.rec.y;           // length = states[index].length after a link hop
-        if (pr.found) {
-            index = (int)pr.target;
+        if (!first) length = rec_word(r, R_LEN);        // length = states[index].length after a link hop
+        if (r.found) {
+            index = r.target;
             length += 1;
             return;
         }
@@ -181,7 +216,8 @@ __device__ __forceinline__ void warp_transfer(const uint4 *slots, uint32_t bmask
             length = 0;
             return;
         }
-        index = pr.rec.x;
+        index = rec_word(r, R_LINK);
         first = false;
     }
 }
+#endif  // __CUDACC__
