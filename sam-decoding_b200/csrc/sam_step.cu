@@ -206,8 +206,13 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
             continue;
         }
         const int q = r.target;
+        // one request, two records: q's (lanes 0..15) and, speculatively, link(p)'s (lanes 16..31) - the
+        // first state the redirect walk of a clone-on-split visits - so both DRAM reads overlap
+        const int lp = rec_word(r, R_LINK);
         int qw = 0;
         if (lane < SAMD_REC) qw = recs[(size_t)q * SAMD_REC + lane];
+        else if (lp >= 0) qw = recs[(size_t)lp * SAMD_REC + (lane - SAMD_REC)];
+        const int lpw = __shfl_sync(SAMD_FULL, qw, (lane + SAMD_REC) & 31);      // link(p)'s words in lanes 0..15
         const int len_p = rec_word(r, R_LEN);
         if (len_p + 1 == __shfl_sync(SAMD_FULL, qw, R_LEN)) {
             link_cur = q;
@@ -217,6 +222,7 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
             const int clone = g.n_states++;
             g.n_clones++;
             int cw = qw;
+            if (lane >= SAMD_REC) cw = 0;
             if (lane == R_LEN) cw = len_p + 1;
             if (lane == R_OHEAD || lane == R_OTAIL) cw = -1;
             if (lane < SAMD_REC) recs[(size_t)clone * SAMD_REC + lane] = cw;
@@ -246,6 +252,7 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
             // redirect p's suffix chain from q to the clone
             Look cp = r;
             int pp = p;
+            bool first_hop = true;
             while (true) {
                 if (lane == 0) {
                     if (cp.k >= 0) recs[(size_t)pp * SAMD_REC + R_TGT + cp.k] = clone;
@@ -254,7 +261,10 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
                 __syncwarp();
                 pp = rec_word(cp, R_LINK);
                 if (pp == -1) break;
-                cp = warp_look<false>(recs, slots, bmask, pp, tok, lane);
+                // the first hop's record was fetched together with q's (nothing wrote to it since)
+                cp = first_hop ? look_words<false>(lpw, slots, bmask, pp, tok, lane)
+                               : warp_look<false>(recs, slots, bmask, pp, tok, lane);
+                first_hop = false;
                 if (!(cp.found && cp.target == q)) break;
             }
             if (lane == 0) recs[(size_t)q * SAMD_REC + R_LINK] = clone;

@@ -169,12 +169,10 @@ __device__ __forceinline__ void ovf_probe(const uint4 *slots, uint32_t bmask, ui
     }
 }
 
+// match `tok` against a record whose sixteen words are already held by lanes 0..15 (`w`)
 template <bool kReadOnly>
-__device__ __forceinline__ Look warp_look(const int32_t *recs, const uint4 *slots, uint32_t bmask, int state, int tok, int lane) {
+__device__ __forceinline__ Look look_words(int w, const uint4 *slots, uint32_t bmask, int state, int tok, int lane) {
     Look r;
-    const int32_t *p = recs + (size_t)state * SAMD_REC;
-    int w = 0;
-    if (lane < SAMD_REC) w = kReadOnly ? __ldg(p + lane) : p[lane];
     r.w = w;
     r.slot = SAMD_NIL;
     r.probed = false;
@@ -191,6 +189,14 @@ __device__ __forceinline__ Look warp_look(const int32_t *recs, const uint4 *slot
     r.found = false;
     if ((uint32_t)__shfl_sync(SAMD_FULL, w, R_OHEAD) != SAMD_NIL) ovf_probe(slots, bmask, (uint32_t)state, (uint32_t)tok, lane, kReadOnly, r);
     return r;
+}
+
+template <bool kReadOnly>
+__device__ __forceinline__ Look warp_look(const int32_t *recs, const uint4 *slots, uint32_t bmask, int state, int tok, int lane) {
+    const int32_t *p = recs + (size_t)state * SAMD_REC;
+    int w = 0;
+    if (lane < SAMD_REC) w = kReadOnly ? __ldg(p + lane) : p[lane];
+    return look_words<kReadOnly>(w, slots, bmask, state, tok, lane);
 }
 
 // Hint: pull the 64 B record of `state` towards the SM (both sectors) ahead of its use.
