@@ -166,7 +166,28 @@ def _cpu_worker(job):
     return run(w0, w1)
 
 
-def cpu_arm(n_sample, prompt, steps, warmup, seed0, cores):
+def _cpu_worker_c(job):
+    """Same block of work through the oracle's C restatement (oracle/sam_oracle.c)."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import c_oracle as CO
+    streams, counts, tokens, start, prompt, w0, w1 = job
+    R = len(streams)
+    sams = [CO.CSam(streams.shape[1] + 8) for _ in range(R)]
+    for a, s in zip(sams, streams):
+        a.extend(s[:prompt])
+    arr = (CO.vp * R)(*[a.h for a in sams])
+    tk = np.ascontiguousarray(tokens.transpose(0, 1, 2), dtype=np.int32)
+    ct = np.ascontiguousarray(counts, dtype=np.int32)
+    st = np.ascontiguousarray(start, dtype=np.int32)
+    run = lambda lo, hi: CO.lib().so_run_steps(arr, R, CO._p(tk), CO._p(ct), CO._p(st), lo, hi, N_PREDICTS, LEN_BIAS, LEN_THRESHOLD)
+    run(0, w0)
+    t0 = time.perf_counter()
+    run(w0, w1)
+    return time.perf_counter() - t0
+
+
+def cpu_arm(n_sample, prompt, steps, warmup, seed0, cores, worker=None):
     """Returns (queries/s, per-worker max wall seconds, description) on a bounded sample."""
     from multiprocessing import Pool
     streams, counts, tokens, start = make_workload(n_sample, prompt, steps + warmup, seed0, procs=1)
@@ -176,7 +197,7 @@ def cpu_arm(n_sample, prompt, steps, warmup, seed0, cores):
         sl = slice(c, min(n_sample, c + per))
         jobs.append((streams[sl], counts[:, sl], tokens[:, sl], start[:, sl], prompt, warmup, warmup + steps))
     with Pool(len(jobs)) as pool:
-        walls = pool.map(_cpu_worker, jobs)
+        walls = pool.map(worker or _cpu_worker, jobs)
     wall = max(walls)
     return n_sample * steps / wall, wall, len(jobs)
 
@@ -187,7 +208,7 @@ def run_reference(a):
         return
     cores = min(os.cpu_count() or 1, 32)
     # bounded sample: a step of the reference arm is one pass over `n_sample` requests of the c2 workload
-    n_sample = cores * 16
+    n_sample = cores * 64
     steps = min(a.steps, 256)
     warm = min(a.warmup, 4)
     t0 = time.time()
@@ -229,6 +250,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     K.require_device()
     launches0 = E.launch_count()
@@ -305,39 +327,35 @@ def run_ours(a):
     torch.cuda.synchronize()
     kern_ms = float(np.mean([x.elapsed_time(y) for x, y in evs]))
 
-    # e2e: host buffers in, drafts out, through the public engine API, one sync per step
+    # e2e: host buffers in, drafts out, through the public engine API (DraftEngine.step_host): per step the
+    # caller stages its inputs (counts | start tokens | accepted tokens) in a pinned buffer, the step kernel
+    # reads them and writes every output (type, match lengths, state indices, draft length, draft tokens)
+    # straight into pinned host memory over PCIe (zero-copy), then the stream is synchronised
     dyn.copy_from(snap)
-    h_tok = torch.as_tensor(tokens).pin_memory()
-    h_cnt = torch.as_tensor(counts).pin_memory()
-    h_st = torch.as_tensor(start).pin_memory()
-    b_tok = torch.empty(R, 8, dtype=torch.int32, device=dev)
-    b_cnt = torch.empty(R, dtype=torch.int32, device=dev)
-    b_st = torch.empty(R, dtype=torch.int32, device=dev)
-    h_draft = torch.empty(R, N_PREDICTS, dtype=torch.int32).pin_memory()
-    h_type = torch.empty(R, dtype=torch.int32).pin_memory()
-    h_match = torch.empty(R, dtype=torch.int32).pin_memory()
+    inp, res = eng.host_buffers(8)
+    h_in = torch.empty(W + S, inp.numel(), dtype=torch.int32).pin_memory()
+    h_in[:, :R] = torch.as_tensor(counts)
+    h_in[:, R:2 * R] = torch.as_tensor(start)
+    h_in[:, 2 * R:] = torch.as_tensor(tokens).reshape(W + S, R * 8)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    eng.step_host(inp, res)                  # untimed warm-up of the host path (zero counts: appends nothing)
+    dyn.copy_from(snap)
+    torch.cuda.synchronize()
     e2e_t0 = time.perf_counter()
     ev0.record()
     for s in range(W, W + S):
-        b_tok.copy_(h_tok[s], non_blocking=True)
-        b_cnt.copy_(h_cnt[s], non_blocking=True)
-        b_st.copy_(h_st[s], non_blocking=True)
-        eng.step(b_tok, b_cnt, b_st)
-        h_draft.copy_(eng.draft, non_blocking=True)
-        h_type.copy_(eng.out_type, non_blocking=True)
-        h_match.copy_(eng.match_dyn, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        inp.copy_(h_in[s])                   # the caller's host-side staging of this step's inputs
+        eng.step_host(inp, res)
     ev1.record()
     torch.cuda.synchronize()
     e2e_wall = time.perf_counter() - e2e_t0
     e2e_ms = max(ev0.elapsed_time(ev1), e2e_wall * 1e3)
     clocks.stop()
-    assert int(h_draft.sum().item()) == draft_checksum, "e2e and device runs disagree"
-    h2d = R * 8 * 4 + R * 4 + R * 4
-    d2h = R * N_PREDICTS * 4 + R * 4 + R * 4
+    assert int(res[6 * R:].sum().item()) == draft_checksum, "e2e and device runs disagree"
+    h2d = inp.numel() * 4
+    d2h = res.numel() * 4
 
     # max over ranks
     if world > 1:
@@ -382,7 +400,7 @@ def run_ours(a):
         "clocks_whole_run": clocks.summary(),
         "setup_s": time.time() - t_setup,
     }
-    del g, snap, h_tok, d_tokens
+    del g, snap, h_in, d_tokens
     torch.cuda.empty_cache()
     if rank == 0 and not a.no_extras:
         try:
@@ -395,11 +413,26 @@ def run_ours(a):
             out["static"] = {"error": repr(e)}
     if rank == 0 and not a.no_cpu:
         cores = min(os.cpu_count() or 1, 32)
-        n_sample = cores * 16
+        n_sample = cores * 64
         qps, wall, used = cpu_arm(n_sample, N, 256, 4, 2000, cores)
         out["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": used, "kind": "port",
                                "sample": f"{n_sample} requests x 256 steps of the same workload (prefill untimed, {wall:.2f} s "
                                          f"of work per core), Python port of the reference path (oracle/samd_oracle.py)"}
+        try:
+            qps_c, wall_c, used_c = cpu_arm(n_sample, N, 256, 4, 2000, cores, worker=_cpu_worker_c)
+            out["cpu_baseline_c"] = {"value": qps_c, "unit": UNIT, "cores": used_c, "kind": "port",
+                                     "sample": f"same sample through the oracle's plain-C restatement (oracle/sam_oracle.c), "
+                                               f"{wall_c:.3f} s per core; reported for context - the reference itself is Python"}
+        except Exception as e:
+            out["cpu_baseline_c"] = {"error": repr(e)}
+    if world > 1 and not a.no_extras:
+        try:
+            res = bench_sharded_static(a, dev, rank, world)
+            if rank == 0:
+                out["sharded_static"] = res
+        except Exception as e:
+            if rank == 0:
+                out["sharded_static"] = {"error": repr(e)}
     out["gpu_launches"] = S          # kernels of ours inside the timed region: one sam_step_kernel per step
     out["gpu_launches_total_process"] = E.launch_count() - launches0
     if world > 1:
@@ -524,6 +557,53 @@ def bench_static(a, dev, n_corpus=2_000_000, n_q=4096, steps=64, warm=8):
             "queries_per_s": n_q * steps / (ms * 1e-3), "us_per_step": ms / steps * 1e3, "host_build_s": build_s,
             "host_build_tokens_per_s": st.n_tokens / build_s, "mean_match_static": float(eng.match_static.float().mean()),
             "draft_source_hist": {"dyn": src[0], "static": src[1], "tree_model": src[2]}}
+
+
+def bench_sharded_static(a, dev, rank, world, tokens_per_shard=2_000_000, n_q=4096, steps=64, warm=8):
+    """Config c5's retrieval half at a host-buildable size: the static corpus is split by document over the
+    ranks; per step every rank advances ALL query cursors on its shard, computes packed keys, one NCCL
+    all-reduce-max (Q x 8 bytes) merges them and the draft is read from the replicated corpus tokens."""
+    import torch
+    import torch.distributed as dist
+    from samd_b200 import dist as D, synth
+    docs = synth.make_corpus(tokens_per_shard * world, VOCAB, 5000, singletons=True)       # same corpus on every rank
+    t0 = time.time()
+    sh = D.ShardedStaticSam(docs, synth.EOS, rank, world, n_q, dev)
+    build_s = time.time() - t0
+    q = synth.corpus_queries(docs, n_q, 8 * (steps + warm) + 1, VOCAB, 5001).astype(np.int32)
+    rng = np.random.default_rng(5002)
+    counts = rng.integers(1, 9, size=(steps + warm, n_q)).astype(np.int32)
+    ends = np.cumsum(counts, axis=0)
+    begins = ends - counts
+    cols = np.arange(8)[None, None, :]
+    rows = np.arange(n_q)[None, :, None]
+    tokens = np.where(cols < counts[:, :, None], q[rows, np.minimum(begins[:, :, None] + cols, q.shape[1] - 1)], 0).astype(np.int32)
+    start = q[np.arange(n_q)[None, :], ends].astype(np.int32)
+    d_tok, d_cnt, d_st = (torch.as_tensor(x).to(dev) for x in (tokens, counts, start))
+
+    def step(s):
+        sh.advance(d_tok[s], d_cnt[s])
+        return sh.lookup_draft(d_st[s], N_PREDICTS)
+
+    for s in range(warm):
+        step(s)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(warm, warm + steps):
+        match, draft = step(s)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"workload": f"c5 (reduced corpus): static SAM over {sh.n_corpus} tokens split by document over {world} GPUs "
+                        f"({sh.sam.n_tokens} tokens on rank 0), {n_q} queries/step advanced 1-8 tokens, packed-u64 NCCL "
+                        f"all-reduce-max ({n_q * 8} B) per step, draft {N_PREDICTS} from the replicated corpus",
+            "queries_per_s": n_q * steps / (ms * 1e-3), "us_per_step": ms / steps * 1e3, "host_build_s": build_s,
+            "mean_match": float(match.float().mean()), "gpu_launches_per_step": 3, "collectives_per_step": 1}
 
 
 def main():

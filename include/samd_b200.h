@@ -53,9 +53,10 @@ int         samd_device_count(void);          /* 0 without a usable CUDA device 
 /* ----------------------------------------------------------------------------------------
  * Dynamic suffix automaton, one per request           (samd/sam/dyn_sam.py:8-113,
  *                                                       samd_sam_only/sam/dyn_sam.py:11-121)
- * Per-request arenas in HBM: state records {link,len,min_endpos,edge_head} (16 B), a
- * bucketed open-addressing transition table keyed (state, token) (16 B slots, 128 B
- * buckets), the token history (1-based, text[0] = -1) and a small meta block.
+ * Per-request arenas in HBM: 64-byte state records {link, length, min_endpos, five inline
+ * out-edges, overflow list head/tail}, an open-addressing overflow table keyed (state, token)
+ * for states with more than five out-edges (16 B slots, 128 B buckets), the token history
+ * (1-based, text[0] = -1) and a small meta block.  Token ids must be non-negative.
  * -------------------------------------------------------------------------------------- */
 /* DynSAM.__init__ for n_requests independent requests; max_tokens bounds prompt + decoded. */
 int samd_dyn_create(int n_requests, int max_tokens, samd_dyn_t *out);

@@ -41,7 +41,7 @@ struct VerifyParams {
     unsigned long long *node_key;
     int *done, *active, *counters, *kv_start;
     int max_nodes, max_batch, epoch, finished_target;
-    int chunk, chunks_per_row, n_items1, n_items2, vec_ok;
+    int chunk, chunks_per_row, n_items1, n_items2, vec_ok, stage_cap;
 };
 
 template <int kDtype>
@@ -358,17 +358,43 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         const int per_tensor = A.n_heads * cols;
         const long long per_req = (long long)A.n_kv * per_tensor;
         const long long total = per_req * n_active;
-        int cur_a = -1, acc1 = 0, start = 0;
-        const int32_t *idx = nullptr;
+        // stage the active requests' move lists in shared memory once per CTA: the copy loop then has
+        // no dependent metadata loads in front of its row loads
+        constexpr int MW = 3 + KV_GROUP;                       // {request, accept_len, start, first KV_GROUP sources}
+        int *s_meta = s_am_all + VW * T;
+        const int staged = min(n_active, P.stage_cap);
+        for (int i = threadIdx.x; i < staged * MW; i += VT) {
+            const int a_i = i / MW, f = i - a_i * MW;
+            const int b = __ldcg(active + a_i);
+            int v;
+            if (f == 0) v = b;
+            else if (f == 1) v = __ldcg(A.out_accept_len_dev + b);
+            else if (f == 2) v = __ldcg(P.kv_start + b);
+            else {
+                const int j = f - 3;
+                v = j < __ldcg(A.out_accept_len_dev + b) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j) : j;
+            }
+            s_meta[i] = v;
+        }
+        __syncthreads();
         for (long long g = (long long)gwarp * 32 + lane; g < total; g += (long long)n_warps * 32) {
             const int a_i = (int)(g / per_req);
             const int unit = (int)(g - (long long)a_i * per_req);
-            const int b = __ldcg(active + a_i);
-            if (a_i != cur_a) {
-                cur_a = a_i;
+            int b, acc1, start;
+            int src[KV_GROUP];
+            if (a_i < staged) {
+                const int *m = s_meta + a_i * MW;
+                b = m[0];
+                acc1 = m[1];
+                start = m[2];
+#pragma unroll
+                for (int u = 0; u < KV_GROUP; ++u) src[u] = m[3 + u];
+            } else {
+                b = __ldcg(active + a_i);
                 acc1 = __ldcg(A.out_accept_len_dev + b);
                 start = __ldcg(P.kv_start + b);
-                idx = A.out_indices_dev + (size_t)b * A.depth;
+#pragma unroll
+                for (int u = 0; u < KV_GROUP; ++u) src[u] = u < acc1 ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + u) : u;
             }
             const int kv = unit / per_tensor;
             const int w = unit - kv * per_tensor;
@@ -376,10 +402,12 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
             char *hb = reinterpret_cast<char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.kv_ptrs_dev) + kv)) +
                        (size_t)b * A.kv_batch_stride + (size_t)hd * A.kv_head_stride + ((size_t)col << 4);
             for (int j0 = 0; j0 < acc1; j0 += KV_GROUP) {
-                int src[KV_GROUP];
                 uint4 val[KV_GROUP];
+                if (j0 > 0) {
 #pragma unroll
-                for (int u = 0; u < KV_GROUP; ++u) src[u] = (j0 + u < acc1) ? __ldcg(idx + j0 + u) : j0 + u;
+                    for (int u = 0; u < KV_GROUP; ++u)
+                        src[u] = (j0 + u < acc1) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j0 + u) : j0 + u;
+                }
 #pragma unroll
                 for (int u = 0; u < KV_GROUP; ++u)
                     if (src[u] != j0 + u) val[u] = *reinterpret_cast<const uint4 *>(hb + (size_t)(start + src[u]) * A.kv_pos_stride);
@@ -459,7 +487,8 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     P.kv_start = h->kv_start;
     P.max_nodes = h->max_nodes;
     P.epoch = ++h->epoch;
-    const size_t smem = (size_t)VW * a->n_nodes * sizeof(int);
+    P.stage_cap = move ? std::min(a->batch, 512) : 0;
+    const size_t smem = ((size_t)VW * a->n_nodes + (size_t)P.stage_cap * (3 + KV_GROUP)) * sizeof(int);
     auto kern = a->dtype == SAMD_DTYPE_BF16   ? verify_compact_kernel<SAMD_DTYPE_BF16>
                 : a->dtype == SAMD_DTYPE_FP16 ? verify_compact_kernel<SAMD_DTYPE_FP16>
                                               : verify_compact_kernel<SAMD_DTYPE_FP32>;

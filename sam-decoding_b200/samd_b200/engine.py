@@ -16,7 +16,9 @@ from . import _cabi as K
 
 
 def _i32(t: torch.Tensor) -> torch.Tensor:
-    assert t.dtype == torch.int32 and t.is_cuda and t.is_contiguous(), "expected a contiguous int32 CUDA tensor"
+    # device memory, or pinned host memory (mapped into the device address space under UVA: zero-copy I/O)
+    assert t.dtype == torch.int32 and (t.is_cuda or t.is_pinned()) and t.is_contiguous(), \
+        "expected a contiguous int32 CUDA (or pinned host) tensor"
     return t
 
 
@@ -211,11 +213,16 @@ class DraftEngine:
             int(flavour), int(n_predicts), int(len_bias), int(len_threshold), float(alpha)
         B, dev = dyn.n_requests, dyn.device
         self.static_cursor = static.new_cursors(B) if static is not None else None
-        mk = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
-        self.out_type, self.match_dyn, self.match_static = mk(B), mk(B), mk(B)
-        self.index_dyn, self.index_static, self.draft_len = mk(B), mk(B), mk(B)
-        self.draft = mk(B, self.n_predicts)
+        # every output is a view of ONE device buffer, so a host caller needs a single D2H copy:
+        # [type | match_dyn | match_static | index_dyn | index_static | draft_len | draft (B x n_predicts)]
+        n = self.n_predicts
+        self.out_buf = torch.zeros(B * (6 + n), dtype=torch.int32, device=dev)
+        f = lambda i: self.out_buf[i * B:(i + 1) * B]
+        self.out_type, self.match_dyn, self.match_static = f(0), f(1), f(2)
+        self.index_dyn, self.index_static, self.draft_len = f(3), f(4), f(5)
+        self.draft = self.out_buf[6 * B:].view(B, n)
         self._args = K.StepArgs()
+        self._io = None
 
     def reset(self, mask: Optional[torch.Tensor] = None):
         """DraftModel.reset (draft.py:47-50)."""
@@ -227,8 +234,9 @@ class DraftEngine:
                 self.static_cursor.masked_fill_(mask.bool().unsqueeze(1), 0)
 
     def step(self, tokens: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
-             start_tok: Optional[torch.Tensor] = None):
-        """update(tokens[:, :counts]) then lookup(start_tok); either half may be omitted."""
+             start_tok: Optional[torch.Tensor] = None, out_buf: Optional[torch.Tensor] = None):
+        """update(tokens[:, :counts]) then lookup(start_tok); either half may be omitted.  `out_buf` (same
+        layout as self.out_buf, device or pinned host memory) redirects every output."""
         a = self._args
         a.dyn = self.dyn.handle
         a.stat = self.static.handle if self.static is not None else None
@@ -243,12 +251,41 @@ class DraftEngine:
         a.start_tok_dev = K.ptr(_i32(start_tok)) if start_tok is not None else None
         a.flavour, a.n_predicts, a.len_bias, a.len_threshold, a.alpha = \
             self.flavour, self.n_predicts, self.len_bias, self.len_threshold, self.alpha
-        a.out_type_dev, a.out_match_dyn_dev, a.out_match_static_dev = \
-            self.out_type.data_ptr(), self.match_dyn.data_ptr(), self.match_static.data_ptr()
-        a.out_index_dyn_dev, a.out_index_static_dev = self.index_dyn.data_ptr(), self.index_static.data_ptr()
-        a.out_draft_dev, a.draft_stride, a.out_draft_len_dev = self.draft.data_ptr(), self.n_predicts, self.draft_len.data_ptr()
+        ob = self.out_buf if out_buf is None else _i32(out_buf)
+        assert ob.numel() == self.out_buf.numel()
+        base, B4 = ob.data_ptr(), 4 * self.dyn.n_requests
+        a.out_type_dev, a.out_match_dyn_dev, a.out_match_static_dev = base, base + B4, base + 2 * B4
+        a.out_index_dyn_dev, a.out_index_static_dev, a.out_draft_len_dev = base + 3 * B4, base + 4 * B4, base + 5 * B4
+        a.out_draft_dev, a.draft_stride = base + 6 * B4, self.n_predicts
         with torch.cuda.device(self.dyn.device):
             K.check(K.lib().samd_step(C.byref(a), K.stream_ptr()), "samd_step")
+
+    # ---- host-buffer path: one H2D copy in, one launch, one D2H copy out ---------------------------
+    def host_buffers(self, max_tokens_per_step: int = 8):
+        """Pinned host staging buffers for step_host(): `inp` = [counts (B) | start (B) | tokens (B x k)],
+        `out` = the layout of `out_buf`.  Returns (inp, out) int32 tensors."""
+        B, k = self.dyn.n_requests, int(max_tokens_per_step)
+        inp = torch.zeros(B * (2 + k), dtype=torch.int32).pin_memory()
+        out = torch.zeros(self.out_buf.numel(), dtype=torch.int32).pin_memory()
+        dev_in = torch.zeros(B * (2 + k), dtype=torch.int32, device=self.dyn.device)
+        self._io = (dev_in, k)
+        return inp, out
+
+    def step_host(self, inp: torch.Tensor, out: torch.Tensor, sync: bool = True, zero_copy: bool = True):
+        """DraftModel.update + lookup with HOST inputs / outputs (pinned buffers from host_buffers()).
+        zero_copy (default): the step kernel reads `inp` and writes `out` directly over PCIe (pinned memory
+        is mapped into the device address space) - one launch, no copy-engine operations.  Otherwise:
+        H2D copy, kernel, D2H copy on the stream.  By default waits until `out` is complete."""
+        dev_in, k = self._io
+        B = self.dyn.n_requests
+        if zero_copy:
+            self.step(inp[2 * B:].view(B, k), inp[:B], inp[B:2 * B], out_buf=out)
+        else:
+            dev_in.copy_(inp, non_blocking=True)
+            self.step(dev_in[2 * B:].view(B, k), dev_in[:B], dev_in[B:2 * B])
+            out.copy_(self.out_buf, non_blocking=True)
+        if sync:
+            torch.cuda.current_stream(self.dyn.device).synchronize()
 
     def tree_draft(self, start_tok: torch.Tensor, K_top: int = 8, max_paths: Optional[int] = None):
         """sam_only static tree for requests whose out_type is DRAFT_STATIC_TREE (after step())."""

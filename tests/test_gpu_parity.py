@@ -391,3 +391,90 @@ def test_verify_full_size_properties():
             want[:, s0:s0 + al] = t_ref[b].index_select(1, src)
             assert torch.equal(t[b], want)
         assert cache_len[b].item() == s0 + al
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3])
+def test_document_sharded_static_sam(world):
+    """per-shard packed keys + max-reduce + draft from the replicated corpus.  All shards
+    are built on this one GPU and the all-reduce is replaced by torch.maximum (the NCCL/gloo reduction
+    itself is covered by tests/test_dist_gloo.py and bench.py --gpus N)."""
+    E, K = _engine_mod()
+    from samd_b200 import dist as D, synth
+    docs = [d.tolist() for d in synth.make_corpus(30000, 500, 61, doc_len=(16, 96), singletons=True)]
+    eos = synth.EOS
+    nq, qlen = 64, 40
+    q = synth.corpus_queries([np.array(d) for d in docs], nq, qlen, 500, 62)
+    q[q == eos] = 9                                    # EOS-free queries: equality with the global automaton is exact
+    shards = [D.ShardedStaticSam(docs, eos, g, world, nq, torch.device("cuda")) for g in range(world)]
+    whole = O.build_static(docs, eos)
+    assert sum(s.sam.n_tokens for s in shards) == whole.n and shards[-1].offset + shards[-1].sam.n_tokens == whole.n
+    pos = 0
+    rng = np.random.default_rng(63)
+    cursors = [[0, 0] for _ in range(nq)]
+    while pos < qlen - 1:
+        k = int(rng.integers(1, 9))
+        k = min(k, qlen - 1 - pos)
+        tok = _dev_i32(q[:, pos:pos + k])
+        start = _dev_i32(q[:, pos + k])
+        keys = None
+        for s in shards:
+            s.advance(tok)
+            kk = s.local_keys(start).clone()
+            keys = kk if keys is None else torch.maximum(keys, kk)
+        match, draft = shards[0].draft(keys, start, 16)
+        torch.cuda.synchronize()
+        pos += k
+        for i in range(nq):
+            st, ln = cursors[i]
+            for t in q[i, pos - k:pos]:
+                st, ln = whole.step(st, ln, int(t))
+            cursors[i] = [st, ln]
+            s2, l2 = whole.step(st, ln, int(q[i, pos]))
+            assert match[i].item() == l2
+            if l2:
+                assert draft[i].tolist() == O.static_draft_samd(whole, s2, int(q[i, pos]), 16)
+
+
+# --------------------------------------------------------------------------------------
+def test_c2_full_size_against_c_oracle():
+    """BASELINE config 2 at FULL size: 1024 requests x 8192-token prompts, then 6 decode steps of 1-8
+    appended tokens.  Every request's match length, state index and 16-token draft is compared with the
+    oracle's C restatement (oracle/sam_oracle.c), and the automaton sizes (states, edges, clones) of all
+    1024 arenas must add up to the oracle's."""
+    E, K = _engine_mod()
+    from c_oracle import CSam
+    from samd_b200 import synth
+    R, N, steps = 1024, 8192, 6
+    total = N + 8 * steps + 1
+    rng = np.random.default_rng(20)
+    streams = np.stack([synth.copy_mix(total, 32000, 9000 + r, uniform_fresh=(r % 4 == 3)).astype(np.int32) for r in range(R)])
+    dyn = E.DynSamBatch(R, total + 8)
+    eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=16, len_bias=5, len_threshold=-BIG)
+    eng.step(_dev_i32(streams[:, :N]), None, None)
+    oracles = [CSam(total + 8) for _ in range(R)]
+    for r in range(R):
+        oracles[r].extend(streams[r, :N])
+    pos = np.full(R, N)
+    for s in range(steps):
+        cnt = rng.integers(1, 9, size=R).astype(np.int32)
+        tok = np.zeros((R, 8), dtype=np.int32)
+        for r in range(R):
+            tok[r, :cnt[r]] = streams[r, pos[r]:pos[r] + cnt[r]]
+            oracles[r].extend(tok[r, :cnt[r]])
+        pos += cnt
+        start = streams[np.arange(R), pos]
+        eng.step(_dev_i32(tok), _dev_i32(cnt), _dev_i32(start))
+        torch.cuda.synchronize()
+        idx, mlen, draft = eng.index_dyn.cpu().numpy(), eng.match_dyn.cpu().numpy(), eng.draft.cpu().numpy()
+        for r in range(R):
+            kind, seq, info = oracles[r].select_samd(None, int(start[r]), 16, 5, -BIG)
+            assert kind == 0 and (info[0], info[1]) == (idx[r], mlen[r]), (s, r)
+            assert seq == draft[r].tolist(), (s, r)
+    st = dyn.stats()
+    infos = [o.info() for o in oracles]
+    assert st["overflowed"] == 0
+    assert st["n_states"] == sum(i["n_states"] for i in infos)
+    assert st["n_edges"] == sum(i["n_edges"] for i in infos)
+    assert st["n_clones"] == sum(i["n_clones"] for i in infos)
+    assert st["tokens"] == int(pos.sum())

@@ -190,3 +190,53 @@ class _KeyOnly:
 
     def __lt__(self, other):
         return self.item[0] < other.item[0]
+
+
+# --------------------------------------------------------------------------------------
+# the C restatement (oracle/sam_oracle.c) against the same fixtures
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["v2", "v4", "mix1k", "mix4k", "light2k"])
+def test_c_oracle_dyn_matches_reference(name):
+    from c_oracle import CSam
+    z = load("dyn_sam.npz")
+    stream, cuts = z[f"{name}/stream"], z[f"{name}/cuts"]
+    so = unragged(z[f"{name}/draft_so_flat"], z[f"{name}/draft_so_offs"])
+    sam = CSam(len(stream) + 8)
+    lo = 0
+    for k, hi in enumerate(cuts):
+        sam.extend(stream[lo:hi])
+        lo = hi
+        tok = int(stream[hi])
+        i, l = sam.peek(tok)
+        assert (i, l) == (z[f"{name}/index"][k], z[f"{name}/match"][k])
+        assert sam.draft_samd(i, tok, 16) == z[f"{name}/draft16"][k].tolist()
+        assert sam.draft_samd(i, tok, 40) == z[f"{name}/draft40"][k].tolist()
+        assert sam.draft_so(i, l, tok, 40, 4.0) == so[k]
+    link, length, end = sam.export()
+    assert link.tolist() == z[f"{name}/link"].tolist()
+    assert length.tolist() == z[f"{name}/length"].tolist()
+    assert end.tolist() == z[f"{name}/min_endpos"].tolist()
+
+
+def test_c_oracle_static_and_selection_match_reference():
+    from c_oracle import CSam
+    z = load("draft_select.npz")
+    docs = docs_of(z)
+    st = CSam.build(docs, 2)
+    zs = load("static_sam.npz")
+    assert st.export()[0].tolist() == zs["mid/link"].tolist()          # same corpus as static_sam.npz "mid"
+    cuts_all = unragged(z["cuts_flat"], z["cuts_offs"])
+    k = 0
+    for r, stream in enumerate(z["streams"]):
+        dyn = CSam(len(stream) + 8)
+        st.reset_cursor()
+        lo = 0
+        for hi in cuts_all[r]:
+            dyn.extend(stream[lo:hi])
+            st.advance(stream[lo:hi])
+            lo = hi
+            kind, seq, _ = dyn.select_samd(st, int(stream[hi]), 16, 5, 5)
+            assert kind == z["samd_source"][k]
+            if kind != 2:
+                assert seq == z["samd_seq"][k].tolist()
+            k += 1
