@@ -25,13 +25,13 @@
 #define VW (VT / 32)
 #define UNROLL 8               // 128-bit loads in flight per lane
 #define KV_GROUP 8             // accepted rows staged in registers per pass
+#define MAX_WAVES 8            // KV work is released in up to this many request waves
 
 struct samd_verify_s {
     unsigned long long *node_key;   // [max_batch][max_nodes]
     int *done;                      // [max_batch]
-    int *active;                    // [2][max_batch] requests with rows to move (double-buffered by epoch parity)
-    int *counters;                  // {n_active[0], n_active[1], finished walks (monotonic), epoch whose walks are all done}
-    long long finished_total;
+    int *active;                    // [2][MAX_WAVES][max_batch] requests with rows to move (double-buffered by epoch parity)
+    int *counters;                  // [5][G]: n_active par0/par1, walked par0/par1, wave flags (epoch of completion)
     int *kv_start;                  // [max_batch] cache_len before the bump
     int max_batch, max_nodes, epoch, device, n_sms;
 };
@@ -40,8 +40,8 @@ struct VerifyParams {
     samd_verify_args a;
     unsigned long long *node_key;
     int *done, *active, *counters, *kv_start;
-    int max_nodes, max_batch, epoch, finished_target;
-    int chunk, chunks_per_row, n_items1, n_items2, vec_ok, stage_cap;
+    int max_nodes, max_batch, epoch;
+    int chunk, chunks_per_row, n_items1, n_items2, vec_ok, stage_cap, n_kv_ctas, n_waves;
 };
 
 template <int kDtype>
@@ -178,16 +178,28 @@ template <int kDtype>
 __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
     extern __shared__ int s_am_all[];                          // [VW][n_nodes] node argmax, one slab per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gwarp = warp * gridDim.x + blockIdx.x;          // warp-major: consecutive items land on different SMs
-    const int n_warps = gridDim.x * VW;
+    // Roles: the last n_kv_ctas CTAs (one per SM when the grid is full) only move KV rows, wave by wave, while
+    // the others stream logits - the row moves (256-byte granules, DRAM-activation bound) overlap the streaming.
+    const int n_stream_ctas = (int)gridDim.x - P.n_kv_ctas;
+    const bool kv_role = (int)blockIdx.x >= n_stream_ctas;
+    const int gwarp = warp * n_stream_ctas + blockIdx.x;      // warp-major: consecutive items land on different SMs
+    const int n_warps = n_stream_ctas * VW;
+    const int G = P.n_waves, par = P.epoch & 1;
+    int *cnt_active = P.counters + par * MAX_WAVES, *cnt_walked = P.counters + (2 + par) * MAX_WAVES;
+    int *wave_flag = P.counters + 4 * MAX_WAVES;
+    if (blockIdx.x == 0 && threadIdx.x < 2 * MAX_WAVES) {     // re-arm the other parity for the next launch
+        const int g = threadIdx.x % MAX_WAVES;
+        (threadIdx.x < MAX_WAVES ? P.counters + (par ^ 1) * MAX_WAVES : P.counters + (2 + (par ^ 1)) * MAX_WAVES)[g] = 0;
+    }
     const samd_verify_args &A = P.a;
     const int T = A.n_nodes;
     const int C = P.chunks_per_row;
-    int *s_am = s_am_all + warp * T;
+    int *s_am = s_am_all + warp * 2 * T;                     // [T] node argmax, then [T] tree tokens
+    int *s_tok = s_am + T;
     const uint16_t *logits = reinterpret_cast<const uint16_t *>(A.logits_dev);
 
     // ------------------------------ phase 1: argmax + path walk ---------------------------
-    for (int item = gwarp; item < P.n_items1; item += n_warps) {
+    for (int item = kv_role ? P.n_items1 : gwarp; item < P.n_items1; item += n_warps) {
         const int c = item % C;
         const int t = (item / C) % T;
         const int b = item / (C * T);
@@ -269,50 +281,78 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         if (!fin) continue;
 
         // ---- this warp finished request b: path walk (samd/utils.py:127-141) ------------------
+        // keys, tree tokens and this lane's path row are fetched together (one memory round trip); the walk
+        // itself then runs out of shared memory and registers
         __threadfence();
         if (lane == 0) P.done[b] = 0;
+        const int32_t *tok = A.tree_tokens_dev + (size_t)b * T;
+        const int n_paths = A.retrieve_dev ? (A.n_paths_dev ? A.n_paths_dev[b] : A.n_paths) : 1;
+        const int depth = A.retrieve_dev ? A.depth : n_rows;
+        constexpr int WD = 8;                                   // path depth held in registers
+        const bool fast = A.retrieve_dev && depth <= WD && n_paths <= 32;
+        int rp[WD];
+#pragma unroll
+        for (int j = 0; j < WD; ++j) rp[j] = (fast && lane < n_paths && j < depth) ? ri_at(P, b, lane, j) : -1;
         for (int i = lane; i < T; i += 32) {
             unsigned long long *kp = &P.node_key[(size_t)b * P.max_nodes + i];
             const unsigned long long k = __ldcg(kp);
+            s_tok[i] = i < n_rows ? tok[i] : 0;
             const int am = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
             s_am[i] = am;
             *kp = 0;                                            // re-arm for the next launch
             if (A.out_node_argmax_dev && i < n_rows) A.out_node_argmax_dev[(size_t)b * T + i] = am;
         }
         __syncwarp();
-        const int32_t *tok = A.tree_tokens_dev + (size_t)b * T;
-        const int n_paths = A.retrieve_dev ? (A.n_paths_dev ? A.n_paths_dev[b] : A.n_paths) : 1;
-        const int depth = A.retrieve_dev ? A.depth : n_rows;
         unsigned int bestpk = 0;
-        for (int p = lane; p < n_paths; p += 32) {
-            int acc = 0;
-            int prev = ri_at(P, b, p, 0);
-            for (int j = 0; j + 1 < depth; ++j) {
-                const int nxt = ri_at(P, b, p, j + 1);
-                const int rowi = prev < 0 ? n_rows - 1 : prev;           // -1 wraps to the last row
-                const int cand = nxt < 0 ? 0 : tok[nxt];                 // -1 selects the appended 0
-                if (cand != s_am[rowi]) break;
-                acc++;
-                prev = nxt;
+        if (fast) {
+            if (lane < n_paths) {
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j + 1 < WD; ++j) {
+                    if (j + 1 < depth && acc == j) {
+                        const int rowi = rp[j] < 0 ? n_rows - 1 : rp[j];          // -1 wraps to the last row
+                        const int cand = rp[j + 1] < 0 ? 0 : s_tok[rp[j + 1]];    // -1 selects the appended 0
+                        if (cand == s_am[rowi]) acc++;
+                    }
+                }
+                bestpk = ((unsigned)acc << 16) | (unsigned)(0xFFFF - lane);
             }
-            bestpk = max(bestpk, ((unsigned)acc << 16) | (unsigned)(0xFFFF - p));   // max accept, first path
+        } else {
+            for (int p = lane; p < n_paths; p += 32) {
+                int acc = 0;
+                int prev = ri_at(P, b, p, 0);
+                for (int j = 0; j + 1 < depth; ++j) {
+                    const int nxt = ri_at(P, b, p, j + 1);
+                    const int rowi = prev < 0 ? n_rows - 1 : prev;
+                    const int cand = nxt < 0 ? 0 : s_tok[nxt];
+                    if (cand != s_am[rowi]) break;
+                    acc++;
+                    prev = nxt;
+                }
+                bestpk = max(bestpk, ((unsigned)acc << 16) | (unsigned)(0xFFFF - p));   // max accept, first path
+            }
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) bestpk = max(bestpk, __shfl_xor_sync(SAMD_FULL, bestpk, o));
         const int acc = (int)(bestpk >> 16);
         const int best = acc == 0 ? 0 : (int)(0xFFFF - (bestpk & 0xFFFF));
         const int out_stride = A.retrieve_dev ? A.depth : T;
-        for (int j = lane; j < out_stride; j += 32) {
+        int moved = 0, last = 0;
+        for (int j0 = 0; j0 < out_stride; j0 += 32) {
+            const int j = j0 + lane;
             int tk = -1, ix = -1;
-            if (j <= acc) {
+            if (j < out_stride && j <= acc) {
                 ix = ri_at(P, b, best, j);
-                tk = ix < 0 ? 0 : tok[ix];
+                tk = ix < 0 ? 0 : s_tok[ix];
+                moved += ix != j;
             }
-            if (A.out_tokens_dev) A.out_tokens_dev[(size_t)b * out_stride + j] = tk;
-            if (A.out_indices_dev) A.out_indices_dev[(size_t)b * out_stride + j] = ix;
+            if (j < out_stride) {
+                if (A.out_tokens_dev) A.out_tokens_dev[(size_t)b * out_stride + j] = tk;
+                if (A.out_indices_dev) A.out_indices_dev[(size_t)b * out_stride + j] = ix;
+            }
+            if (acc >= j0 && acc < j0 + 32) last = __shfl_sync(SAMD_FULL, ix, acc - j0);
         }
         if (lane == 0) {
-            const int last = ri_at(P, b, best, acc);
             if (A.out_best_dev) A.out_best_dev[b] = best;
             if (A.out_accept_len_dev) A.out_accept_len_dev[b] = acc + 1;
             if (A.out_next_token_dev) A.out_next_token_dev[b] = s_am[last < 0 ? n_rows - 1 : last];
@@ -324,96 +364,99 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
             P.kv_start[b] = start;
         }
         // publish: requests that really move rows join the compact active list of phase 2
-        int moved = 0;
-        for (int j = lane; j <= acc; j += 32) moved += ri_at(P, b, best, j) != j;
         moved = __reduce_add_sync(SAMD_FULL, moved);
         __syncwarp();
         if (lane == 0) {
-            if (moved > 0 && P.n_items2 > 0) P.active[(P.epoch & 1) * P.max_batch + atomicAdd(&P.counters[P.epoch & 1], 1)] = b;
+            const int g = (int)(((long long)b * G) / A.batch);          // the request's wave
+            if (moved > 0 && P.n_items2 > 0) P.active[(size_t)(par * MAX_WAVES + g) * P.max_batch + atomicAdd(&cnt_active[g], 1)] = b;
             __threadfence();
-            // monotonic count of finished walks; whoever completes the batch raises the (write-once,
-            // read-many) flag the phase-2 pollers watch, so polling never contends with this atomic
-            if ((unsigned)(atomicAdd(&P.counters[2], 1) + 1) == (unsigned)P.finished_target) {
+            // whoever completes a wave raises its (write-once, read-many) flag; pollers never touch the counter
+            const int wave_size = (int)((((long long)g + 1) * A.batch + G - 1) / G - ((long long)g * A.batch + G - 1) / G);
+            if (atomicAdd(&cnt_walked[g], 1) + 1 == wave_size) {
                 __threadfence();
-                *reinterpret_cast<volatile int *>(&P.counters[3]) = P.epoch;
+                *reinterpret_cast<volatile int *>(&wave_flag[g]) = P.epoch;
             }
         }
         __syncwarp();
     }
 
     // ------------------------------ phase 2: KV row moves ---------------------------------
-    // All walks are awaited (phase 1 is a single wave, so they end together), then the moved rows of
-    // the active requests are flattened into 16-byte units and strided over every lane of the grid.
-    if (P.n_items2 > 0) {
-        if (gwarp == 0 && lane == 0) P.counters[(P.epoch + 1) & 1] = 0;      // re-arm the other list
-        __syncthreads();
-        if (threadIdx.x == 0) {                                 // one poller per CTA, plain loads, backoff
-            while (*reinterpret_cast<volatile int *>(&P.counters[3]) != P.epoch) __nanosleep(400);
-            __threadfence();
-        }
-        __syncthreads();
-        const int n_active = __ldcg(&P.counters[P.epoch & 1]);
-        const int *active = P.active + (P.epoch & 1) * P.max_batch;
+    // KV CTAs only.  Requests are released in G waves (phase 1 streams rows request-major, so waves finish
+    // in order); per wave the moved rows of the active requests are flattened into 16-byte units and strided
+    // over the lanes of all KV CTAs.
+    // (n_kv_ctas == 0: sequential mode - every CTA streams first, then every CTA moves rows, one wave)
+    if (P.n_items2 > 0 && (kv_role || P.n_kv_ctas == 0)) {
+        const int kwarp = P.n_kv_ctas ? warp * P.n_kv_ctas + ((int)blockIdx.x - n_stream_ctas) : gwarp;
+        const int n_kwarps = P.n_kv_ctas ? P.n_kv_ctas * VW : n_warps;
         const int cols = A.row_bytes >> 4;                      // 16-byte columns per (head,row)
         const int per_tensor = A.n_heads * cols;
         const long long per_req = (long long)A.n_kv * per_tensor;
-        const long long total = per_req * n_active;
-        // stage the active requests' move lists in shared memory once per CTA: the copy loop then has
-        // no dependent metadata loads in front of its row loads
         constexpr int MW = 3 + KV_GROUP;                       // {request, accept_len, start, first KV_GROUP sources}
-        int *s_meta = s_am_all + VW * T;
-        const int staged = min(n_active, P.stage_cap);
-        for (int i = threadIdx.x; i < staged * MW; i += VT) {
-            const int a_i = i / MW, f = i - a_i * MW;
-            const int b = __ldcg(active + a_i);
-            int v;
-            if (f == 0) v = b;
-            else if (f == 1) v = __ldcg(A.out_accept_len_dev + b);
-            else if (f == 2) v = __ldcg(P.kv_start + b);
-            else {
-                const int j = f - 3;
-                v = j < __ldcg(A.out_accept_len_dev + b) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j) : j;
+        int *s_meta = s_am_all + VW * 2 * T;
+        for (int g = 0; g < G; ++g) {
+            __syncthreads();
+            if (threadIdx.x == 0) {                             // one poller per CTA, plain loads, backoff
+                while (*reinterpret_cast<volatile int *>(&wave_flag[g]) != P.epoch) __nanosleep(300);
+                __threadfence();
             }
-            s_meta[i] = v;
-        }
-        __syncthreads();
-        for (long long g = (long long)gwarp * 32 + lane; g < total; g += (long long)n_warps * 32) {
-            const int a_i = (int)(g / per_req);
-            const int unit = (int)(g - (long long)a_i * per_req);
-            int b, acc1, start;
-            int src[KV_GROUP];
-            if (a_i < staged) {
-                const int *m = s_meta + a_i * MW;
-                b = m[0];
-                acc1 = m[1];
-                start = m[2];
-#pragma unroll
-                for (int u = 0; u < KV_GROUP; ++u) src[u] = m[3 + u];
-            } else {
-                b = __ldcg(active + a_i);
-                acc1 = __ldcg(A.out_accept_len_dev + b);
-                start = __ldcg(P.kv_start + b);
-#pragma unroll
-                for (int u = 0; u < KV_GROUP; ++u) src[u] = u < acc1 ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + u) : u;
-            }
-            const int kv = unit / per_tensor;
-            const int w = unit - kv * per_tensor;
-            const int hd = w / cols, col = w - hd * cols;
-            char *hb = reinterpret_cast<char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.kv_ptrs_dev) + kv)) +
-                       (size_t)b * A.kv_batch_stride + (size_t)hd * A.kv_head_stride + ((size_t)col << 4);
-            for (int j0 = 0; j0 < acc1; j0 += KV_GROUP) {
-                uint4 val[KV_GROUP];
-                if (j0 > 0) {
-#pragma unroll
-                    for (int u = 0; u < KV_GROUP; ++u)
-                        src[u] = (j0 + u < acc1) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j0 + u) : j0 + u;
+            __syncthreads();
+            const int n_active = __ldcg(&cnt_active[g]);
+            const int *active = P.active + (size_t)(par * MAX_WAVES + g) * P.max_batch;
+            const long long total = per_req * n_active;
+            // stage the wave's move lists in shared memory: no dependent metadata loads in the copy loop
+            const int staged = min(n_active, P.stage_cap);
+            for (int i = threadIdx.x; i < staged * MW; i += VT) {
+                const int a_i = i / MW, f = i - a_i * MW;
+                const int b = __ldcg(active + a_i);
+                int v;
+                if (f == 0) v = b;
+                else if (f == 1) v = __ldcg(A.out_accept_len_dev + b);
+                else if (f == 2) v = __ldcg(P.kv_start + b);
+                else {
+                    const int j = f - 3;
+                    v = j < __ldcg(A.out_accept_len_dev + b) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j) : j;
                 }
+                s_meta[i] = v;
+            }
+            __syncthreads();
+            for (long long u = (long long)kwarp * 32 + lane; u < total; u += (long long)n_kwarps * 32) {
+                const int a_i = (int)(u / per_req);
+                const int unit = (int)(u - (long long)a_i * per_req);
+                int b, acc1, start;
+                int src[KV_GROUP];
+                if (a_i < staged) {
+                    const int *m = s_meta + a_i * MW;
+                    b = m[0];
+                    acc1 = m[1];
+                    start = m[2];
 #pragma unroll
-                for (int u = 0; u < KV_GROUP; ++u)
-                    if (src[u] != j0 + u) val[u] = *reinterpret_cast<const uint4 *>(hb + (size_t)(start + src[u]) * A.kv_pos_stride);
+                    for (int q = 0; q < KV_GROUP; ++q) src[q] = m[3 + q];
+                } else {
+                    b = __ldcg(active + a_i);
+                    acc1 = __ldcg(A.out_accept_len_dev + b);
+                    start = __ldcg(P.kv_start + b);
 #pragma unroll
-                for (int u = 0; u < KV_GROUP; ++u)
-                    if (src[u] != j0 + u) *reinterpret_cast<uint4 *>(hb + (size_t)(start + j0 + u) * A.kv_pos_stride) = val[u];
+                    for (int q = 0; q < KV_GROUP; ++q) src[q] = q < acc1 ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + q) : q;
+                }
+                const int kv = unit / per_tensor;
+                const int w = unit - kv * per_tensor;
+                const int hd = w / cols, col = w - hd * cols;
+                char *hb = reinterpret_cast<char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.kv_ptrs_dev) + kv)) +
+                           (size_t)b * A.kv_batch_stride + (size_t)hd * A.kv_head_stride + ((size_t)col << 4);
+                for (int j0 = 0; j0 < acc1; j0 += KV_GROUP) {
+                    uint4 val[KV_GROUP];
+                    if (j0 > 0) {
+#pragma unroll
+                        for (int q = 0; q < KV_GROUP; ++q)
+                            src[q] = (j0 + q < acc1) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j0 + q) : j0 + q;
+                    }
+#pragma unroll
+                    for (int q = 0; q < KV_GROUP; ++q)
+                        if (src[q] != j0 + q) val[q] = *reinterpret_cast<const uint4 *>(hb + (size_t)(start + src[q]) * A.kv_pos_stride);
+#pragma unroll
+                    for (int q = 0; q < KV_GROUP; ++q)
+                        if (src[q] != j0 + q) *reinterpret_cast<uint4 *>(hb + (size_t)(start + j0 + q) * A.kv_pos_stride) = val[q];
+                }
             }
         }
     }
@@ -429,14 +472,13 @@ extern "C" int samd_verify_create(int max_batch, int max_nodes, samd_verify_t *o
     SAMD_CUDA(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, h->device));
     SAMD_CUDA(cudaMalloc(&h->node_key, (size_t)max_batch * max_nodes * sizeof(unsigned long long)));
     SAMD_CUDA(cudaMalloc(&h->done, (size_t)max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMalloc(&h->active, (size_t)2 * max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMalloc(&h->counters, 4 * sizeof(int)));
-    h->finished_total = 0;
+    SAMD_CUDA(cudaMalloc(&h->active, (size_t)2 * MAX_WAVES * max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMalloc(&h->counters, 5 * MAX_WAVES * sizeof(int)));
     SAMD_CUDA(cudaMalloc(&h->kv_start, (size_t)max_batch * sizeof(int)));
     SAMD_CUDA(cudaMemset(h->node_key, 0, (size_t)max_batch * max_nodes * sizeof(unsigned long long)));
     SAMD_CUDA(cudaMemset(h->done, 0, (size_t)max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMemset(h->active, 0, (size_t)2 * max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMemset(h->counters, 0, 4 * sizeof(int)));
+    SAMD_CUDA(cudaMemset(h->active, 0, (size_t)2 * MAX_WAVES * max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMemset(h->counters, 0, 5 * MAX_WAVES * sizeof(int)));
     SAMD_CUDA(cudaMemset(h->kv_start, 0, (size_t)max_batch * sizeof(int)));
     SAMD_CUDA(cudaDeviceSynchronize());
     *out = h;
@@ -455,7 +497,9 @@ extern "C" int samd_verify_destroy(samd_verify_t h) {
 }
 
 static int g_chunk_override = 0;
+static int g_overlap_mode = 0;
 extern "C" void samd_verify_set_chunk(int elements) { g_chunk_override = elements; }
+extern "C" void samd_verify_set_overlap(int on) { g_overlap_mode = on; }
 
 extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, void *stream) {
     SAMD_REQUIRE(h && a, "samd_verify_compact: bad arguments");
@@ -482,37 +526,53 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     P.active = h->active;
     P.counters = h->counters;
     P.max_batch = h->max_batch;
-    h->finished_total += a->batch;
-    P.finished_target = (int)(uint32_t)h->finished_total;     // device counter wraps mod 2^32 as well
     P.kv_start = h->kv_start;
     P.max_nodes = h->max_nodes;
     P.epoch = ++h->epoch;
     P.stage_cap = move ? std::min(a->batch, 512) : 0;
-    const size_t smem = ((size_t)VW * a->n_nodes + (size_t)P.stage_cap * (3 + KV_GROUP)) * sizeof(int);
+    const size_t smem = ((size_t)VW * 2 * a->n_nodes + (size_t)P.stage_cap * (3 + KV_GROUP)) * sizeof(int);
     auto kern = a->dtype == SAMD_DTYPE_BF16   ? verify_compact_kernel<SAMD_DTYPE_BF16>
                 : a->dtype == SAMD_DTYPE_FP16 ? verify_compact_kernel<SAMD_DTYPE_FP16>
                                               : verify_compact_kernel<SAMD_DTYPE_FP32>;
     int per_sm = 0;
     SAMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, VT, smem));
     SAMD_REQUIRE(per_sm > 0, "samd_verify_compact: kernel does not fit on an SM");
-    const long long resident_warps = (long long)h->n_sms * per_sm * VW;
-    // split rows into chunks only when whole rows would leave most of the machine idle
+    // persistent grid: every CTA must be resident (KV CTAs spin on the streaming CTAs' results)
     const long long rows = (long long)a->batch * a->n_nodes;
+    long long grid;
     int chunks = 1;
-    if (g_chunk_override > 0) chunks = (a->vocab + g_chunk_override - 1) / g_chunk_override;
-    else
+    if (move && !g_overlap_mode) {
+        // sequential mode (default): all CTAs stream the logits in one wave, then all CTAs move the rows.
+        // Measured on B200 (C4): 90 us; dedicating a quarter of the CTAs to row moves that overlap the
+        // streaming (overlap mode below) measured 111 us - the moves are bound by DRAM row activations and
+        // need every lane in flight, and they steal DRAM cycles from the stream.
+        grid = std::max<long long>(1, (long long)h->n_sms * per_sm);
+        P.n_kv_ctas = 0;
+        P.n_waves = 1;
+        while (rows * chunks * 2 <= grid * VW && a->vocab / (chunks * 2) >= 2048) chunks *= 2;
+    } else if (move) {
+        grid = std::max<long long>(2, (long long)h->n_sms * per_sm);
+        P.n_kv_ctas = (int)std::max<long long>(1, grid / 4);     // one KV CTA per SM when per_sm == 4
+        P.n_waves = std::min(std::min(a->batch, 4), MAX_WAVES);
+        // short rounds so that request waves complete (and release their KV work) progressively
+        const long long stream_warps = (grid - P.n_kv_ctas) * VW;
+        while (rows * chunks < 4 * stream_warps && a->vocab / (chunks * 2) >= 2048) chunks *= 2;
+    } else {
+        const long long resident_warps = (long long)h->n_sms * per_sm * VW;
+        P.n_kv_ctas = 0;
+        P.n_waves = 1;
+        // split rows into chunks only when whole rows would leave most of the machine idle
         while (rows * chunks * 2 <= resident_warps && a->vocab / (chunks * 2) >= 2048) chunks *= 2;
+        grid = 0;
+    }
+    if (g_chunk_override > 0) chunks = (a->vocab + g_chunk_override - 1) / g_chunk_override;
     int chunk = ((a->vocab + chunks - 1) / chunks + 7) & ~7;
     P.chunk = chunk;
     P.chunks_per_row = (a->vocab + chunk - 1) / chunk;
     P.n_items1 = a->batch * a->n_nodes * P.chunks_per_row;
     P.n_items2 = move ? a->batch * a->n_kv : 0;
     P.vec_ok = ((uintptr_t)a->logits_dev % 16 == 0) && (a->batch_stride % 8 == 0) && (a->row_stride % 8 == 0);
-    // persistent grid: every CTA must be resident (phase 2 spins on phase-1 results)
-    const long long want_warps = std::max<long long>(P.n_items1, P.n_items2);
-    long long grid = std::min<long long>((long long)h->n_sms * per_sm, (want_warps + VW - 1) / VW);
-    if (move) grid = (long long)h->n_sms * per_sm;             // phase 2 strides its units over the whole machine
-    if (grid < 1) grid = 1;
+    if (!move) grid = std::max<long long>(1, std::min<long long>((long long)h->n_sms * per_sm, ((long long)P.n_items1 + VW - 1) / VW));
     kern<<<(int)grid, VT, smem, (cudaStream_t)stream>>>(P);
     samd_count_launch();
     SAMD_CUDA(cudaGetLastError());
