@@ -380,6 +380,11 @@ def run_ours(a):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650"
     achieved = alg_bytes_per_launch / (kern_ms * 1e-3) / 1e9
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+    except Exception:
+        pass
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": S, "warmup": W,
         "ms_per_step": dev_ms / S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -388,7 +393,8 @@ def run_ours(a):
                 "ms_per_step": e2e_ms / S},
         "gpu_launches": None,
         "roofline": {"kernel": "sam_step_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": traffic.get("sam_step_kernel", {}).get("bytes_per_launch"),
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launch_us": kern_ms * 1e3,
                      "note": "latency-bound pointer chase: queries/s and probes/query are the figures of merit"},
         "step_kernel": {"us_per_launch_events": kern_ms * 1e3, "us_per_step_graph": dev_ms / S * 1e3,
@@ -405,12 +411,17 @@ def run_ours(a):
     if rank == 0 and not a.no_extras:
         try:
             out["verify"] = bench_verify(a, dev, hbm_peak)
+            out["verify"]["roofline"]["traffic"] = traffic.get("verify_compact_kernel", {}).get("bytes_per_launch")
         except Exception as e:  # side measurement must not kill the headline line
             out["verify"] = {"error": repr(e)}
         try:
             out["static"] = bench_static(a, dev)
         except Exception as e:
             out["static"] = {"error": repr(e)}
+        try:
+            out["c1"] = bench_c1(a, dev)
+        except Exception as e:
+            out["c1"] = {"error": repr(e)}
     if rank == 0 and not a.no_cpu:
         cores = min(os.cpu_count() or 1, 32)
         n_sample = cores * 64
@@ -523,6 +534,67 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5):
                          "unit": "GB/s", "frac": gbs_full / hbm_peak, "traffic": None},
             "roofline_verify_only": {"achieved": gbs_nokv, "peak": hbm_peak, "unit": "GB/s", "frac": gbs_nokv / hbm_peak},
             "gpu_launches_per_step": 1}
+
+
+def bench_c1(a, dev, prompt=4096, steps=256):
+    """Config c1 (the reference demo's shape, tests/test_samd_sam_only.py): ONE request, 4k-token prompt, samd_sam_only
+    flavour (max_predicts 40, alpha 4).  Latency comparison: a single warp walks the chain, so this is the regime
+    where a CPU core is competitive - reported for completeness, next to the Python / C ports on one core."""
+    import torch
+    from samd_b200 import _cabi as K, engine as E, synth
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    stream = synth.copy_mix(prompt + 8 * steps + 1, VOCAB, 1000).astype(np.int32)
+    rng = np.random.default_rng(1001)
+    counts = rng.integers(1, 9, size=steps).astype(np.int32)
+    ends = prompt + np.cumsum(counts)
+    dyn = E.DynSamBatch(1, prompt + 8 * steps + 16, dev)
+    eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAM_ONLY, n_predicts=40, len_bias=5, alpha=4.0)
+    d_prompt = torch.as_tensor(stream[None, :prompt]).to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.step(d_prompt, None, None)
+    e1.record()
+    torch.cuda.synchronize()
+    build_ms = e0.elapsed_time(e1)
+    toks = [torch.as_tensor(stream[None, ends[i] - counts[i]:ends[i]]).to(dev) for i in range(steps)]
+    starts = [torch.as_tensor(stream[ends[i]:ends[i] + 1]).to(dev) for i in range(steps)]
+    g = torch.cuda.CUDAGraph()
+    snap = E.DynSamBatch(1, dyn.max_tokens, dev)
+    snap.copy_from(dyn)
+    with torch.cuda.graph(g):
+        for i in range(steps):
+            eng.step(toks[i], None, starts[i])
+    g.replay()
+    torch.cuda.synchronize()
+    dyn.copy_from(snap)
+    torch.cuda.synchronize()
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    gpu_us = e0.elapsed_time(e1) / steps * 1e3
+    # one CPU core: Python port and C restatement on the same stream
+    import samd_oracle as O
+    import c_oracle as CO
+    t0 = time.perf_counter()
+    po = O.Automaton()
+    po.extend(stream[:prompt].tolist())
+    py_build = time.perf_counter() - t0
+    empty = O.Automaton()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        po.extend(stream[ends[i] - counts[i]:ends[i]].tolist())
+        O.select_sam_only(po, empty, None, int(stream[ends[i]]), 40, 4.0, 8, 5)
+    py_us = (time.perf_counter() - t0) / steps * 1e6
+    co = CO.CSam(len(stream) + 8)
+    t0 = time.perf_counter()
+    co.extend(stream[:prompt])
+    c_build = time.perf_counter() - t0
+    return {"workload": f"c1: one request, {prompt}-token prompt, {steps} steps of 1-8 appended tokens + lookup + draft "
+                        f"(samd_sam_only flavour, max_predicts 40, alpha 4)",
+            "gpu_build_tokens_per_s": prompt / (build_ms * 1e-3), "gpu_us_per_step": gpu_us,
+            "cpu_python_port_build_tokens_per_s": prompt / py_build, "cpu_python_port_us_per_step": py_us,
+            "cpu_c_port_build_tokens_per_s": prompt / c_build, "cores": 1}
 
 
 def bench_static(a, dev, n_corpus=2_000_000, n_q=4096, steps=64, warm=8):
