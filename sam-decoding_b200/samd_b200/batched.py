@@ -1,0 +1,167 @@
+"""Batched (B > 1) speculative decode loop on top of the C ABI - SURVEY.md section 8f row 3.
+
+The reference hard-wires batch size 1 (samd/samd_model.py:240).  Its per-request logic is applied here to B
+requests in lockstep, with everything that the reference does on the host kept on the device:
+
+    prefill (ragged prompts, right padded)                      -> DraftModel.update for every request
+    loop:  samd_step            accepted tokens in, drafts out   (one launch for the whole batch)
+           LM forward           [B, n_predicts] draft tokens, per-request positions, per-request KV offsets
+           samd_verify_compact  accept lengths, accepted tokens, next tokens, cache_len += accept_len
+           one tiny device->host read (all-finished flag) per step
+
+Drafts are sequences of `n_predicts` tokens (the samd flavour's sequence type).  A request whose suffix match is
+below `len_threshold` - where the reference would fall back to its tree model - simply verifies its start token
+(draft = [start, pad...]); greedy verification makes any draft lossless, so the output stream equals plain
+greedy decoding token for token.  KV rows are written at per-request offsets, so no compaction is needed for
+sequence drafts (cache.py:123-126,133).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from transformers.cache_utils import Cache, CacheLayerMixin
+
+from . import _cabi as K
+from . import engine as E
+
+
+class _Layer(CacheLayerMixin):
+    is_compileable = False
+    is_sliding = False
+
+    def __init__(self, parent, idx):
+        super().__init__()
+        self.parent, self.idx = parent, idx
+        self.is_initialized = True
+
+    def lazy_initialization(self, key_states, value_states):
+        pass
+
+    def update(self, key_states, value_states, *args, **kwargs):
+        return self.parent.write(key_states, value_states, self.idx)
+
+    def get_mask_sizes(self, query_length):
+        return self.parent.kv_len, 0
+
+    def get_seq_length(self):
+        return 0
+
+    def get_max_cache_shape(self):
+        return self.parent.max_len
+
+    def reset(self):
+        pass
+
+
+class RaggedKVCache(Cache):
+    """[2L, B, H_kv, max_len, D_h] with a device-side length per request (SamdStaticCache generalised to B > 1):
+    new rows are written at cache_len[b] + t."""
+
+    def __init__(self, config, batch, max_len, dtype, device):
+        L = config.num_hidden_layers
+        super().__init__(layers=[_Layer(self, i) for i in range(L)])
+        heads = getattr(config, "num_key_value_heads", None) or config.num_attention_heads
+        dh = getattr(config, "head_dim", None) or config.hidden_size // config.num_attention_heads
+        self.kv = torch.zeros(2 * L, batch, heads, max_len, dh, dtype=dtype, device=device)
+        self.n_layers, self.batch, self.max_len = L, batch, max_len
+        self.cache_len = torch.zeros(batch, dtype=torch.int32, device=device)
+        self.kv_len = 0                 # key length the current forward attends over
+        self.rows = None                # [B, T] absolute row of every new token in the current forward
+        self._bidx = torch.arange(batch, device=device)[:, None]
+
+    def begin(self, n_new: int, kv_len: int):
+        self.rows = self.cache_len.long()[:, None] + torch.arange(n_new, device=self.kv.device)[None, :]
+        self.kv_len = kv_len
+
+    def write(self, k, v, layer):
+        kc, vc = self.kv[layer], self.kv[self.n_layers + layer]
+        kc[self._bidx, :, self.rows] = k.transpose(1, 2)
+        vc[self._bidx, :, self.rows] = v.transpose(1, 2)
+        return kc[:, :, :self.kv_len], vc[:, :, :self.kv_len]
+
+    def get_seq_length(self, layer_idx=0):
+        return 0
+
+
+class BatchedSamdDecoder:
+    def __init__(self, lm, batch: int, max_cache_len: int, n_predicts: int = 16, len_bias: int = 5, len_threshold: int = 5,
+                 static: Optional[E.StaticSamDevice] = None, eos_token_id: Optional[int] = None, max_tokens: int = 16384,
+                 dtype=torch.float16, device="cuda"):
+        self.lm, self.B, self.T = lm, batch, n_predicts
+        self.device, self.dtype, self.eos = torch.device(device), dtype, eos_token_id
+        self.cache = RaggedKVCache(lm.config, batch, max_cache_len, dtype, self.device)
+        self.dyn = E.DynSamBatch(batch, max_tokens, self.device)
+        self.eng = E.DraftEngine(self.dyn, static, K.FLAVOUR_SAMD, n_predicts=n_predicts, len_bias=len_bias,
+                                 len_threshold=len_threshold)
+        self.ver = E.Verifier(batch, n_predicts, self.device)
+        self._ar = torch.arange(n_predicts, device=self.device)
+
+    def _mask(self, n_new: int, kv_len: int, base: torch.Tensor) -> torch.Tensor:
+        """[B, 1, n_new, kv_len] additive mask: token t of request b sees keys j <= base[b] + t."""
+        j = torch.arange(kv_len, device=self.device)[None, None, :]
+        lim = (base.long()[:, None] + torch.arange(n_new, device=self.device)[None, :])[:, :, None]
+        m = torch.zeros(self.B, n_new, kv_len, dtype=self.dtype, device=self.device)
+        m.masked_fill_(j > lim, torch.finfo(self.dtype).min)
+        return m[:, None]
+
+    @torch.inference_mode()
+    def generate(self, prompts: Sequence[Sequence[int]], max_new_tokens: int):
+        B, T, dev = self.B, self.T, self.device
+        assert len(prompts) == B
+        lens = torch.tensor([len(p) for p in prompts], dtype=torch.int32, device=dev)
+        n_max = int(lens.max())
+        ids = torch.zeros(B, n_max, dtype=torch.long, device=dev)
+        for b, p in enumerate(prompts):
+            ids[b, :len(p)] = torch.as_tensor(p, dtype=torch.long)
+        # ---- prefill ------------------------------------------------------------------------
+        self.eng.reset()
+        self.cache.cache_len.zero_()
+        self.cache.begin(n_max, n_max)
+        pos = torch.arange(n_max, device=dev)[None, :].expand(B, -1)
+        logits = self.lm(input_ids=ids, position_ids=pos, past_key_values=self.cache,
+                         attention_mask=self._mask(n_max, n_max, torch.zeros(B, dtype=torch.int32, device=dev))).logits
+        self.cache.cache_len.copy_(lens)
+        self.eng.step(ids.to(torch.int32).contiguous(), lens, None)                # DraftModel.update(prompt), ragged counts
+        start = logits[torch.arange(B, device=dev), lens.long() - 1].argmax(-1).to(torch.int32)
+        out = torch.zeros(B, max_new_tokens + T, dtype=torch.int32, device=dev)
+        out_len = torch.zeros(B, dtype=torch.int32, device=dev)
+        done = torch.zeros(B, dtype=torch.bool, device=dev)
+        acc_tokens = torch.zeros(B, T, dtype=torch.int32, device=dev)
+        acc_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        steps, accept_hist, res = 0, [], None
+        # ---- decode ---------------------------------------------------------------------------
+        while True:
+            self.eng.step(acc_tokens, acc_count, start)                            # update(accepted) + lookup(start): one launch
+            draft = self.eng.draft
+            draft[:, 0] = start                                                    # short matches verify the start token only
+            kv_len = int(self.cache.cache_len.max()) + T
+            self.cache.begin(T, kv_len)
+            pos = self.cache.cache_len.long()[:, None] + self._ar[None, :]
+            logits = self.lm(input_ids=draft.long(), position_ids=pos, past_key_values=self.cache,
+                             attention_mask=self._mask(T, kv_len, self.cache.cache_len)).logits
+            saved_len = self.cache.cache_len.clone()
+            res = self.ver.verify(logits.contiguous(), draft, None, cache_len=self.cache.cache_len, out=res)
+            n_acc = torch.where(done, torch.zeros_like(res["accept_len"]), res["accept_len"])
+            if self.eos is not None:                                               # truncate at the first EOS (samd_model.py:257-263)
+                is_eos = (res["tokens"] == self.eos) & (self._ar[None, :] < n_acc[:, None])
+                first = torch.where(is_eos.any(1), is_eos.int().argmax(1).int() + 1, n_acc)
+                done = done | is_eos.any(1)
+                n_acc = torch.minimum(n_acc, first)
+            room = (max_new_tokens - out_len).clamp(min=0)
+            n_emit = torch.minimum(n_acc, room)
+            cols = out_len.long()[:, None] + self._ar[None, :]
+            keep = self._ar[None, :] < n_emit[:, None]
+            out.scatter_(1, torch.where(keep, cols, torch.full_like(cols, max_new_tokens + T - 1)),
+                         torch.where(keep, res["tokens"], torch.zeros_like(res["tokens"])))
+            out_len = out_len + n_emit
+            done = done | (out_len >= max_new_tokens)
+            self.cache.cache_len.copy_(saved_len + n_acc)                           # finished requests stop advancing
+            acc_tokens, acc_count, start = res["tokens"], n_acc, res["next_token"]
+            steps += 1
+            accept_hist.append(n_acc)
+            if bool(done.all()):                                                   # the step's one host sync
+                break
+        lens_out = out_len.tolist()
+        rows = out.tolist()
+        return [rows[b][:lens_out[b]] for b in range(B)], dict(steps=steps, accept_lengths=torch.stack(accept_hist, 1).tolist())

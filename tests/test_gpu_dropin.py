@@ -222,3 +222,25 @@ def test_generate_is_lossless_on_a_tiny_llama(pkg):
     assert len(out.output_ids[0]) == prompt.shape[1] + n_new
     assert sum(out.accepet_length_per_step) >= n_new and out.decode_steps < n_new      # some drafts were accepted
     assert out.decode_tokens == sum(out.accepet_length_per_step)
+
+
+def test_batched_decoder_is_lossless_on_a_tiny_llama():
+    """B = 4 requests with ragged prompts decoded in lockstep (one samd_step launch,
+    one LM forward, one samd_verify_compact launch per step, per-request KV offsets) must reproduce plain
+    greedy decoding of every request, including EOS truncation."""
+    from samd_b200 import synth
+    from samd_b200.batched import BatchedSamdDecoder
+    lm = _tiny_llama(torch.float32)
+    prompts = [synth.copy_mix(n, 96, 300 + i, p_copy=0.7).tolist() for i, n in enumerate((150, 97, 200, 64))]
+    n_new = 64
+    want = [_plain_greedy(lm, torch.as_tensor([p]).cuda(), n_new)[len(p):] for p in prompts]
+    dec = BatchedSamdDecoder(lm, 4, 512, n_predicts=8, len_bias=5, len_threshold=3, dtype=torch.float32)
+    got, stats = dec.generate(prompts, n_new)
+    assert got == want
+    assert stats["steps"] < n_new                                  # drafts were accepted
+    eos = want[1][10]                                              # pick a token request 1 really emits
+    dec2 = BatchedSamdDecoder(lm, 4, 512, n_predicts=8, len_bias=5, len_threshold=3, eos_token_id=eos, dtype=torch.float32)
+    got2, _ = dec2.generate(prompts, n_new)
+    for g, w in zip(got2, want):
+        cut = w.index(eos) + 1 if eos in w else len(w)
+        assert g == w[:cut]
