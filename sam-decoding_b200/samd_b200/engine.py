@@ -329,6 +329,7 @@ class Verifier:
         self._args = K.VerifyArgs()
         self._kv_key = None
         self._kv_ptrs = None
+        self._last_key, self._last_out = None, None
 
     def bind_kv(self, kv_tensors: Optional[List[torch.Tensor]]):
         """Register the 2L cache tensors [B, H, max_len, Dh] (key_cache + value_cache order)."""
@@ -351,6 +352,14 @@ class Verifier:
     def verify(self, logits: torch.Tensor, tree_tokens: torch.Tensor, retrieve: Optional[torch.Tensor],
                cache_len: Optional[torch.Tensor] = None, move_kv: bool = True, n_nodes: Optional[torch.Tensor] = None,
                n_paths: Optional[torch.Tensor] = None, out: Optional[dict] = None, want_argmax: bool = False) -> dict:
+        # fast path: identical buffers as the previous call -> relaunch with the argument block as it is
+        key = (logits.data_ptr(), logits.shape, logits.stride(), logits.dtype, tree_tokens.data_ptr(),
+               None if retrieve is None else (retrieve.data_ptr(), retrieve.shape), K.ptr(cache_len), bool(move_kv),
+               K.ptr(n_nodes), K.ptr(n_paths), None if out is None else out["tokens"].data_ptr(), want_argmax, self._kv_key)
+        if key == getattr(self, "_last_key", None) and out is self._last_out:
+            with torch.cuda.device(self.device):
+                K.check(K.lib().samd_verify_compact(self._h, C.byref(self._args), K.stream_ptr()), "samd_verify_compact")
+            return out
         assert logits.is_cuda and logits.dim() == 3 and logits.stride(2) == 1
         B, T, V = logits.shape
         dt = {torch.bfloat16: K.DTYPE_BF16, torch.float16: K.DTYPE_FP16, torch.float32: K.DTYPE_FP32}.get(logits.dtype)
@@ -384,7 +393,8 @@ class Verifier:
         else:
             a.kv_ptrs_dev, a.n_kv, a.move_kv = None, 0, 0
         a.cache_len_dev = K.ptr(_i32(cache_len)) if cache_len is not None else None
-        if out is None or out["tokens"].shape != (B, width):
+        fresh = out is None or out["tokens"].shape != (B, width)
+        if fresh:
             mk = lambda *s: torch.empty(*s, dtype=torch.int32, device=logits.device)
             out = dict(best=mk(B), accept_len=mk(B), next_token=mk(B), tokens=mk(B, width), indices=mk(B, width))
         if want_argmax and "node_argmax" not in out:
@@ -395,6 +405,9 @@ class Verifier:
         a.out_node_argmax_dev = out["node_argmax"].data_ptr() if want_argmax else None
         with torch.cuda.device(self.device):
             K.check(K.lib().samd_verify_compact(self._h, C.byref(a), K.stream_ptr()), "samd_verify_compact")
+        # remember the argument block for the fast path (keyed on the caller-provided `out`, if any)
+        self._last_key = key[:10] + (out["tokens"].data_ptr(),) + key[11:]
+        self._last_out = out
         return out
 
     def close(self):

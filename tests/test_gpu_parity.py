@@ -478,3 +478,40 @@ def test_c2_full_size_against_c_oracle():
     assert st["n_edges"] == sum(i["n_edges"] for i in infos)
     assert st["n_clones"] == sum(i["n_clones"] for i in infos)
     assert st["tokens"] == int(pos.sum())
+
+
+def test_verify_compact_is_graph_replayable():
+    """The fused kernel keeps its launch epoch in device memory, so a captured launch can be replayed: three
+    replays on fresh KV copies must each produce the reference result (golden KV fixture, 16 requests)."""
+    E, K = _engine_mod()
+    z = load("verify.npz")
+    init = torch.from_numpy(z["kv/init_bits"]).view(torch.bfloat16)
+    cases = z["kv/cases"]
+    n_case = len(cases)
+    sel = [int(b) for b, _ in cases]
+    lg = torch.from_numpy(z["bf16/logits_bits"]).view(torch.bfloat16)[sel].contiguous().cuda()
+    tok = _dev_i32(z["tree_tokens"][sel])
+    ri = _dev_i32(z["retrieve"])
+    kv0 = [init[i].repeat(n_case, 1, 1, 1).contiguous().cuda() for i in range(init.shape[0])]
+    kv = [t.clone() for t in kv0]
+    start = _dev_i32(np.array([s for _, s in cases]))
+    cache_len = start.clone()
+    ver = E.Verifier(n_case, lg.shape[1])
+    ver.bind_kv(kv)
+    out = ver.verify(lg, tok, ri, cache_len=cache_len, move_kv=True)          # eager warm-up allocates `out`
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ver.verify(lg, tok, ri, cache_len=cache_len, move_kv=True, out=out)
+    for _ in range(3):
+        for t, t0 in zip(kv, kv0):
+            t.copy_(t0)
+        cache_len.copy_(start)
+        out["accept_len"].zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for c in range(n_case):
+            got = torch.stack([t[c] for t in kv]).view(torch.int16).cpu().numpy()
+            assert np.array_equal(got, z["kv/after_bits"][c][:, 0]), c
+        assert np.array_equal(out["accept_len"].cpu().numpy(), z["bf16/accept_len"][sel])
+        assert np.array_equal(cache_len.cpu().numpy(), start.cpu().numpy() + z["bf16/accept_len"][sel])
