@@ -427,6 +427,10 @@ def run_ours(a):
         except Exception as e:
             out["static"] = {"error": repr(e)}
         try:
+            out["c2_concurrent"] = bench_c2_concurrent(a, dev, (streams, counts, tokens, start))
+        except Exception as e:
+            out["c2_concurrent"] = {"error": repr(e)}
+        try:
             out["c1"] = bench_c1(a, dev)
         except Exception as e:
             out["c1"] = {"error": repr(e)}
@@ -557,6 +561,48 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5):
                          "unit": "GB/s", "frac": gbs_full / hbm_peak, "traffic": None},
             "roofline_verify_only": {"achieved": gbs_nokv, "peak": hbm_peak, "unit": "GB/s", "frac": gbs_nokv / hbm_peak},
             "gpu_launches_per_step": 1}
+
+
+def bench_c2_concurrent(a, dev, workload, n_streams=4):
+    """Context for the headline: the step kernel is a latency-bound pointer chase that keeps ~6 % of the SM
+    warp slots busy, so independent 1024-request batches overlap almost perfectly.  n_streams batches (own
+    arenas, same token streams) run as n_streams CUDA graphs on n_streams streams; aggregate queries/s."""
+    import torch
+    from samd_b200 import _cabi as K, engine as E
+    streams, counts, tokens, start = workload
+    R, N, S, W = a.requests, a.prompt, a.steps, a.warmup
+    d_tokens, d_counts, d_start = (torch.as_tensor(x).to(dev) for x in (tokens, counts, start))
+    d_prompt = torch.as_tensor(streams[:, :N]).to(dev)
+    cuda_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+    engines, graphs = [], []
+    for cs in cuda_streams:
+        with torch.cuda.stream(cs):
+            dyn = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
+            eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=N_PREDICTS, len_bias=LEN_BIAS, len_threshold=LEN_THRESHOLD)
+            eng.step(d_prompt, None, None)
+            for s in range(W):
+                eng.step(d_tokens[s], d_counts[s], d_start[s])
+        engines.append(eng)
+    torch.cuda.synchronize()
+    for eng, cs in zip(engines, cuda_streams):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=cs):
+            for s in range(W, W + S):
+                eng.step(d_tokens[s], d_counts[s], d_start[s])
+        graphs.append(g)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in cuda_streams]
+    e0.record()
+    for g, cs, ev in zip(graphs, cuda_streams, ends):
+        cs.wait_event(e0)
+        with torch.cuda.stream(cs):
+            g.replay()
+            ev.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(ev) for ev in ends)
+    return {"workload": f"{n_streams} independent c2 batches ({R} requests each) in flight on {n_streams} streams",
+            "queries_per_s": n_streams * R * S / (ms * 1e-3), "us_per_step_per_batch": ms / S * 1e3, "n_streams": n_streams}
 
 
 def bench_c1(a, dev, prompt=4096, steps=256):

@@ -291,12 +291,14 @@ struct StepParams {
     double alpha;
     int32_t *out_type, *out_match_dyn, *out_match_static, *out_index_dyn, *out_index_static, *out_draft, *out_draft_len;
     int draft_stride;
+    long long *dbg_cycles;      // optional [n_requests] per-request SM cycles (profiling hook)
 };
 
 __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
     const int r = blockIdx.x;
     const int lane = threadIdx.x;
     if (r >= P.dyn.n_requests) return;
+    const long long t_begin = P.dbg_cycles ? clock64() : 0;
     int32_t *recs = P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC;
     uint4 *slots = P.dyn.slots + (size_t)r * P.dyn.h_cap;
     int32_t *text = P.dyn.text + (size_t)r * P.dyn.t_cap;
@@ -446,8 +448,12 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
         if (P.out_index_static) P.out_index_static[r] = t_idx;
         if (P.out_draft_len) P.out_draft_len[r] = n_out;
         meta[META_PROBES] += q_hops;          // probes spent in lookups (the extend-side count is META_HOPS)
+        if (P.dbg_cycles) P.dbg_cycles[r] = clock64() - t_begin;
     }
 }
+
+static long long *g_dbg_cycles = nullptr;
+extern "C" void samd_step_set_debug_cycles(int64_t *cycles_dev) { g_dbg_cycles = (long long *)cycles_dev; }
 
 extern "C" int samd_step(const samd_step_args *a, void *stream) {
     SAMD_REQUIRE(a && a->dyn, "samd_step: dyn handle required");
@@ -477,6 +483,7 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     P.out_draft = a->out_draft_dev;
     P.out_draft_len = a->out_draft_len_dev;
     P.draft_stride = a->draft_stride;
+    P.dbg_cycles = g_dbg_cycles;
     SAMD_REQUIRE(a->flavour == SAMD_FLAVOUR_SAMD || a->flavour == SAMD_FLAVOUR_SAM_ONLY, "samd_step: bad flavour");
     SAMD_REQUIRE(!a->tokens_dev || a->token_stride > 0, "samd_step: token_stride must be positive");
     SAMD_REQUIRE(!a->out_draft_dev || a->draft_stride >= a->n_predicts, "samd_step: draft_stride < n_predicts");

@@ -35,8 +35,10 @@ def _as_i32_row(tokens, device) -> torch.Tensor:
     if isinstance(tokens, torch.Tensor):
         t = tokens.reshape(1, -1)
         return t.to(device=device, dtype=torch.int32).contiguous()
-    a = np.asarray(tokens, dtype=np.int32).reshape(1, -1)
-    return torch.from_numpy(a).to(device)
+    a = np.asarray(tokens, dtype=np.int64).reshape(1, -1)
+    if a.size and (a.min() < 0 or a.max() >= 2 ** 31 - 1):
+        raise ValueError("token ids must be in [0, 2^31 - 2] (the flat automaton reserves -1 for free edges)")
+    return torch.from_numpy(a.astype(np.int32)).to(device)
 
 
 class DynSamView:

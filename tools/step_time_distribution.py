@@ -1,0 +1,23 @@
+import sys; sys.path.insert(0,"sam-decoding_b200"); sys.path.insert(0,".")  # run from the repo root
+import numpy as np, torch, bench
+from samd_b200 import _cabi as K, engine as E
+class A: requests=1024; prompt=8192; steps=32; warmup=8
+streams, counts, tokens, start = bench.make_workload(1024, 8192, 40, 2000)
+dev=torch.device("cuda")
+dyn=E.DynSamBatch(1024, 8192+8*40+16, dev)
+eng=E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=16, len_bias=5, len_threshold=5)
+eng.step(torch.as_tensor(streams[:, :8192]).to(dev), None, None)
+dt,dc,ds=(torch.as_tensor(x).to(dev) for x in (tokens,counts,start))
+cyc=torch.zeros(1024,dtype=torch.int64,device=dev)
+K.lib().samd_step_set_debug_cycles(cyc.data_ptr())
+allc=[]
+for s in range(40):
+    eng.step(dt[s],dc[s],ds[s]); torch.cuda.synchronize()
+    if s>=8: allc.append((cyc.cpu().numpy().copy(), counts[s].copy()))
+K.lib().samd_step_set_debug_cycles(None)
+c=np.stack([a for a,_ in allc]).astype(float)/1.9e3   # us at ~1.9GHz
+k=np.stack([b for _,b in allc])
+print("per-step max us: mean %.1f ; per-request mean %.1f p50 %.1f p90 %.1f p99 %.1f p99.9 %.1f" % (c.max(1).mean(), c.mean(), np.percentile(c,50), np.percentile(c,90), np.percentile(c,99), np.percentile(c,99.9)))
+for kk in range(1,9):
+    m=c[k==kk]; print("k=%d n=%d mean %.1f p99 %.1f max %.1f" % (kk, m.size, m.mean(), np.percentile(m,99), m.max()))
+print("us per token (k>=1): %.2f" % (c.sum()/k.sum()))
