@@ -1,1 +1,1 @@
-python cyc.py 2>&1 | tail -12
+python scout_ab.py 2>&1 | tail -5

@@ -169,6 +169,8 @@ int samd_step(const samd_step_args *args, void *stream);
 /* profiling hook: when non-NULL, every samd_step launch that performs a lookup writes each request's SM
  * cycle count to cycles_dev[n_requests] */
 void samd_step_set_debug_cycles(int64_t *cycles_dev);
+/* tuning hook: 0 disables the scout (prefetcher) warps of samd_step; default 1 */
+void samd_step_set_scouts(int on);
 
 /* Cursor-only walks.  samd_static_walk = StaticSAM.transfer_tokens (static_sam.py:102-104) when
  * tokens_dev != NULL, then StaticSAM.lookup (:106-109) when peek_tok_dev != NULL (non-mutating).

@@ -294,10 +294,45 @@ struct StepParams {
     long long *dbg_cycles;      // optional [n_requests] per-request SM cycles (profiling hook)
 };
 
-__global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
+// Scout warp: walks the cursor chain of the tokens this step will append (and of the final lookup) on the
+// automaton AS IT IS - transfers only, nothing is written - one dependent read per token, i.e. faster than the
+// builder warp, whose chain also carries clone / redirect work.  Every record (and the draft's text lines) it
+// touches lands in this SM's L1/L2 just before the builder needs it.  It may observe records the builder is
+// updating concurrently; that can only send it down a different (still valid) path - it is a prefetcher and
+// produces no output.
+template <bool kStatic>
+__device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slots, uint32_t bmask, const int32_t *text,
+                                           int idx, const int32_t *tk, int k, int peek, int n_predicts, long long text_n, int lane) {
+    int len = 0, hops = 0;
+    for (int i = 0; i < k; i += 32) {
+        const int mine = (i + lane < k) ? tk[i + lane] : 0;
+        const int lim = min(32, k - i);
+        for (int j = 0; j < lim; ++j) warp_transfer<kStatic>(recs, slots, bmask, idx, len, __shfl_sync(SAMD_FULL, mine, j), lane, hops);
+    }
+    if (peek < 0) return;
+    warp_transfer<kStatic>(recs, slots, bmask, idx, len, peek, lane, hops);
+    // the draft will be read right after the earliest end position of the matched state
+    const int e = kStatic ? __ldg(recs + (size_t)idx * SAMD_REC + R_END) : recs[(size_t)idx * SAMD_REC + R_END];
+    if (lane * 8 < n_predicts + 8 && (long long)e + 1 + lane * 8 <= text_n) asm volatile("prefetch.global.L1 [%0];" ::"l"(text + e + 1 + lane * 8));
+}
+
+__global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
     const int r = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     if (r >= P.dyn.n_requests) return;
+    if (threadIdx.x >= 32) {
+        const int k = P.tokens ? (P.counts ? P.counts[r] : P.token_stride) : 0;
+        const int32_t *tk = P.tokens ? P.tokens + (size_t)r * P.token_stride : nullptr;
+        const int peek = P.start_tok ? P.start_tok[r] : -1;
+        if (threadIdx.x < 64) {
+            const int32_t *meta = P.dyn.meta + (size_t)r * META_WORDS;
+            scout_walk<false>(P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC, P.dyn.slots + (size_t)r * P.dyn.h_cap, P.dyn.bmask,
+                              P.dyn.text + (size_t)r * P.dyn.t_cap, meta[META_CUR], tk, k, peek, P.n_predicts, (long long)meta[META_N], lane);
+        } else if (P.has_static) {
+            scout_walk<true>(P.st.recs, P.st.slots, P.st.bmask, P.st.text, P.static_cursor[2 * r], tk, k, peek, P.n_predicts, (long long)P.st.n_tokens, lane);
+        }
+        return;
+    }
     const long long t_begin = P.dbg_cycles ? clock64() : 0;
     int32_t *recs = P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC;
     uint4 *slots = P.dyn.slots + (size_t)r * P.dyn.h_cap;
@@ -453,6 +488,8 @@ __global__ void __launch_bounds__(32) sam_step_kernel(StepParams P) {
 }
 
 static long long *g_dbg_cycles = nullptr;
+static int g_scouts = 1;
+extern "C" void samd_step_set_scouts(int on) { g_scouts = on; }
 extern "C" void samd_step_set_debug_cycles(int64_t *cycles_dev) { g_dbg_cycles = (long long *)cycles_dev; }
 
 extern "C" int samd_step(const samd_step_args *a, void *stream) {
@@ -487,7 +524,9 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     SAMD_REQUIRE(a->flavour == SAMD_FLAVOUR_SAMD || a->flavour == SAMD_FLAVOUR_SAM_ONLY, "samd_step: bad flavour");
     SAMD_REQUIRE(!a->tokens_dev || a->token_stride > 0, "samd_step: token_stride must be positive");
     SAMD_REQUIRE(!a->out_draft_dev || a->draft_stride >= a->n_predicts, "samd_step: draft_stride < n_predicts");
-    sam_step_kernel<<<P.dyn.n_requests, 32, 0, (cudaStream_t)stream>>>(P);
+    // warp 0 builds, warp 1 scouts the dynamic automaton, warp 2 (if any) scouts the static one
+    const int threads = g_scouts ? (P.has_static ? 96 : 64) : 32;
+    sam_step_kernel<<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
     samd_count_launch();
     SAMD_CUDA(cudaGetLastError());
     return 0;

@@ -223,6 +223,11 @@ __device__ __forceinline__ void warp_transfer(const int32_t *recs, const uint4 *
             return;
         }
         index = rec_word(r, R_LINK);
+        if (index < 0) {                                 // only a scout racing with the builder can see a pending link
+            index = 0;
+            length = 0;
+            return;
+        }
         first = false;
     }
 }
