@@ -253,6 +253,9 @@ void samd_verify_set_overlap(int on);
 int samd_kv_compact(void *const *kv_ptrs_dev, int32_t n_kv, int32_t n_heads, int32_t row_bytes, int64_t kv_batch_stride,
                     int64_t kv_head_stride, int64_t kv_pos_stride, const int32_t *indices_dev, int32_t depth,
                     const int32_t *accept_len_dev, int32_t *cache_len_dev, int32_t batch, void *stream);
+/* profiling aid: n_warps warps each chase `hops` dependent pointers through n_records 64-byte records
+ * (record word 0 = next index); measures dependent-load latency at the step kernel's concurrency */
+int samd_debug_pointer_chase(const void *recs_dev, int64_t n_records, int n_warps, int hops, int32_t *sink_dev, void *stream);
 /* number of kernel launches the library has issued (for bench.py's gpu_launches) */
 int64_t samd_launch_count(void);
 

@@ -29,3 +29,25 @@ extern "C" int samd_device_count(void) {
     }
     return n;
 }
+
+// ---------------------------------------------------------------------------------------
+// Microbenchmark (profiling aid): dependent-load latency at the step kernel's concurrency.  Every warp
+// chases `hops` pointers through a table of 64-byte records (next = rec[0]); returns nothing useful.
+// ---------------------------------------------------------------------------------------
+__global__ void chase_kernel(const int4 *recs, long long n, int hops, int *sink) {
+    long long idx = ((long long)blockIdx.x * 2654435761ll) % n;
+    int acc = 0;
+    for (int h = 0; h < hops; ++h) {
+        const int4 r = recs[idx * 4];          // all lanes, same address: one 16 B broadcast load
+        acc += r.y;
+        idx = (long long)(unsigned)r.x % n;
+    }
+    if (threadIdx.x == 0) sink[blockIdx.x] = acc + (int)idx;
+}
+
+extern "C" int samd_debug_pointer_chase(const void *recs_dev, int64_t n_records, int n_warps, int hops, int32_t *sink_dev, void *stream) {
+    chase_kernel<<<n_warps, 32, 0, (cudaStream_t)stream>>>((const int4 *)recs_dev, (long long)n_records, hops, sink_dev);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -302,18 +302,37 @@ struct StepParams {
 // produces no output.
 template <bool kStatic>
 __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slots, uint32_t bmask, const int32_t *text,
-                                           int idx, const int32_t *tk, int k, int peek, int n_predicts, long long text_n, int lane) {
-    int len = 0, hops = 0;
-    for (int i = 0; i < k; i += 32) {
-        const int mine = (i + lane < k) ? tk[i + lane] : 0;
-        const int lim = min(32, k - i);
-        for (int j = 0; j < lim; ++j) warp_transfer<kStatic>(recs, slots, bmask, idx, len, __shfl_sync(SAMD_FULL, mine, j), lane, hops);
+                                           int idx, const int32_t *tk, int k, int peek, int n_predicts, long long text_n,
+                                           long long cap, int lane) {
+    // `cap` bounds every state index before it is dereferenced: the scout races with the builder and may read a
+    // record whose initialisation is not visible yet (stale memory), so nothing it reads is trusted as an address
+    if (k > 64) return;                                                      // long appends (prefill): nothing useful to scout
+    if ((unsigned long long)idx >= (unsigned long long)cap) return;
+    const int total = k + (peek >= 0 ? 1 : 0);
+    int mine = 0;
+    for (int i = 0; i < total; ++i) {
+        if ((i & 31) == 0) mine = (i + lane < k) ? tk[i + lane] : peek;      // tokens, then the lookup token
+        const int tok = __shfl_sync(SAMD_FULL, mine, i & 31);
+        while (true) {                                                       // transfer_state, no bookkeeping
+            const Look r = warp_look<kStatic>(recs, slots, bmask, idx, tok, lane);
+            if (r.found) {
+                idx = r.target;
+                if ((unsigned long long)idx >= (unsigned long long)cap) idx = 0;
+                break;
+            }
+            if (idx == 0) break;
+            idx = rec_word(r, R_LINK);
+            if ((unsigned long long)idx >= (unsigned long long)cap) {
+                idx = 0;
+                break;
+            }
+        }
     }
     if (peek < 0) return;
-    warp_transfer<kStatic>(recs, slots, bmask, idx, len, peek, lane, hops);
     // the draft will be read right after the earliest end position of the matched state
     const int e = kStatic ? __ldg(recs + (size_t)idx * SAMD_REC + R_END) : recs[(size_t)idx * SAMD_REC + R_END];
-    if (lane * 8 < n_predicts + 8 && (long long)e + 1 + lane * 8 <= text_n) asm volatile("prefetch.global.L1 [%0];" ::"l"(text + e + 1 + lane * 8));
+    if (e >= 0 && lane * 8 < n_predicts + 8 && (long long)e + 1 + lane * 8 <= text_n)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(text + e + 1 + lane * 8));
 }
 
 __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
@@ -327,9 +346,11 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
         if (threadIdx.x < 64) {
             const int32_t *meta = P.dyn.meta + (size_t)r * META_WORDS;
             scout_walk<false>(P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC, P.dyn.slots + (size_t)r * P.dyn.h_cap, P.dyn.bmask,
-                              P.dyn.text + (size_t)r * P.dyn.t_cap, meta[META_CUR], tk, k, peek, P.n_predicts, (long long)meta[META_N], lane);
+                              P.dyn.text + (size_t)r * P.dyn.t_cap, meta[META_CUR], tk, k, peek, P.n_predicts, (long long)meta[META_N],
+                              (long long)P.dyn.s_cap, lane);
         } else if (P.has_static) {
-            scout_walk<true>(P.st.recs, P.st.slots, P.st.bmask, P.st.text, P.static_cursor[2 * r], tk, k, peek, P.n_predicts, (long long)P.st.n_tokens, lane);
+            scout_walk<true>(P.st.recs, P.st.slots, P.st.bmask, P.st.text, P.static_cursor[2 * r], tk, k, peek, P.n_predicts,
+                             (long long)P.st.n_tokens, (long long)P.st.n_states, lane);
         }
         return;
     }

@@ -91,6 +91,7 @@ SYMBOLS = {
     "samd_dyn_transfer": (C.c_int, [vp, vp, C.c_int32, vp, vp]),
     "samd_kv_compact": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32,
                                   vp, vp, C.c_int32, vp]),
+    "samd_debug_pointer_chase": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, vp, vp]),
     "samd_verify_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
     "samd_verify_destroy": (C.c_int, [vp]),
     "samd_verify_compact": (C.c_int, [vp, C.POINTER(VerifyArgs), vp]),
