@@ -244,9 +244,9 @@ typedef struct samd_verify_args {
 int samd_verify_compact(samd_verify_t h, const samd_verify_args *args, void *stream);
 /* tuning hook: logits elements per phase-1 work item (0 = default) */
 void samd_verify_set_chunk(int elements);
-/* tuning hook: 1 = dedicate a quarter of the CTAs to KV row moves that overlap the logits stream,
- * 0 (default) = stream first, then move rows with every CTA */
-void samd_verify_set_overlap(int on);
+/* profiling hook: [grid warps][3] uint64 globaltimer ns per warp of the next launches - start, end of the logits
+ * stream, exit; NULL = off */
+void samd_verify_set_debug_times(uint64_t *times_dev);
 /* Stand-alone SamdStaticCache.select_indices (samd/cache.py:118-133): rows cache_len+indices[b][j] ->
  * cache_len+j for j < accept_len[b] in every KV tensor, then cache_len[b] += accept_len[b].
  * indices_dev NULL = sequence draft (only the length bump, cache.py:123-126,133). */

@@ -1,18 +1,20 @@
 // Fused greedy tree verification + KV-cache compaction, one persistent launch (sm_100a).
 //
-// Work is warp-granular and statically strided over a grid that is fully resident:
-//   phase 1  item = (request, tree row, chunk).  A warp streams its slice of the logits row with
-//            128-bit no-allocate loads (8 in flight per lane), keeps a running (key, index) maximum
-//            under torch.argmax's rule (lowest index among equal maxima, NaN is the maximum,
-//            +0 == -0) and reduces it with shuffles - no block barrier, no shared memory.  Rows
-//            split into several chunks are combined with a 64-bit atomicMax.  The warp that
-//            completes a request's last item walks the P x D path table (samd/utils.py:127-141),
-//            writes best / accept_len / next_token / accepted tokens + indices, snapshots and bumps
-//            cache_len and publishes the request as ready.
-//   phase 2  item = (request, KV tensor).  The warp waits for the request's walk, then moves rows
-//            cache_len+indices[j] -> cache_len+j (samd/cache.py:118-133) for all heads in 16-byte
-//            columns, loads of a row group before its stores (the reference gathers into a
-//            temporary first; ascending j with indices[j] >= j makes that order equivalent).
+// Work is warp-granular over a grid that is fully resident (two grid-wide barriers):
+//   phase 1   item = a chunk (about 16k elements) of one logits row, handed out dynamically from 64 work queues.
+//             A warp streams its chunk with 128-bit no-allocate loads (8 in flight per lane), keeps a WARP-uniform
+//             running (key, index) maximum under torch.argmax's rule (lowest index among equal maxima, NaN is the
+//             maximum, +0 == -0) - no block barrier, no shared memory - and publishes it with a fire-and-forget
+//             64-bit atomicMax.  Nothing in the loop waits on a round trip but the logits themselves.
+//   barrier A every row maximum is published.
+//   phase 1b  one warp per request walks the P x D path table (samd/utils.py:127-141), writes best / accept_len /
+//             next_token / accepted tokens + indices, snapshots and bumps cache_len and, if rows have to move,
+//             appends a move record to the active list.
+//   barrier B every walk is published.
+//   phase 2   the moved rows of the active requests are flattened into 16-byte units over every lane of the grid:
+//             rows cache_len+indices[j] -> cache_len+j (samd/cache.py:118-133) for all heads, loads of a row group
+//             before its stores (the reference gathers into a temporary first; ascending j with indices[j] >= j
+//             makes that order equivalent).
 #include "samd_common.cuh"
 #include "../../include/samd_b200.h"
 
@@ -25,13 +27,12 @@
 #define VW (VT / 32)
 #define UNROLL 8               // 128-bit loads in flight per lane
 #define KV_GROUP 8             // accepted rows staged in registers per pass
-#define MAX_WAVES 8            // KV work is released in up to this many request waves
+#define KV_REC (3 + KV_GROUP)   // move record: {request, accept_len, start, first KV_GROUP source rows}
 
 struct samd_verify_s {
     unsigned long long *node_key;   // [max_batch][max_nodes]
-    int *done;                      // [max_batch]
-    int *active;                    // [2][MAX_WAVES][max_batch] requests with rows to move (double-buffered by epoch parity)
-    int *counters;                  // [5][MAX_WAVES]: n_active par0/par1, walked par0/par1, wave flags; then {epoch, exit count}
+    int *active;                    // [max_batch][KV_REC] move records of the requests with rows to move
+    int *counters;                  // [CN_WORDS] epoch, exit count, work counter, barrier arrivals and flags, n_active
     int occ_per_sm[3];              // cached occupancy per dtype
     int *kv_start;                  // [max_batch] cache_len before the bump
     int max_batch, max_nodes, device, n_sms;
@@ -40,10 +41,17 @@ struct samd_verify_s {
 struct VerifyParams {
     samd_verify_args a;
     unsigned long long *node_key;
-    int *done, *active, *counters, *kv_start;
+    int *active, *counters, *kv_start;
     int max_nodes, max_batch;
-    int chunk, chunks_per_row, n_items1, n_items2, vec_ok, stage_cap, n_kv_ctas, n_waves;
+    int chunk, chunks_per_row, n_items1, n_items2, vec_ok, stage_cap;
+    unsigned long long *dbg_times;   // optional [grid warps][3] globaltimer ns: start, end of streaming, exit (profiling hook)
 };
+
+__device__ __forceinline__ unsigned long long samd_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <int kDtype>
 __device__ __forceinline__ uint32_t orderable16(uint32_t b) {
@@ -175,120 +183,192 @@ __device__ __forceinline__ int ri_at(const VerifyParams &P, int b, int p, int j)
     return P.a.retrieve_dev[(size_t)b * P.a.retrieve_batch_stride + (size_t)p * P.a.depth + j];
 }
 
+// one unit of phase-1 work: a chunk of one logits row
+struct Item {
+    int item, b, t, e0, len;
+    bool act;                                                  // rows past the request's node count stream nothing
+};
+
+__device__ __forceinline__ Item decode_item(const VerifyParams &P, int item) {
+    Item I;
+    I.item = item;
+    I.act = false;
+    I.b = I.t = I.e0 = I.len = 0;
+    if (item >= P.n_items1) return I;
+    const int C = P.chunks_per_row, T = P.a.n_nodes;
+    const int row = item / C;
+    I.e0 = (item - row * C) * P.chunk;
+    I.len = min(P.chunk, P.a.vocab - I.e0);
+    I.b = row / T;
+    I.t = row - I.b * T;
+    I.act = I.t < (P.a.n_nodes_dev ? P.a.n_nodes_dev[I.b] : T);
+    return I;
+}
+
+__device__ __forceinline__ size_t item_offset(const VerifyParams &P, const Item &I) {
+    return (size_t)I.b * P.a.batch_stride + (size_t)I.t * P.a.row_stride + I.e0;
+}
+
+// counters[] slots (all re-armed by the kernel itself, so a launch can be captured in a CUDA graph and replayed)
+enum { CN_EPOCH = 0, CN_EXIT, CN_ARRIVE_A, CN_FLAG_A, CN_ARRIVE_B, CN_FLAG_B, CN_ACTIVE, CN_QUEUES = 32 };
+// Work queues: one counter would be hit by every warp for every item, and same-address atomics serialise at about
+// 3 ns each on B200 (measured: 62k items took 135 us whatever their size) - so the dynamic items are dealt round-robin
+// into N_QUEUES queues, each with its own counter on its own 128-byte line.
+#define N_QUEUES 64
+#define QUEUE_STRIDE 32
+#define CN_WORDS (CN_QUEUES + N_QUEUES * QUEUE_STRIDE)
+
 template <int kDtype>
 __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
-    extern __shared__ int s_am_all[];                          // [VW][n_nodes] node argmax, one slab per warp
+    extern __shared__ int s_am_all[];                          // [VW][2][n_nodes] node argmax + tree tokens, one slab per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // Roles: the last n_kv_ctas CTAs (one per SM when the grid is full) only move KV rows, wave by wave, while
-    // the others stream logits - the row moves (256-byte granules, DRAM-activation bound) overlap the streaming.
-    const int n_stream_ctas = (int)gridDim.x - P.n_kv_ctas;
-    const bool kv_role = (int)blockIdx.x >= n_stream_ctas;
-    const int gwarp = warp * n_stream_ctas + blockIdx.x;      // warp-major: consecutive items land on different SMs
-    const int n_warps = n_stream_ctas * VW;
-    // The launch epoch lives in device memory (bumped by the last CTA to leave), so the kernel can be captured
-    // in a CUDA graph and replayed: nothing launch-specific is baked into its arguments.
-    const int epoch = *reinterpret_cast<volatile int *>(&P.counters[5 * MAX_WAVES]) + 1;
-    const int G = P.n_waves, par = epoch & 1;
-    int *cnt_active = P.counters + par * MAX_WAVES, *cnt_walked = P.counters + (2 + par) * MAX_WAVES;
-    int *wave_flag = P.counters + 4 * MAX_WAVES;
-    if (blockIdx.x == 0 && threadIdx.x < 2 * MAX_WAVES) {     // re-arm the other parity for the next launch
-        const int g = threadIdx.x % MAX_WAVES;
-        (threadIdx.x < MAX_WAVES ? P.counters + (par ^ 1) * MAX_WAVES : P.counters + (2 + (par ^ 1)) * MAX_WAVES)[g] = 0;
-    }
+    const int n_ctas = (int)gridDim.x;
+    const int gwarp = warp * n_ctas + blockIdx.x;             // warp-major: consecutive items land on different SMs
+    const int n_warps = n_ctas * VW;
+    // The launch epoch lives in device memory (bumped by the last CTA to leave): nothing launch-specific is baked
+    // into the kernel arguments.  Flags are written once per launch with the epoch value and only ever compared.
+    const int epoch = *reinterpret_cast<volatile int *>(&P.counters[CN_EPOCH]) + 1;
     const samd_verify_args &A = P.a;
     const int T = A.n_nodes;
     const int C = P.chunks_per_row;
+    unsigned long long *dbg = P.dbg_times ? P.dbg_times + ((size_t)blockIdx.x * VW + warp) * 3 : nullptr;
+    if (dbg && lane == 0) dbg[0] = samd_globaltimer();
     int *s_am = s_am_all + warp * 2 * T;                     // [T] node argmax, then [T] tree tokens
     int *s_tok = s_am + T;
     const uint16_t *logits = reinterpret_cast<const uint16_t *>(A.logits_dev);
 
-    // ------------------------------ phase 1: argmax + path walk ---------------------------
-    for (int item = kv_role ? P.n_items1 : gwarp; item < P.n_items1; item += n_warps) {
-        const int c = item % C;
-        const int t = (item / C) % T;
-        const int b = item / (C * T);
-        const int n_rows = A.n_nodes_dev ? A.n_nodes_dev[b] : T;
-        if (t < n_rows) {
-            const int e0 = c * P.chunk;
-            const int len = min(P.chunk, A.vocab - e0);
-            const uint16_t *row = logits + (size_t)b * A.batch_stride + (size_t)t * A.row_stride + e0;
-            uint32_t best_key = 0, best_idx = 0;
-            if constexpr (kDtype == SAMD_DTYPE_FP32) {
-                // fp32 logits (the reference's --dtype float32 runs): coalesced scalar loads, per-lane maxima
-                const uint32_t *row32 = reinterpret_cast<const uint32_t *>(A.logits_dev) + (size_t)b * A.batch_stride +
-                                        (size_t)t * A.row_stride + e0;
+    // ------------------------------ phase 1: row argmax -----------------------------------
+    // Items (row chunks) are handed out dynamically - the first one per warp is its own index, the rest come from
+    // a counter: measured on B200, equal static shares finish between 27 and 50 us after launch (the memory system
+    // is not fair between SMs), so fast warps must be able to take more.  Nothing in the item loop waits on a
+    // round trip other than the logits themselves: the result is a fire-and-forget 64-bit max, the next item index
+    // is requested one item ahead, and the first vector group of the NEXT item is requested before the current
+    // item's last group is folded.
+    {
+        constexpr bool k16 = kDtype != SAMD_DTYPE_FP32;
+        constexpr int G = UNROLL / 2;
+        const uint32_t ninf = kDtype == SAMD_DTYPE_BF16 ? 0xFF80FF80u : 0xFC00FC00u;
+        const bool vec16 = k16 && P.vec_ok;
+        uint4 xa[G], xb[G];
+        Item cur = decode_item(P, gwarp), nx;
+        int queue = gwarp % N_QUEUES;                           // lane 0's view is the one that counts
+        bool stolen = false;
+        if (vec16 && cur.act)
+            load_group<G>(xa, reinterpret_cast<const uint4 *>(logits + item_offset(P, cur)), 0, cur.len >> 3, lane, ninf);
+        for (; cur.item < P.n_items1; cur = nx) {
+            // (claiming later - one pass before the item is needed - measured slower: 52.4 vs 49.5 us on C4)
+            int claim = 0;                                      // requested now, consumed in the item's last pass
+            if (lane == 0) claim = atomicAdd(&P.counters[CN_QUEUES + queue * QUEUE_STRIDE], 1);
+            bool fetched = false;
+            auto fetch_next = [&]() {
+                int nxt = 0;
+                if (lane == 0) {
+                    nxt = n_warps + claim * N_QUEUES + queue;
+                    if (nxt >= P.n_items1 && !stolen) {         // home queue drained: one try at the opposite queue
+                        stolen = true;
+                        queue = (queue + N_QUEUES / 2) % N_QUEUES;
+                        nxt = n_warps + atomicAdd(&P.counters[CN_QUEUES + queue * QUEUE_STRIDE], 1) * N_QUEUES + queue;
+                    }
+                }
+                nx = decode_item(P, __shfl_sync(SAMD_FULL, nxt, 0));
+                fetched = true;
+                if (vec16 && nx.act)
+                    load_group<G>(xa, reinterpret_cast<const uint4 *>(logits + item_offset(P, nx)), 0, nx.len >> 3, lane, ninf);
+            };
+            if (cur.act) {
+                const int e0 = cur.e0, len = cur.len;
+                const uint16_t *row = logits + item_offset(P, cur);
+                uint32_t best_key = 0, best_idx = 0;
+                if constexpr (kDtype == SAMD_DTYPE_FP32) {
+                    // fp32 logits (the reference's --dtype float32 runs): coalesced scalar loads, per-lane maxima
+                    const uint32_t *row32 = reinterpret_cast<const uint32_t *>(A.logits_dev) + item_offset(P, cur);
 #pragma unroll 4
-                for (int e = lane; e < len; e += 32) {
-                    const uint32_t ke = orderable32(__ldg(row32 + e));
-                    if (ke > best_key) {
-                        best_key = ke;
-                        best_idx = (uint32_t)(e0 + e);
+                    for (int e = lane; e < len; e += 32) {
+                        const uint32_t ke = orderable32(__ldg(row32 + e));
+                        if (ke > best_key) {
+                            best_key = ke;
+                            best_idx = (uint32_t)(e0 + e);
+                        }
                     }
-                }
-            } else if (P.vec_ok) {
-                // The running maximum is WARP-uniform: a group of 32 x UNROLL vectors is reduced to one
-                // key per lane with packed max instructions, then across lanes with redux.sync; only when
-                // the group beats the running maximum (about ln(#groups) times per row) is the first
-                // maximal element located, from the registers that still hold the group.
-                const uint4 *v4 = reinterpret_cast<const uint4 *>(row);
-                const int nvec = len >> 3;
-                const uint32_t ninf = kDtype == SAMD_DTYPE_BF16 ? 0xFF80FF80u : 0xFC00FC00u;
-                // software pipeline: the loads of the next half-group are in flight while this one is folded
-                constexpr int G = UNROLL / 2;
-                uint4 xa[G], xb[G];
-                load_group<G>(xa, v4, 0, nvec, lane, ninf);
-                for (int v0 = 0; v0 < nvec; v0 += 64 * G) {
-                    const int v1 = v0 + 32 * G;
-                    if (v1 < nvec) load_group<G>(xb, v4, v1, nvec, lane, ninf);
-                    fold_group<kDtype, G>(xa, v0, nvec, lane, e0, best_key, best_idx);
-                    if (v1 < nvec) {
+                } else if (P.vec_ok) {
+                    // The running maximum is WARP-uniform: a group of 32 x G vectors is reduced to one key per lane
+                    // with packed max instructions, then across lanes with redux.sync; only when the group beats the
+                    // running maximum (about ln(#groups) times per row) is the first maximal element located, from
+                    // the registers that still hold the group.  The loads of the next half-group are in flight
+                    // while this one is folded (xa was requested before this item began).
+                    const uint4 *v4 = reinterpret_cast<const uint4 *>(row);
+                    const int nvec = len >> 3;
+                    for (int v0 = 0; v0 < nvec; v0 += 64 * G) {
+                        const int v1 = v0 + 32 * G;
+                        if (v1 < nvec) load_group<G>(xb, v4, v1, nvec, lane, ninf);
+                        fold_group<kDtype, G>(xa, v0, nvec, lane, e0, best_key, best_idx);
                         if (v1 + 32 * G < nvec) load_group<G>(xa, v4, v1 + 32 * G, nvec, lane, ninf);
-                        fold_group<kDtype, G>(xb, v1, nvec, lane, e0, best_key, best_idx);
+                        else fetch_next();                      // last pass: xa is free, start on the next item
+                        if (v1 < nvec) fold_group<kDtype, G>(xb, v1, nvec, lane, e0, best_key, best_idx);
+                    }
+                    const int tail = nvec << 3;
+                    if (len - tail > 0) {                      // < 8 trailing elements, all later than the vectors
+                        const uint32_t ke = lane < len - tail ? orderable16<kDtype>(row[tail + lane]) : 0u;
+                        const uint32_t wk = __reduce_max_sync(SAMD_FULL, ke);
+                        if (wk > best_key) {
+                            best_key = wk;
+                            best_idx = (uint32_t)(e0 + tail + __ffs(__ballot_sync(SAMD_FULL, ke == wk)) - 1);
+                        }
+                    }
+                } else {
+                    for (int e = lane; e < len; e += 32) {
+                        const uint32_t ke = orderable16<kDtype>(row[e]);
+                        if (ke > best_key) {
+                            best_key = ke;
+                            best_idx = (uint32_t)(e0 + e);
+                        }
                     }
                 }
-                const int tail = nvec << 3;
-                if (len - tail > 0) {                          // < 8 trailing elements, all later than the vectors
-                    const uint32_t ke = lane < len - tail ? orderable16<kDtype>(row[tail + lane]) : 0u;
-                    const uint32_t wk = __reduce_max_sync(SAMD_FULL, ke);
-                    if (wk > best_key) {
-                        best_key = wk;
-                        best_idx = (uint32_t)(e0 + tail + __ffs(__ballot_sync(SAMD_FULL, ke == wk)) - 1);
-                    }
-                }
-            } else {
-                for (int e = lane; e < len; e += 32) {
-                    const uint32_t ke = orderable16<kDtype>(row[e]);
-                    if (ke > best_key) {
-                        best_key = ke;
-                        best_idx = (uint32_t)(e0 + e);
-                    }
-                }
-            }
-            unsigned long long pk = best_key ? (((unsigned long long)best_key << 32) | (unsigned long long)(0xFFFFFFFFu - best_idx)) : 0ull;
+                unsigned long long pk = best_key ? (((unsigned long long)best_key << 32) | (unsigned long long)(0xFFFFFFFFu - best_idx)) : 0ull;
+                if (!vec16) {                                   // per-lane maxima: combine (the vector path is warp-uniform)
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(SAMD_FULL, pk, o);
-                pk = other > pk ? other : pk;
+                    for (int o = 16; o; o >>= 1) {
+                        const unsigned long long other = __shfl_xor_sync(SAMD_FULL, pk, o);
+                        pk = other > pk ? other : pk;
+                    }
+                }
+                if (lane == 0) {
+                    unsigned long long *kp = &P.node_key[(size_t)cur.b * P.max_nodes + cur.t];
+                    if (C == 1) *reinterpret_cast<volatile unsigned long long *>(kp) = pk;
+                    else atomicMax(kp, pk);
+                }
             }
-            if (lane == 0) {
-                unsigned long long *kp = &P.node_key[(size_t)b * P.max_nodes + t];
-                if (C == 1) *reinterpret_cast<volatile unsigned long long *>(kp) = pk;
-                else atomicMax(kp, pk);
-            }
+            if (!fetched) fetch_next();
         }
-        int fin = 0;
-        if (lane == 0) {
-            __threadfence();
-            fin = atomicAdd(&P.done[b], 1) == T * C - 1;
-        }
-        fin = __shfl_sync(SAMD_FULL, fin, 0);
-        if (!fin) continue;
+    }
+    if (dbg && lane == 0) dbg[1] = samd_globaltimer();
 
-        // ---- this warp finished request b: path walk (samd/utils.py:127-141) ------------------
+    // ------------------------------ barrier A: every row maximum is published -----------------
+    if (lane == 0) __threadfence();                            // this warp's keys, before the CTA arrives
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&P.counters[CN_ARRIVE_A], 1) == n_ctas - 1) {
+            P.counters[CN_ARRIVE_A] = 0;
+            __threadfence();
+            *reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_A]) = epoch;
+        }
+    }
+
+    // ------------------------------ phase 1b: path walks (samd/utils.py:127-141) ---------------
+    // one warp per request, spread over the SMs (warp 0 of CTA b for the first n_ctas requests); CTAs with neither
+    // a walk nor row moves to do leave right after arriving
+    if (gwarp < A.batch) {
+        if (lane == 0) {
+            while (*reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_A]) != epoch) __nanosleep(100);
+            __threadfence();
+        }
+        __syncwarp();
+    }
+    for (int b = gwarp; b < A.batch; b += n_warps) {
         // keys, tree tokens and this lane's path row are fetched together (one memory round trip); the walk
         // itself then runs out of shared memory and registers
-        __threadfence();
-        if (lane == 0) P.done[b] = 0;
+        const int n_rows = A.n_nodes_dev ? A.n_nodes_dev[b] : T;
         const int32_t *tok = A.tree_tokens_dev + (size_t)b * T;
         const int n_paths = A.retrieve_dev ? (A.n_paths_dev ? A.n_paths_dev[b] : A.n_paths) : 1;
         const int depth = A.retrieve_dev ? A.depth : n_rows;
@@ -297,6 +377,8 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         int rp[WD];
 #pragma unroll
         for (int j = 0; j < WD; ++j) rp[j] = (fast && lane < n_paths && j < depth) ? ri_at(P, b, lane, j) : -1;
+        int start = 0;
+        if (lane == 0 && A.cache_len_dev) start = A.cache_len_dev[b];
         for (int i = lane; i < T; i += 32) {
             unsigned long long *kp = &P.node_key[(size_t)b * P.max_nodes + i];
             const unsigned long long k = __ldcg(kp);
@@ -341,12 +423,21 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         const int acc = (int)(bestpk >> 16);
         const int best = acc == 0 ? 0 : (int)(0xFFFF - (bestpk & 0xFFFF));
         const int out_stride = A.retrieve_dev ? A.depth : T;
-        int moved = 0, last = 0;
+        int moved = 0, last = 0, ix0 = -1;                     // ix0: this lane's accepted index for j = lane
         for (int j0 = 0; j0 < out_stride; j0 += 32) {
             const int j = j0 + lane;
             int tk = -1, ix = -1;
-            if (j < out_stride && j <= acc) {
+            if (fast) {                                         // the best path's row is in that lane's registers
+#pragma unroll
+                for (int q = 0; q < WD; ++q) {
+                    const int v = __shfl_sync(SAMD_FULL, rp[q], best);
+                    if (lane == q) ix = v;
+                }
+                if (j > acc) ix = -1;
+            } else if (j < out_stride && j <= acc) {
                 ix = ri_at(P, b, best, j);
+            }
+            if (j < out_stride && j <= acc) {
                 tk = ix < 0 ? 0 : s_tok[ix];
                 moved += ix != j;
             }
@@ -354,126 +445,120 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
                 if (A.out_tokens_dev) A.out_tokens_dev[(size_t)b * out_stride + j] = tk;
                 if (A.out_indices_dev) A.out_indices_dev[(size_t)b * out_stride + j] = ix;
             }
+            if (j0 == 0) ix0 = ix;
             if (acc >= j0 && acc < j0 + 32) last = __shfl_sync(SAMD_FULL, ix, acc - j0);
         }
         if (lane == 0) {
             if (A.out_best_dev) A.out_best_dev[b] = best;
             if (A.out_accept_len_dev) A.out_accept_len_dev[b] = acc + 1;
             if (A.out_next_token_dev) A.out_next_token_dev[b] = s_am[last < 0 ? n_rows - 1 : last];
-            int start = 0;
-            if (A.cache_len_dev) {
-                start = A.cache_len_dev[b];
-                A.cache_len_dev[b] = start + acc + 1;
-            }
+            if (A.cache_len_dev) A.cache_len_dev[b] = start + acc + 1;
             P.kv_start[b] = start;
         }
-        // publish: requests that really move rows join the compact active list of phase 2
+        // publish: requests that really move rows append their move record {request, accept_len, start, first
+        // KV_GROUP source rows} to the compact active list of phase 2
         moved = __reduce_add_sync(SAMD_FULL, moved);
-        __syncwarp();
-        if (lane == 0) {
-            const int g = (int)(((long long)b * G) / A.batch);          // the request's wave
-            if (moved > 0 && P.n_items2 > 0) P.active[(size_t)(par * MAX_WAVES + g) * P.max_batch + atomicAdd(&cnt_active[g], 1)] = b;
-            __threadfence();
-            // whoever completes a wave raises its (write-once, read-many) flag; pollers never touch the counter
-            const int wave_size = (int)((((long long)g + 1) * A.batch + G - 1) / G - ((long long)g * A.batch + G - 1) / G);
-            if (atomicAdd(&cnt_walked[g], 1) + 1 == wave_size) {
+        if (P.n_items2 > 0) {
+            int slot = 0;
+            if (lane == 0 && moved > 0) slot = atomicAdd(&P.counters[CN_ACTIVE], 1);
+            slot = __shfl_sync(SAMD_FULL, slot, 0);
+            start = __shfl_sync(SAMD_FULL, start, 0);
+            if (moved > 0) {
+                int *rec = P.active + (size_t)slot * KV_REC;
+                if (lane == 0) rec[0] = b, rec[1] = acc + 1, rec[2] = start;
+                if (lane < KV_GROUP) rec[3 + lane] = lane <= acc ? ix0 : lane;
+            }
+            __syncwarp();
+            if (lane == 0) {
                 __threadfence();
-                *reinterpret_cast<volatile int *>(&wave_flag[g]) = epoch;
+                if (atomicAdd(&P.counters[CN_ARRIVE_B], 1) == A.batch - 1) {  // barrier B: every walk is published
+                    P.counters[CN_ARRIVE_B] = 0;
+                    __threadfence();
+                    *reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_B]) = epoch;
+                }
             }
         }
         __syncwarp();
     }
 
     // ------------------------------ phase 2: KV row moves ---------------------------------
-    // KV CTAs only.  Requests are released in G waves (phase 1 streams rows request-major, so waves finish
-    // in order); per wave the moved rows of the active requests are flattened into 16-byte units and strided
-    // over the lanes of all KV CTAs.
-    // (n_kv_ctas == 0: sequential mode - every CTA streams first, then every CTA moves rows, one wave)
-    if (P.n_items2 > 0 && (kv_role || P.n_kv_ctas == 0)) {
-        const int kwarp = P.n_kv_ctas ? warp * P.n_kv_ctas + ((int)blockIdx.x - n_stream_ctas) : gwarp;
-        const int n_kwarps = P.n_kv_ctas ? P.n_kv_ctas * VW : n_warps;
+    // The moved rows of the active requests are flattened into 16-byte units and strided over every lane of the
+    // grid.  (Dedicating a quarter of the CTAs to row moves that overlap the logits stream was measured slower,
+    // 111 vs 90 us on C4: the moves are bound by DRAM row activations and steal DRAM cycles from the stream.)
+    if (P.n_items2 > 0) {
         const int cols = A.row_bytes >> 4;                      // 16-byte columns per (head,row)
         const int per_tensor = A.n_heads * cols;
         const long long per_req = (long long)A.n_kv * per_tensor;
-        constexpr int MW = 3 + KV_GROUP;                       // {request, accept_len, start, first KV_GROUP sources}
+        constexpr int MW = KV_REC;
         int *s_meta = s_am_all + VW * 2 * T;
-        for (int g = 0; g < G; ++g) {
-            __syncthreads();
-            if (threadIdx.x == 0) {                             // one poller per CTA, plain loads, backoff
-                while (*reinterpret_cast<volatile int *>(&wave_flag[g]) != epoch) __nanosleep(300);
-                __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {                                 // one poller per CTA, plain loads, backoff
+            while (*reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_B]) != epoch) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+        const int n_active = __ldcg(&P.counters[CN_ACTIVE]);
+        const int *active = P.active;
+        const long long total = per_req * n_active;
+        // stage the move records in shared memory: no dependent metadata loads in the copy loop
+        const int staged = min(n_active, P.stage_cap);
+        for (int i = threadIdx.x; i < staged * MW; i += VT) s_meta[i] = __ldcg(active + i);
+        __syncthreads();
+        // (more loads in flight per lane - 4 units x 2 rows - was measured: 98 vs 89 us; the row moves are
+        // bound by scattered 256-byte DRAM accesses with read/write turnarounds, not by latency)
+        for (long long u = (long long)gwarp * 32 + lane; u < total; u += (long long)n_warps * 32) {
+            const int a_i = (int)(u / per_req);
+            const int unit = (int)(u - (long long)a_i * per_req);
+            int b, acc1, start;
+            int src[KV_GROUP];
+            if (a_i < staged) {
+                const int *m = s_meta + a_i * MW;
+                b = m[0];
+                acc1 = m[1];
+                start = m[2];
+#pragma unroll
+                for (int q = 0; q < KV_GROUP; ++q) src[q] = m[3 + q];
+            } else {
+                const int *m = active + (size_t)a_i * MW;
+                b = __ldcg(m);
+                acc1 = __ldcg(m + 1);
+                start = __ldcg(m + 2);
+#pragma unroll
+                for (int q = 0; q < KV_GROUP; ++q) src[q] = __ldcg(m + 3 + q);
             }
-            __syncthreads();
-            const int n_active = __ldcg(&cnt_active[g]);
-            const int *active = P.active + (size_t)(par * MAX_WAVES + g) * P.max_batch;
-            const long long total = per_req * n_active;
-            // stage the wave's move lists in shared memory: no dependent metadata loads in the copy loop
-            const int staged = min(n_active, P.stage_cap);
-            for (int i = threadIdx.x; i < staged * MW; i += VT) {
-                const int a_i = i / MW, f = i - a_i * MW;
-                const int b = __ldcg(active + a_i);
-                int v;
-                if (f == 0) v = b;
-                else if (f == 1) v = __ldcg(A.out_accept_len_dev + b);
-                else if (f == 2) v = __ldcg(P.kv_start + b);
-                else {
-                    const int j = f - 3;
-                    v = j < __ldcg(A.out_accept_len_dev + b) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j) : j;
-                }
-                s_meta[i] = v;
-            }
-            __syncthreads();
-            // (more loads in flight per lane - 4 units x 2 rows - was measured: 98 vs 89 us; the row moves are
-            // bound by scattered 256-byte DRAM accesses with read/write turnarounds, not by latency)
-            for (long long u = (long long)kwarp * 32 + lane; u < total; u += (long long)n_kwarps * 32) {
-                const int a_i = (int)(u / per_req);
-                const int unit = (int)(u - (long long)a_i * per_req);
-                int b, acc1, start;
-                int src[KV_GROUP];
-                if (a_i < staged) {
-                    const int *m = s_meta + a_i * MW;
-                    b = m[0];
-                    acc1 = m[1];
-                    start = m[2];
-#pragma unroll
-                    for (int q = 0; q < KV_GROUP; ++q) src[q] = m[3 + q];
-                } else {
-                    b = __ldcg(active + a_i);
-                    acc1 = __ldcg(A.out_accept_len_dev + b);
-                    start = __ldcg(P.kv_start + b);
-#pragma unroll
-                    for (int q = 0; q < KV_GROUP; ++q) src[q] = q < acc1 ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + q) : q;
-                }
-                const int kv = unit / per_tensor;
-                const int w = unit - kv * per_tensor;
-                const int hd = w / cols, col = w - hd * cols;
-                char *hb = reinterpret_cast<char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.kv_ptrs_dev) + kv)) +
-                           (size_t)b * A.kv_batch_stride + (size_t)hd * A.kv_head_stride + ((size_t)col << 4);
-                for (int j0 = 0; j0 < acc1; j0 += KV_GROUP) {
-                    uint4 val[KV_GROUP];
-                    if (j0 > 0) {
-#pragma unroll
-                        for (int q = 0; q < KV_GROUP; ++q)
-                            src[q] = (j0 + q < acc1) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j0 + q) : j0 + q;
-                    }
+            const int kv = unit / per_tensor;
+            const int w = unit - kv * per_tensor;
+            const int hd = w / cols, col = w - hd * cols;
+            char *hb = reinterpret_cast<char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.kv_ptrs_dev) + kv)) +
+                       (size_t)b * A.kv_batch_stride + (size_t)hd * A.kv_head_stride + ((size_t)col << 4);
+            for (int j0 = 0; j0 < acc1; j0 += KV_GROUP) {
+                uint4 val[KV_GROUP];
+                if (j0 > 0) {
 #pragma unroll
                     for (int q = 0; q < KV_GROUP; ++q)
-                        if (src[q] != j0 + q) val[q] = *reinterpret_cast<const uint4 *>(hb + (size_t)(start + src[q]) * A.kv_pos_stride);
-#pragma unroll
-                    for (int q = 0; q < KV_GROUP; ++q)
-                        if (src[q] != j0 + q) *reinterpret_cast<uint4 *>(hb + (size_t)(start + j0 + q) * A.kv_pos_stride) = val[q];
+                        src[q] = (j0 + q < acc1) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j0 + q) : j0 + q;
                 }
+#pragma unroll
+                for (int q = 0; q < KV_GROUP; ++q)
+                    if (src[q] != j0 + q) val[q] = *reinterpret_cast<const uint4 *>(hb + (size_t)(start + src[q]) * A.kv_pos_stride);
+#pragma unroll
+                for (int q = 0; q < KV_GROUP; ++q)
+                    if (src[q] != j0 + q) *reinterpret_cast<uint4 *>(hb + (size_t)(start + j0 + q) * A.kv_pos_stride) = val[q];
             }
         }
     }
-    // last CTA out: bump the device-side epoch (every CTA read it before it could change)
+    if (dbg && lane == 0) dbg[2] = samd_globaltimer();
+    // last CTA out: re-arm the work and active counters and bump the device-side epoch (every CTA read it before it
+    // could change)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(&P.counters[5 * MAX_WAVES + 1], 1) == (int)gridDim.x - 1) {
-            P.counters[5 * MAX_WAVES + 1] = 0;
+        if (atomicAdd(&P.counters[CN_EXIT], 1) == n_ctas - 1) {
+            P.counters[CN_EXIT] = 0;
+            P.counters[CN_ACTIVE] = 0;
+            for (int q = 0; q < N_QUEUES; ++q) P.counters[CN_QUEUES + q * QUEUE_STRIDE] = 0;
             __threadfence();
-            *reinterpret_cast<volatile int *>(&P.counters[5 * MAX_WAVES]) = epoch;
+            *reinterpret_cast<volatile int *>(&P.counters[CN_EPOCH]) = epoch;
         }
     }
 }
@@ -487,14 +572,12 @@ extern "C" int samd_verify_create(int max_batch, int max_nodes, samd_verify_t *o
     SAMD_CUDA(cudaGetDevice(&h->device));
     SAMD_CUDA(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, h->device));
     SAMD_CUDA(cudaMalloc(&h->node_key, (size_t)max_batch * max_nodes * sizeof(unsigned long long)));
-    SAMD_CUDA(cudaMalloc(&h->done, (size_t)max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMalloc(&h->active, (size_t)2 * MAX_WAVES * max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMalloc(&h->counters, (5 * MAX_WAVES + 2) * sizeof(int)));
+    SAMD_CUDA(cudaMalloc(&h->active, (size_t)max_batch * KV_REC * sizeof(int)));
+    SAMD_CUDA(cudaMalloc(&h->counters, CN_WORDS * sizeof(int)));
     SAMD_CUDA(cudaMalloc(&h->kv_start, (size_t)max_batch * sizeof(int)));
     SAMD_CUDA(cudaMemset(h->node_key, 0, (size_t)max_batch * max_nodes * sizeof(unsigned long long)));
-    SAMD_CUDA(cudaMemset(h->done, 0, (size_t)max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMemset(h->active, 0, (size_t)2 * MAX_WAVES * max_batch * sizeof(int)));
-    SAMD_CUDA(cudaMemset(h->counters, 0, (5 * MAX_WAVES + 2) * sizeof(int)));
+    SAMD_CUDA(cudaMemset(h->active, 0, (size_t)max_batch * KV_REC * sizeof(int)));
+    SAMD_CUDA(cudaMemset(h->counters, 0, CN_WORDS * sizeof(int)));
     SAMD_CUDA(cudaMemset(h->kv_start, 0, (size_t)max_batch * sizeof(int)));
     SAMD_CUDA(cudaDeviceSynchronize());
     *out = h;
@@ -504,7 +587,6 @@ extern "C" int samd_verify_create(int max_batch, int max_nodes, samd_verify_t *o
 extern "C" int samd_verify_destroy(samd_verify_t h) {
     if (!h) return 0;
     cudaFree(h->node_key);
-    cudaFree(h->done);
     cudaFree(h->active);
     cudaFree(h->counters);
     cudaFree(h->kv_start);
@@ -513,9 +595,10 @@ extern "C" int samd_verify_destroy(samd_verify_t h) {
 }
 
 static int g_chunk_override = 0;
-static int g_overlap_mode = 0;
+static int g_min_chunk = 2048;
+static unsigned long long *g_dbg_times = nullptr;
+extern "C" void samd_verify_set_debug_times(uint64_t *times_dev) { g_dbg_times = (unsigned long long *)times_dev; }
 extern "C" void samd_verify_set_chunk(int elements) { g_chunk_override = elements; }
-extern "C" void samd_verify_set_overlap(int on) { g_overlap_mode = on; }
 
 extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, void *stream) {
     SAMD_REQUIRE(h && a, "samd_verify_compact: bad arguments");
@@ -538,11 +621,11 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     VerifyParams P;
     P.a = *a;
     P.node_key = h->node_key;
-    P.done = h->done;
     P.active = h->active;
     P.counters = h->counters;
     P.max_batch = h->max_batch;
     P.kv_start = h->kv_start;
+    P.dbg_times = g_dbg_times;
     P.max_nodes = h->max_nodes;
     P.stage_cap = move ? std::min(a->batch, 512) : 0;
     const size_t smem = ((size_t)VW * 2 * a->n_nodes + (size_t)P.stage_cap * (3 + KV_GROUP)) * sizeof(int);
@@ -555,42 +638,23 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
         if (smem <= 8192) h->occ_per_sm[a->dtype] = per_sm;
     }
     SAMD_REQUIRE(per_sm > 0, "samd_verify_compact: kernel does not fit on an SM");
-    // persistent grid: every CTA must be resident (KV CTAs spin on the streaming CTAs' results)
+    // persistent grid: every CTA must be resident (the kernel has grid-wide barriers)
     const long long rows = (long long)a->batch * a->n_nodes;
-    long long grid;
-    int chunks = 1;
-    if (move && !g_overlap_mode) {
-        // sequential mode (default): all CTAs stream the logits in one wave, then all CTAs move the rows.
-        // Measured on B200 (C4): 90 us; dedicating a quarter of the CTAs to row moves that overlap the
-        // streaming (overlap mode below) measured 111 us - the moves are bound by DRAM row activations and
-        // need every lane in flight, and they steal DRAM cycles from the stream.
-        grid = std::max<long long>(1, (long long)h->n_sms * per_sm);
-        P.n_kv_ctas = 0;
-        P.n_waves = 1;
-        while (rows * chunks * 2 <= grid * VW && a->vocab / (chunks * 2) >= 2048) chunks *= 2;
-    } else if (move) {
-        grid = std::max<long long>(2, (long long)h->n_sms * per_sm);
-        P.n_kv_ctas = (int)std::max<long long>(1, grid / 4);     // one KV CTA per SM when per_sm == 4
-        P.n_waves = std::min(std::min(a->batch, 4), MAX_WAVES);
-        // short rounds so that request waves complete (and release their KV work) progressively
-        const long long stream_warps = (grid - P.n_kv_ctas) * VW;
-        while (rows * chunks < 4 * stream_warps && a->vocab / (chunks * 2) >= 2048) chunks *= 2;
-    } else {
-        const long long resident_warps = (long long)h->n_sms * per_sm * VW;
-        P.n_kv_ctas = 0;
-        P.n_waves = 1;
-        // split rows into chunks only when whole rows would leave most of the machine idle
-        while (rows * chunks * 2 <= resident_warps && a->vocab / (chunks * 2) >= 2048) chunks *= 2;
-        grid = 0;
-    }
+    const long long resident_warps = (long long)h->n_sms * per_sm * VW;
+    // Items are handed out dynamically.  Measured on C4 (uniform chunks): 16000 elements 50.0 us, 8192 51.4, 4000
+    // 54.3, 2000 67.4, whole rows 53.7 - an item switch costs about half a microsecond of issue latency, so chunks
+    // are about 16k elements unless the launch is too small to give every resident warp one.
+    int chunks = std::max(1, (a->vocab + 8192) / 16384);
+    while (rows * chunks < resident_warps && a->vocab / (chunks * 2) >= g_min_chunk) chunks *= 2;
     if (g_chunk_override > 0) chunks = (a->vocab + g_chunk_override - 1) / g_chunk_override;
-    int chunk = ((a->vocab + chunks - 1) / chunks + 7) & ~7;
+    const int chunk = ((a->vocab + chunks - 1) / chunks + 7) & ~7;
     P.chunk = chunk;
     P.chunks_per_row = (a->vocab + chunk - 1) / chunk;
-    P.n_items1 = a->batch * a->n_nodes * P.chunks_per_row;
+    P.n_items1 = (int)rows * P.chunks_per_row;
     P.n_items2 = move ? a->batch * a->n_kv : 0;
     P.vec_ok = ((uintptr_t)a->logits_dev % 16 == 0) && (a->batch_stride % 8 == 0) && (a->row_stride % 8 == 0);
-    if (!move) grid = std::max<long long>(1, std::min<long long>((long long)h->n_sms * per_sm, ((long long)P.n_items1 + VW - 1) / VW));
+    const long long grid = move ? std::max<long long>(1, (long long)h->n_sms * per_sm)
+                                : std::max<long long>(1, std::min<long long>((long long)h->n_sms * per_sm, ((long long)P.n_items1 + VW - 1) / VW));
     kern<<<(int)grid, VT, smem, (cudaStream_t)stream>>>(P);
     samd_count_launch();
     SAMD_CUDA(cudaGetLastError());

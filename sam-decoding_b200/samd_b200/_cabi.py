@@ -96,7 +96,7 @@ SYMBOLS = {
     "samd_verify_destroy": (C.c_int, [vp]),
     "samd_verify_compact": (C.c_int, [vp, C.POINTER(VerifyArgs), vp]),
     "samd_verify_set_chunk": (None, [C.c_int]),
-    "samd_verify_set_overlap": (None, [C.c_int]),
+    "samd_verify_set_debug_times": (None, [C.c_void_p]),
 }
 
 _lib = None

@@ -3,7 +3,7 @@ import sys; sys.path.insert(0, "sam-decoding_b200")
 import torch
 from samd_b200 import _cabi as K
 dev = torch.device("cuda")
-for gb, warps in ((2.4, 1024), (2.4, 4096), (0.05, 1024)):
+for gb, warps in ((0.05, 1024), (2.4, 1024), (16.0, 1024), (64.0, 1024), (64.0, 8192)):
     n = int(gb * 1e9 / 64)
     t = torch.randint(0, 2 ** 31 - 1, (n, 16), dtype=torch.int32, device=dev)
     sink = torch.zeros(warps, dtype=torch.int32, device=dev)
