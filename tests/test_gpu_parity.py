@@ -515,3 +515,77 @@ def test_verify_compact_is_graph_replayable():
             assert np.array_equal(got, z["kv/after_bits"][c][:, 0]), c
         assert np.array_equal(out["accept_len"].cpu().numpy(), z["bf16/accept_len"][sel])
         assert np.array_equal(cache_len.cpu().numpy(), start.cpu().numpy() + z["bf16/accept_len"][sel])
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,V,P,D,dt", [
+    (1, 1, 5, 1, 1, "bf16"), (3, 7, 1001, 5, 4, "fp16"), (5, 61, 32001, 30, 6, "bf16"), (130, 3, 4099, 3, 3, "bf16"),
+    (9, 40, 2500, 40, 10, "fp32"), (17, 12, 777, 33, 8, "bf16"), (700, 2, 64, 2, 2, "fp16"), (2, 64, 151936, 12, 7, "bf16"),
+])
+def test_verify_random_shapes(B, T, V, P, D, dt):
+    """Odd shapes through every code path of the verify kernel: vocabularies that are not a multiple of the vector
+    width (padded row stride -> vector path with a ragged end; unpadded -> scalar path), more than 32 paths or more
+    than 8 levels (the general walk), per-request path tables with -1 padding, ragged node counts, planted ties,
+    and KV row moves - against torch.argmax, the oracle walk and an index_select reference."""
+    E, K = _engine_mod()
+    rng = np.random.default_rng(B * 1000 + T)
+    tdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[dt]
+    for padded in (True, False):
+        Vp = (V + 7) // 8 * 8 if padded else V
+        store = torch.randn(B, T, Vp, device="cuda").to(tdt)
+        logits = store[:, :, :V]
+        # ties: copy the row maximum to a later column in a third of the rows (lowest index must win)
+        am0 = logits.float().argmax(-1)
+        if V > 2:
+            tie_col = torch.clamp(am0 + 1 + torch.randint(0, V, am0.shape, device="cuda") % (V - 1), max=V - 1)
+            mask = torch.rand(B, T, device="cuda") < 0.33
+            vals = logits.gather(2, am0[..., None])
+            logits.scatter_(2, tie_col[..., None], torch.where(mask[..., None], vals, logits.gather(2, tie_col[..., None])))
+        n_nodes = rng.integers(1, T + 1, size=B).astype(np.int32)
+        am = logits.float().argmax(-1).cpu().numpy()      # torch.argmax: first maximal index
+        retrieve = np.full((B, P, D), -1, dtype=np.int32)
+        n_paths = rng.integers(1, P + 1, size=B).astype(np.int32)
+        tree_tokens = rng.integers(1, V, size=(B, T)).astype(np.int32)
+        for b in range(B):
+            for p in range(n_paths[b]):
+                depth = int(rng.integers(1, D + 1))
+                rest = np.sort(rng.choice(np.arange(1, n_nodes[b]), size=min(depth - 1, n_nodes[b] - 1), replace=False)) \
+                    if n_nodes[b] > 1 else np.zeros(0, dtype=np.int64)
+                path = np.concatenate([[0], rest]).astype(np.int32)
+                retrieve[b, p, :len(path)] = path
+                for j in range(1, len(path)):              # plant acceptances along the path
+                    if rng.random() < 0.6:
+                        tree_tokens[b, path[j]] = am[b, path[j - 1]]
+        L, H, ML, DH = 2, 2, T + 40, 16
+        kv = [torch.randn(B, H, ML, DH, device="cuda").to(torch.bfloat16) for _ in range(2 * L)]
+        kv_ref = [t.clone() for t in kv]
+        start = rng.integers(0, 30, size=B).astype(np.int32)
+        cache_len = _dev_i32(start)
+        ver = E.Verifier(B, T)
+        ver.bind_kv(kv)
+        out = None
+        for rep in range(2):                               # the second launch runs on re-armed scratch
+            for t, t0 in zip(kv, kv_ref):
+                t.copy_(t0)
+            cache_len.copy_(_dev_i32(start))
+            out = ver.verify(logits, _dev_i32(tree_tokens), _dev_i32(retrieve), cache_len=cache_len, n_nodes=_dev_i32(n_nodes),
+                             n_paths=_dev_i32(n_paths), want_argmax=True, out=out)
+            torch.cuda.synchronize()
+            got_am = out["node_argmax"].cpu().numpy()
+            o = {k: v.cpu().numpy() for k, v in out.items()}
+            for b in range(B):
+                nr = n_nodes[b]
+                assert np.array_equal(got_am[b, :nr], am[b, :nr]), (padded, b)
+                r = O.verify_greedy(am[b, :nr], tree_tokens[b, :nr], retrieve[b, :n_paths[b]].astype(np.int64))
+                al = r["accept_len"]
+                assert o["best"][b] == r["best"] and o["accept_len"][b] == al and o["next_token"][b] == r["next_token"]
+                assert o["tokens"][b, :al].tolist() == r["tokens"].tolist()
+                assert o["indices"][b, :al].tolist() == r["indices"].tolist()
+                if B <= 20:
+                    src = torch.as_tensor(int(start[b]) + r["indices"], device="cuda")
+                    for t, t_ref in zip(kv, kv_ref):
+                        want = t_ref[b].clone()
+                        want[:, start[b]:start[b] + al] = t_ref[b].index_select(1, src)
+                        assert torch.equal(t[b], want), (padded, b)
+            assert np.array_equal(cache_len.cpu().numpy(), start + o["accept_len"])
+        ver.close()
