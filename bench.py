@@ -333,9 +333,10 @@ def run_ours(a):
     kern_ms = float(np.mean([x.elapsed_time(y) for x, y in evs]))
 
     # e2e: host buffers in, drafts out, through the public engine API (DraftEngine.step_host): per step the
-    # caller stages its inputs (counts | start tokens | accepted tokens) in a pinned buffer, ONE H2D copy, the
-    # step kernel, ONE D2H copy of every output (type, match lengths, state indices, draft length, draft
-    # tokens) into pinned host memory, then the stream is synchronised
+    # caller stages its inputs (counts | start tokens | accepted tokens) in a pinned buffer; the step kernel reads
+    # them and writes every output (type, match lengths, state indices, draft length, draft tokens) straight into
+    # pinned host memory over PCIe (mapped, zero-copy: measured faster than copy-engine staging, 46 vs 66 us);
+    # then the stream is synchronised.  h2d / d2h bytes are the sizes of those two host buffers.
     dyn.copy_from(snap)
     inp, res = eng.host_buffers(8)
     h_in = torch.empty(W + S, inp.numel(), dtype=torch.int32).pin_memory()

@@ -589,3 +589,46 @@ def test_verify_random_shapes(B, T, V, P, D, dt):
                         assert torch.equal(t[b], want), (padded, b)
             assert np.array_equal(cache_len.cpu().numpy(), start + o["accept_len"])
         ver.close()
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("zero_copy", [True, False])
+def test_step_host_matches_device_step(zero_copy):
+    """The host-buffer entry (DraftEngine.step_host: pinned buffers, graph-replayed, zero-copy or staged through
+    device copies) produces exactly what the device-buffer step produces, step after step."""
+    E, K = _engine_mod()
+    from samd_b200 import synth
+    B, N, steps = 48, 512, 12
+    streams = [synth.copy_mix(N + 8 * steps + 1, 500, 7000 + r) for r in range(B)]
+    prompt = _dev_i32(np.stack([s[:N] for s in streams]))
+    engines = []
+    for _ in range(2):
+        dyn = E.DynSamBatch(B, N + 8 * steps + 8)
+        eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=16, len_bias=5, len_threshold=5)
+        eng.step(prompt, None, None)
+        engines.append(eng)
+    dev_eng, host_eng = engines
+    inp, res = host_eng.host_buffers(8)
+    rng = np.random.default_rng(11)
+    pos = [N] * B
+    for s in range(steps):
+        cnt = rng.integers(0, 9, size=B).astype(np.int32)
+        tok = np.zeros((B, 8), dtype=np.int32)
+        start = np.zeros(B, dtype=np.int32)
+        for r in range(B):
+            tok[r, :cnt[r]] = streams[r][pos[r]:pos[r] + cnt[r]]
+            pos[r] += cnt[r]
+            start[r] = streams[r][pos[r]]
+        dev_eng.step(_dev_i32(tok), _dev_i32(cnt), _dev_i32(start))
+        inp[:B] = torch.as_tensor(cnt)
+        inp[B:2 * B] = torch.as_tensor(start)
+        inp[2 * B:] = torch.as_tensor(tok).reshape(-1)
+        host_eng.step_host(inp, res, zero_copy=zero_copy)
+        want = dev_eng.out_buf.cpu().numpy()
+        got = res.numpy()
+        # type, match lengths, state indices, draft length: exact; draft tokens: up to draft_len
+        assert np.array_equal(got[:6 * B], want[:6 * B]), s
+        dl = want[5 * B:6 * B]
+        gd, wd = got[6 * B:].reshape(B, -1), want[6 * B:].reshape(B, -1)
+        for r in range(B):
+            assert np.array_equal(gd[r, :dl[r]], wd[r, :dl[r]]), (s, r)
