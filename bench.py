@@ -494,15 +494,15 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5):
     d_ri = torch.as_tensor(ri_np).to(dev)
     cache0 = cache_len = res = None
 
-    def run(n, move):
+    def run(n, move, recycle=None):
         """n launches (rotating logits buffers) captured as ONE CUDA graph and replayed: per-launch time is pure
         device time, free of host enqueue gaps.  cache_len keeps growing inside a replay (reset between replays)."""
-        outs = [ver.verify(logits[i], d_tok, d_ri, cache_len=cache_len, move_kv=move) for i in range(nbuf)]   # warm + allocate
+        outs = [ver.verify(logits[i], d_tok, d_ri, cache_len=cache_len, move_kv=move, recycle=recycle) for i in range(nbuf)]   # warm + allocate
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for i in range(n):
-                ver.verify(logits[i % nbuf], d_tok, d_ri, cache_len=cache_len, move_kv=move, out=outs[i % nbuf])
+                ver.verify(logits[i % nbuf], d_tok, d_ri, cache_len=cache_len, move_kv=move, out=outs[i % nbuf], recycle=recycle)
         times = []
         for rep in range(7):
             cache_len.copy_(cache0)
@@ -514,7 +514,7 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5):
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1) / n)
         cache_len.copy_(cache0)
-        res_local = ver.verify(logits[0], d_tok, d_ri, cache_len=cache_len, move_kv=move, out=outs[0])
+        res_local = ver.verify(logits[0], d_tok, d_ri, cache_len=cache_len, move_kv=move, out=outs[0], recycle=recycle)
         torch.cuda.synchronize()
         return times[2:], res_local
 
@@ -524,6 +524,19 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5):
     cache_len = cache0.clone()
     t_full, res = run(n_graph, True)
     t_nokv, _ = run(n_graph, False)
+    # Token Recycle's top-8 table update riding on the same pass, and what it replaces: a second
+    # full read of the logits by torch.topk
+    table = E.RecycleTable(synth.token_recycle_tree(), V, dev)
+    t_rec, _ = run(n_graph, True, recycle=table)
+    tk = []
+    for i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        logits[i % nbuf].topk(8)
+        e1.record()
+        tk.append((e0, e1))
+    torch.cuda.synchronize()
+    us_torch_topk = float(np.median([x.elapsed_time(y) for x, y in tk][2:])) * 1e3
     cache_len.copy_(cache0)
     res = ver.verify(logits[0], d_tok, d_ri, cache_len=cache_len, move_kv=True, out=res)
     torch.cuda.synchronize()
@@ -561,7 +574,10 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5):
             "roofline": {"kernel": "verify_compact_kernel", "bound": "hbm", "achieved": gbs_full, "peak": hbm_peak,
                          "unit": "GB/s", "frac": gbs_full / hbm_peak, "traffic": None},
             "roofline_verify_only": {"achieved": gbs_nokv, "peak": hbm_peak, "unit": "GB/s", "frac": gbs_nokv / hbm_peak},
-            "gpu_launches_per_step": 1}
+            "gpu_launches_per_step": 1,
+            "token_recycle": {"us_per_step_with_top8_table_update": float(np.median(t_rec)) * 1e3,
+                              "us_torch_topk_separate_pass": us_torch_topk,
+                              "note": "top-8 of all B*T rows + table[token] update fused into the verify launch"}}
 
 
 def bench_c2_concurrent(a, dev, workload, n_streams=4):

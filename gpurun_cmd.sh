@@ -1,7 +1,2 @@
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err; echo "bench rc=$?"; tail -c 300 gpurun_out/bench_r1_final.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 8 --warmup 3 --no-cpu > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:sam_step_kernel -s 8 -c 2 -f -o gpurun_out/prof_step_r1 python bench.py --steps 8 --warmup 3 --only-step > gpurun_out/ncu_step_full.log 2>&1; echo "ncu step rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:verify_compact -s 12 -c 2 -f -o gpurun_out/prof_verify_r1 python bench.py --only-verify --kv-len 256 > gpurun_out/ncu_verify_full.log 2>&1; echo "ncu verify rc=$?"
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or random_shapes or step_host or graph_replayable" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitizer_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or step_host or graph_replayable" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/sanitizer_racecheck.log
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:.*bool\)1.*' --launch-skip 6 -c 1 -f -o gpurun_out/prof_verify_topk python bench.py --only-verify --kv-len 256 > gpurun_out/ncu_vt.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_vt.log

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SAMD_ABI_VERSION 1
+#define SAMD_ABI_VERSION 2
 
 /* draft flavours (which reference package's rules apply) */
 #define SAMD_FLAVOUR_SAMD      0   /* samd/draft.py:52-63, fixed n_predicts, zero padding      */
@@ -239,9 +239,24 @@ typedef struct samd_verify_args {
     int32_t *out_best_dev, *out_accept_len_dev, *out_next_token_dev;   /* [B] */
     int32_t *out_tokens_dev, *out_indices_dev;      /* [B][depth] (sequence: [B][n_nodes]) */
     int32_t *out_node_argmax_dev;     /* [B][n_nodes] or NULL */
+    /* Token Recycle (samd/tree_model/token_recycle/token_recycle.py:36-47), fused into the same pass over the logits:
+     * out_topk_dev != NULL -> the 8 largest logits of every row, as indices ordered (value descending, index
+     * ascending; NaN largest; column 0 = the row argmax), -1 rows for dead nodes.  recycle_table_dev != NULL ->
+     * additionally table[tree_tokens[b][t]][0..7] = that row's list, the last (b, t) winning when a token feeds
+     * several rows (the reference's zip order); recycle_owner_dev is [vocab] scratch holding -1 between launches. */
+    int32_t *out_topk_dev;            /* [B][n_nodes][8] or NULL */
+    int32_t *recycle_table_dev;       /* [vocab][8], rows of -1 = no entry; or NULL */
+    int32_t *recycle_owner_dev;       /* [vocab] */
 } samd_verify_args;
 
 int samd_verify_compact(samd_verify_t h, const samd_verify_args *args, void *stream);
+/* TokenRecycle.gen_draft (token_recycle.py:49-59) for a batch: tokens[b][0] = start_tok[b]; every other node takes
+ * table[token of its parent][its rank among the parent's children], or 0 when the parent's token has no entry.
+ * parent / rank: [n_nodes] device arrays describing the static tree (node 0 = root, parents before children);
+ * type_dev != NULL restricts the fill to requests whose type equals `only_type` (others are left untouched). */
+int samd_recycle_gen_tree(const int32_t *table_dev, int32_t vocab, const int32_t *parent_dev, const int32_t *rank_dev,
+                          int32_t n_nodes, const int32_t *start_tok_dev, const int32_t *type_dev, int32_t only_type,
+                          int32_t batch, int32_t *out_tokens_dev, void *stream);
 /* tuning hook: logits elements per phase-1 work item (0 = default) */
 void samd_verify_set_chunk(int elements);
 /* profiling hook: [grid warps][3] uint64 globaltimer ns per warp of the next launches - start, end of the logits

@@ -405,6 +405,45 @@ def loop_fixture(ns):
     print("decode_loop.npz", {n: (len(out[f'{n}/accepts']), float(out[f'{n}/accepts'].mean())) for n in names})
 
 
+def recycle_fixture(ns):
+    """TokenRecycle.update / gen_draft (samd/tree_model/token_recycle/token_recycle.py) driven for a few decode
+    steps: logits rows with pairwise-distinct values (so torch.topk's unspecified tie order cannot matter),
+    tokens that repeat inside a step (last row wins) and across steps (later step wins), starts that miss."""
+    import importlib
+    tr = importlib.import_module("samd.tree_model.token_recycle.token_recycle")
+    cfg = ns.samd_config.SamdConfig()
+    model = tr.TokenRecycle(cfg, None, torch.float32, "cpu")
+    tree = cfg.tree
+    T, V, steps = len(tree), 640, 6
+    rng = np.random.default_rng(77)
+    # distinct finite bf16 bit patterns: positive 0x3C00..0x4600 and their negatives
+    pool = np.concatenate([np.arange(0x3C00, 0x4600), np.arange(0xBC00, 0xC600)]).astype(np.uint16)
+    out = {"tree_flat": ragged(tree)[0], "tree_offs": ragged(tree)[1], "vocab": np.array(V)}
+    all_bits, all_tok, all_topk, drafts, starts = [], [], [], [], []
+    for s in range(steps):
+        bits = np.stack([rng.choice(pool, size=V, replace=False) for _ in range(T)])
+        logits = torch.from_numpy(bits.view(np.int16)).view(torch.bfloat16)
+        tokens = rng.integers(3, 60, size=T)                       # small range: repeats inside and across steps
+        model.update(tree_tokens=torch.as_tensor(tokens), tree_logits=logits.float())
+        all_bits.append(bits)
+        all_tok.append(tokens)
+        all_topk.append(np.array(model.logits_to_topk(logits.float())))
+        for q in range(4):
+            st = int(rng.integers(3, 70))                          # some starts have no entry
+            starts.append(st)
+            drafts.append(model.gen_draft(st)[0])
+    out["logits_bits"] = np.stack(all_bits)                         # [steps, T, V] bf16 bits
+    out["tokens"] = np.stack(all_tok)
+    out["topk"] = np.stack(all_topk)                                # [steps, T, 8]
+    out["starts"] = np.array(starts).reshape(steps, 4)
+    out["drafts"] = np.array(drafts).reshape(steps, 4, T)
+    keys = sorted(model.cache)
+    out["cache_keys"] = np.array(keys)
+    out["cache_vals"] = np.array([model.cache[k] for k in keys])
+    np.savez_compressed(os.path.join(OUT, "recycle.npz"), **out)
+    print("recycle.npz", {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
 def pickle_fixture(ns):
     """Pickles written by the reference's own dump_sam (samd/sam/utils.py:20-22), to check that this
     framework's load_sam reads them (module path / class names / attribute layout)."""
@@ -426,11 +465,15 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "pickles":
         pickle_fixture(ns)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "recycle":
+        recycle_fixture(ns)
+        return
     dyn_fixture(ns)
     static_fixture(ns)
     select_fixture(ns)
     verify_fixture(ns)
     loop_fixture(ns)
+    recycle_fixture(ns)
     pickle_fixture(ns)
 
 

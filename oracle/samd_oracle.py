@@ -378,6 +378,46 @@ def row_argmax(logits) -> np.ndarray:
     return np.where(has_nan, first_nan, plain).astype(np.int64)
 
 
+def row_topk(logits, k: int = 8) -> np.ndarray:
+    """torch.topk(k).indices per row as used at samd/tree_model/token_recycle/token_recycle.py:36-38, under the
+    deterministic refinement (value descending, index ascending): torch leaves the order - and the choice - of
+    equal values unspecified, so equality with the reference is defined on rows whose k+1 largest values are
+    distinct, and on the multiset of selected VALUES otherwise.  NaN counts as the largest value (torch.topk's
+    rule, same as argmax), +0.0 == -0.0.  Column 0 is row_argmax()."""
+    try:
+        import torch
+        if isinstance(logits, torch.Tensor):
+            logits = logits.detach().to("cpu", torch.float32).numpy()
+    except ImportError:  # pragma: no cover
+        pass
+    x = np.asarray(logits, dtype=np.float32)
+    key = x.astype(np.float64)
+    key = np.where(np.isposinf(key), np.finfo(np.float64).max, key)
+    key = np.where(np.isnan(x), np.inf, key)                    # NaN above +inf
+    order = np.argsort(-key, axis=-1, kind="stable")            # stable: equal values keep index order
+    return order[..., :k].astype(np.int64)
+
+
+def recycle_update(cache: dict, tree_tokens, topk_rows) -> None:
+    """TokenRecycle.update (token_recycle.py:39-47): cache[token] = that row's top-k, rows in order - a token
+    that occurs twice keeps the LAST row's list."""
+    for tok, best in zip(np.asarray(tree_tokens).tolist(), np.asarray(topk_rows).tolist()):
+        cache[int(tok)] = [int(b) for b in best]
+
+
+def recycle_gen_draft(cache: dict, tree: List[List[int]], start_token: int) -> List[int]:
+    """TokenRecycle.gen_draft (token_recycle.py:49-59): fill the static tree top-down; the children of a node
+    whose token has no entry keep their current value (0)."""
+    tokens = [int(start_token)] + [0] * (len(tree) - 1)
+    for node, childs in enumerate(tree):
+        best = cache.get(tokens[node])
+        if best is None:
+            continue
+        for j, child in enumerate(childs):
+            tokens[child] = best[j]
+    return tokens
+
+
 def verify_greedy(node_argmax: np.ndarray, tree_tokens: np.ndarray, retrieve: np.ndarray):
     """samd/samd_model.py:159-168 (gather) + samd/utils.py:127-141 (greedy posterior) +
     samd/samd_model.py:195-199 (accepted tokens / indices) for ONE request.

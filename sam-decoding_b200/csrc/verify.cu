@@ -33,7 +33,9 @@ struct samd_verify_s {
     unsigned long long *node_key;   // [max_batch][max_nodes]
     int *active;                    // [max_batch][KV_REC] move records of the requests with rows to move
     int *counters;                  // [CN_WORDS] epoch, exit count, work counter, barrier arrivals and flags, n_active
-    int occ_per_sm[3];              // cached occupancy per dtype
+    int occ_per_sm[6];              // cached occupancy per dtype (x top-k variant)
+    unsigned long long *topk_part;  // [topk_items][TOPK] per-chunk top-8 lists
+    long long topk_items;
     int *kv_start;                  // [max_batch] cache_len before the bump
     int max_batch, max_nodes, device, n_sms;
 };
@@ -44,6 +46,7 @@ struct VerifyParams {
     int *active, *counters, *kv_start;
     int max_nodes, max_batch;
     int chunk, chunks_per_row, n_items1, n_items2, vec_ok, stage_cap;
+    unsigned long long *topk_part;   // [n_items1][TOPK] per-chunk lists (top-k launches)
     unsigned long long *dbg_times;   // optional [grid warps][3] globaltimer ns: start, end of streaming, exit (profiling hook)
 };
 
@@ -178,6 +181,105 @@ __device__ __forceinline__ void fold_group(const uint4 (&x)[G], int v0, int nvec
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Top-8 per row (Token Recycle, samd/tree_model/token_recycle/token_recycle.py:36-38) in the same pass.
+// The warp keeps a sorted list of 8 composites  key << 32 | (0xFFFFFFFF - index)  in lanes 0..7 (descending:
+// value descending, index ascending - lane 0 is the argmax) and the warp-uniform key of the 8th entry as the
+// admission threshold; elements equal to -inf never enter (a row with fewer than 8 larger elements is completed
+// from a re-scan when the chunks are merged).
+// ---------------------------------------------------------------------------------------
+#define TOPK 8
+
+template <int kDtype>
+__device__ __forceinline__ uint32_t key_ninf() {
+    return kDtype == SAMD_DTYPE_BF16 ? 0x007Fu : kDtype == SAMD_DTYPE_FP16 ? 0x03FFu : 0x007FFFFFu;
+}
+
+__device__ __forceinline__ void topk_insert(unsigned long long c, unsigned long long &t, uint32_t &thrv, int lane) {
+    const int pos = __popc(__ballot_sync(SAMD_FULL, lane < TOPK && t > c));      // a prefix: the list is sorted
+    const unsigned long long prev = __shfl_up_sync(SAMD_FULL, t, 1);
+    if (lane < TOPK && lane >= pos) t = lane == pos ? c : prev;
+    thrv = (uint32_t)(__shfl_sync(SAMD_FULL, t, TOPK - 1) >> 32);
+}
+
+__device__ __forceinline__ void clear_half(uint4 &x, int e, uint32_t ninf16) {
+    uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if ((e >> 1) == i) w[i] = (e & 1) ? ((w[i] & 0x0000FFFFu) | (ninf16 << 16)) : ((w[i] & 0xFFFF0000u) | ninf16);
+    x = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Vector path: every element of the group above the threshold is pulled out, largest first, and inserted.
+template <int kDtype, int G>
+__device__ __forceinline__ void fold_group_topk(uint4 (&x)[G], int v0, int nvec, int lane, int e0, unsigned long long &t,
+                                                uint32_t &thrv, uint32_t floorv) {
+    while (true) {
+        uint32_t m = vec_pair_max<kDtype>(x[0]);
+#pragma unroll
+        for (int u = 1; u < G; ++u) m = hmax2_bits<kDtype>(m, vec_pair_max<kDtype>(x[u]));
+        const uint32_t wk = __reduce_max_sync(SAMD_FULL, pair_key<kDtype>(m));
+        if (wk <= max(thrv, floorv)) return;                    // warp-uniform
+        bool found = false;
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            if (found) continue;
+            const int vi = v0 + u * 32 + lane;
+            const unsigned bal = __ballot_sync(SAMD_FULL, vi < nvec && pair_key<kDtype>(vec_pair_max<kDtype>(x[u])) == wk);
+            if (bal) {                                         // lowest u, then lowest lane = lowest index
+                found = true;
+                const int src = __ffs(bal) - 1;
+                int e_first = 0;
+                if (lane == src) {
+                    const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                    e_first = 7;
+#pragma unroll
+                    for (int e = 7; e >= 0; --e)
+                        if (orderable16<kDtype>((w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu) == wk) e_first = e;
+                    clear_half(x[u], e_first, kDtype == SAMD_DTYPE_BF16 ? 0xFF80u : 0xFC00u);   // taken
+                }
+                e_first = __shfl_sync(SAMD_FULL, e_first, src);
+                const uint32_t idx = (uint32_t)(e0 + (v0 + u * 32 + src) * 8 + e_first);
+                topk_insert(((unsigned long long)wk << 32) | (0xFFFFFFFFu - idx), t, thrv, lane);
+            }
+        }
+        if (!found) return;                                     // (cannot happen: wk came from a live lane)
+    }
+}
+
+// A lower bound for the admission threshold before the list has filled up: the group's 32 per-lane maxima are 32
+// distinct elements, so nothing below the 8th largest of them can be among the chunk's top 8.  (Without it the
+// first group alone feeds ~45 of a chunk's ~70 insertions.)  Returns a key k such that only keys > k can qualify.
+template <int kDtype, int G>
+__device__ __forceinline__ uint32_t topk_floor(const uint4 (&x)[G], int lane) {
+    uint32_t m = vec_pair_max<kDtype>(x[0]);
+#pragma unroll
+    for (int u = 1; u < G; ++u) m = hmax2_bits<kDtype>(m, vec_pair_max<kDtype>(x[u]));
+    const uint32_t mine = pair_key<kDtype>(m);
+    int rank = 0;                                               // lanes with a larger maximum (ties: lower lane first)
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+        const uint32_t o = __shfl_sync(SAMD_FULL, mine, l);
+        rank += (o > mine) || (o == mine && l < lane);
+    }
+    const unsigned who = __ballot_sync(SAMD_FULL, rank == TOPK - 1);
+    const uint32_t eighth = __shfl_sync(SAMD_FULL, mine, __ffs(who) - 1);
+    return max(key_ninf<kDtype>(), eighth - 1);                 // equal values may still qualify: strictly below
+}
+
+// Element-wise path (fp32, unaligned rows, ragged row ends): 32 consecutive elements, one per lane.
+template <int kDtype>
+__device__ __forceinline__ void fold_elems_topk(uint32_t ke, uint32_t idx, unsigned long long &t, uint32_t &thrv, int lane) {
+    unsigned todo = __ballot_sync(SAMD_FULL, ke > max(thrv, key_ninf<kDtype>()));
+    while (todo) {                                              // ascending lane = ascending index
+        const int src = __ffs(todo) - 1;
+        const uint32_t k = __shfl_sync(SAMD_FULL, ke, src), i = __shfl_sync(SAMD_FULL, idx, src);
+        topk_insert(((unsigned long long)k << 32) | (0xFFFFFFFFu - i), t, thrv, lane);
+        todo &= todo - 1;
+        todo &= __ballot_sync(SAMD_FULL, ke > thrv);
+    }
+}
+
 __device__ __forceinline__ int ri_at(const VerifyParams &P, int b, int p, int j) {
     if (!P.a.retrieve_dev) return j;                          // sequence: identity path
     return P.a.retrieve_dev[(size_t)b * P.a.retrieve_batch_stride + (size_t)p * P.a.depth + j];
@@ -210,7 +312,7 @@ __device__ __forceinline__ size_t item_offset(const VerifyParams &P, const Item 
 }
 
 // counters[] slots (all re-armed by the kernel itself, so a launch can be captured in a CUDA graph and replayed)
-enum { CN_EPOCH = 0, CN_EXIT, CN_ARRIVE_A, CN_FLAG_A, CN_ARRIVE_B, CN_FLAG_B, CN_ACTIVE, CN_QUEUES = 32 };
+enum { CN_EPOCH = 0, CN_EXIT, CN_ARRIVE_A, CN_FLAG_A, CN_ARRIVE_B, CN_FLAG_B, CN_ACTIVE, CN_ARRIVE_C, CN_FLAG_C, CN_QUEUES = 32 };
 // Work queues: one counter would be hit by every warp for every item, and same-address atomics serialise at about
 // 3 ns each on B200 (measured: 62k items took 135 us whatever their size) - so the dynamic items are dealt round-robin
 // into N_QUEUES queues, each with its own counter on its own 128-byte line.
@@ -218,7 +320,7 @@ enum { CN_EPOCH = 0, CN_EXIT, CN_ARRIVE_A, CN_FLAG_A, CN_ARRIVE_B, CN_FLAG_B, CN
 #define QUEUE_STRIDE 32
 #define CN_WORDS (CN_QUEUES + N_QUEUES * QUEUE_STRIDE)
 
-template <int kDtype>
+template <int kDtype, bool kTopK>
 __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
     extern __shared__ int s_am_all[];                          // [VW][2][n_nodes] node argmax + tree tokens, one slab per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -279,15 +381,24 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
                 const int e0 = cur.e0, len = cur.len;
                 const uint16_t *row = logits + item_offset(P, cur);
                 uint32_t best_key = 0, best_idx = 0;
+                unsigned long long tk = 0;                      // top-k launches: lanes 0..7 hold the sorted list
+                uint32_t thrv = 0, floorv = key_ninf<kDtype>();
                 if constexpr (kDtype == SAMD_DTYPE_FP32) {
                     // fp32 logits (the reference's --dtype float32 runs): coalesced scalar loads, per-lane maxima
                     const uint32_t *row32 = reinterpret_cast<const uint32_t *>(A.logits_dev) + item_offset(P, cur);
+                    if constexpr (kTopK) {
+                        for (int e = 0; e < len; e += 32) {
+                            const uint32_t ke = e + lane < len ? orderable32(__ldg(row32 + e + lane)) : 0u;
+                            fold_elems_topk<kDtype>(ke, (uint32_t)(e0 + e + lane), tk, thrv, lane);
+                        }
+                    } else {
 #pragma unroll 4
-                    for (int e = lane; e < len; e += 32) {
-                        const uint32_t ke = orderable32(__ldg(row32 + e));
-                        if (ke > best_key) {
-                            best_key = ke;
-                            best_idx = (uint32_t)(e0 + e);
+                        for (int e = lane; e < len; e += 32) {
+                            const uint32_t ke = orderable32(__ldg(row32 + e));
+                            if (ke > best_key) {
+                                best_key = ke;
+                                best_idx = (uint32_t)(e0 + e);
+                            }
                         }
                     }
                 } else if (P.vec_ok) {
@@ -298,38 +409,64 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
                     // while this one is folded (xa was requested before this item began).
                     const uint4 *v4 = reinterpret_cast<const uint4 *>(row);
                     const int nvec = len >> 3;
+                    if constexpr (kTopK) {
+                        if (nvec >= 32 * G) floorv = topk_floor<kDtype, G>(xa, lane);   // a full first group
+                    }
                     for (int v0 = 0; v0 < nvec; v0 += 64 * G) {
                         const int v1 = v0 + 32 * G;
                         if (v1 < nvec) load_group<G>(xb, v4, v1, nvec, lane, ninf);
-                        fold_group<kDtype, G>(xa, v0, nvec, lane, e0, best_key, best_idx);
+                        if constexpr (kTopK) fold_group_topk<kDtype, G>(xa, v0, nvec, lane, e0, tk, thrv, floorv);
+                        else fold_group<kDtype, G>(xa, v0, nvec, lane, e0, best_key, best_idx);
                         if (v1 + 32 * G < nvec) load_group<G>(xa, v4, v1 + 32 * G, nvec, lane, ninf);
                         else fetch_next();                      // last pass: xa is free, start on the next item
-                        if (v1 < nvec) fold_group<kDtype, G>(xb, v1, nvec, lane, e0, best_key, best_idx);
+                        if (v1 < nvec) {
+                            if constexpr (kTopK) fold_group_topk<kDtype, G>(xb, v1, nvec, lane, e0, tk, thrv, floorv);
+                            else fold_group<kDtype, G>(xb, v1, nvec, lane, e0, best_key, best_idx);
+                        }
                     }
                     const int tail = nvec << 3;
                     if (len - tail > 0) {                      // < 8 trailing elements, all later than the vectors
                         const uint32_t ke = lane < len - tail ? orderable16<kDtype>(row[tail + lane]) : 0u;
-                        const uint32_t wk = __reduce_max_sync(SAMD_FULL, ke);
-                        if (wk > best_key) {
-                            best_key = wk;
-                            best_idx = (uint32_t)(e0 + tail + __ffs(__ballot_sync(SAMD_FULL, ke == wk)) - 1);
+                        if constexpr (kTopK) {
+                            fold_elems_topk<kDtype>(ke, (uint32_t)(e0 + tail + lane), tk, thrv, lane);
+                        } else {
+                            const uint32_t wk = __reduce_max_sync(SAMD_FULL, ke);
+                            if (wk > best_key) {
+                                best_key = wk;
+                                best_idx = (uint32_t)(e0 + tail + __ffs(__ballot_sync(SAMD_FULL, ke == wk)) - 1);
+                            }
                         }
                     }
                 } else {
-                    for (int e = lane; e < len; e += 32) {
-                        const uint32_t ke = orderable16<kDtype>(row[e]);
-                        if (ke > best_key) {
-                            best_key = ke;
-                            best_idx = (uint32_t)(e0 + e);
+                    if constexpr (kTopK) {
+                        for (int e = 0; e < len; e += 32) {
+                            const uint32_t ke = e + lane < len ? orderable16<kDtype>(row[e + lane]) : 0u;
+                            fold_elems_topk<kDtype>(ke, (uint32_t)(e0 + e + lane), tk, thrv, lane);
+                        }
+                    } else {
+                        for (int e = lane; e < len; e += 32) {
+                            const uint32_t ke = orderable16<kDtype>(row[e]);
+                            if (ke > best_key) {
+                                best_key = ke;
+                                best_idx = (uint32_t)(e0 + e);
+                            }
                         }
                     }
                 }
-                unsigned long long pk = best_key ? (((unsigned long long)best_key << 32) | (unsigned long long)(0xFFFFFFFFu - best_idx)) : 0ull;
-                if (!vec16) {                                   // per-lane maxima: combine (the vector path is warp-uniform)
+                unsigned long long pk;
+                if constexpr (kTopK) {
+                    if (lane < TOPK) P.topk_part[(size_t)cur.item * TOPK + lane] = tk;
+                    pk = __shfl_sync(SAMD_FULL, tk, 0);         // the argmax is the head of the list ...
+                    if (pk == 0 && len > 0)                     // ... unless the whole chunk is -inf: its first element
+                        pk = ((unsigned long long)key_ninf<kDtype>() << 32) | (0xFFFFFFFFu - (uint32_t)e0);
+                } else {
+                    pk = best_key ? (((unsigned long long)best_key << 32) | (unsigned long long)(0xFFFFFFFFu - best_idx)) : 0ull;
+                    if (!vec16) {                               // per-lane maxima: combine (the vector path is warp-uniform)
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        const unsigned long long other = __shfl_xor_sync(SAMD_FULL, pk, o);
-                        pk = other > pk ? other : pk;
+                        for (int o = 16; o; o >>= 1) {
+                            const unsigned long long other = __shfl_xor_sync(SAMD_FULL, pk, o);
+                            pk = other > pk ? other : pk;
+                        }
                     }
                 }
                 if (lane == 0) {
@@ -337,6 +474,8 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
                     if (C == 1) *reinterpret_cast<volatile unsigned long long *>(kp) = pk;
                     else atomicMax(kp, pk);
                 }
+            } else if constexpr (kTopK) {
+                if (lane < TOPK) P.topk_part[(size_t)cur.item * TOPK + lane] = 0;   // dead row: empty list
             }
             if (!fetched) fetch_next();
         }
@@ -355,6 +494,13 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         }
     }
 
+    if constexpr (kTopK) {                                      // every warp merges rows: the whole CTA waits for A
+        if (threadIdx.x == 0) {
+            while (*reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_A]) != epoch) __nanosleep(100);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     // ------------------------------ phase 1b: path walks (samd/utils.py:127-141) ---------------
     // one warp per request, spread over the SMs (warp 0 of CTA b for the first n_ctas requests); CTAs with neither
     // a walk nor row moves to do leave right after arriving
@@ -481,6 +627,70 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         __syncwarp();
     }
 
+    // ------------------------------ phase 1c: per-row top-8 (token_recycle.py:36-47) ----------
+    // The chunks' lists are merged row by row (rows strided over every warp); the row that comes last in (request,
+    // node) order among those feeding the same token claims that token's table entry (the reference overwrites
+    // cache[token] in zip order), and writes it once every claim is in (barrier C, waited for after the row moves).
+    if constexpr (kTopK) {
+        const int n_rows_total = A.batch * T;
+        for (int row = gwarp; row < n_rows_total; row += n_warps) {
+            const int b = row / T, tt = row - b * T;
+            const bool live = tt < (A.n_nodes_dev ? A.n_nodes_dev[b] : T);
+            unsigned long long tk = 0;
+            uint32_t thrv = 0;
+            if (live) {
+                const unsigned long long *part = P.topk_part + (size_t)row * C * TOPK;
+                for (int c0 = 0; c0 < C * TOPK; c0 += 32) {
+                    unsigned long long c = c0 + lane < C * TOPK ? __ldcg(part + c0 + lane) : 0ull;
+                    while (true) {
+                        unsigned long long m = c;
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) {
+                            const unsigned long long other = __shfl_xor_sync(SAMD_FULL, m, o);
+                            m = other > m ? other : m;
+                        }
+                        if (m == 0 || m <= __shfl_sync(SAMD_FULL, tk, TOPK - 1)) break;
+                        topk_insert(m, tk, thrv, lane);
+                        if (c == m) c = 0;                      // composites are unique (they carry the index)
+                    }
+                }
+                // fewer than 8 elements above -inf: completed with the lowest-index -inf elements
+                int have = __popc(__ballot_sync(SAMD_FULL, lane < TOPK && tk != 0));
+                for (int e = 0; e < A.vocab && have < TOPK; e += 32) {
+                    uint32_t ke = 0;
+                    if (e + lane < A.vocab) {
+                        const size_t off = (size_t)b * A.batch_stride + (size_t)tt * A.row_stride + e + lane;
+                        if constexpr (kDtype == SAMD_DTYPE_FP32) ke = orderable32(reinterpret_cast<const uint32_t *>(A.logits_dev)[off]);
+                        else ke = orderable16<kDtype>(logits[off]);
+                    }
+                    unsigned bal = __ballot_sync(SAMD_FULL, ke == key_ninf<kDtype>());
+                    while (bal && have < TOPK) {
+                        const uint32_t idx = (uint32_t)(e + __ffs(bal) - 1);
+                        if (lane == have) tk = ((unsigned long long)key_ninf<kDtype>() << 32) | (0xFFFFFFFFu - idx);
+                        ++have;
+                        bal &= bal - 1;
+                    }
+                }
+            }
+            if (lane < TOPK && A.out_topk_dev) A.out_topk_dev[(size_t)row * TOPK + lane] = tk ? (int)(0xFFFFFFFFu - (uint32_t)tk) : -1;
+            if (A.recycle_table_dev && live && lane == 0) {
+                const int tok = A.tree_tokens_dev[row];
+                if (tok >= 0 && tok < A.vocab) atomicMax(&A.recycle_owner_dev[tok], row);
+            }
+        }
+        if (A.recycle_table_dev) {                              // barrier C, arrival
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                if (atomicAdd(&P.counters[CN_ARRIVE_C], 1) == n_ctas - 1) {
+                    P.counters[CN_ARRIVE_C] = 0;
+                    __threadfence();
+                    *reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_C]) = epoch;
+                }
+            }
+        }
+    }
+
     // ------------------------------ phase 2: KV row moves ---------------------------------
     // The moved rows of the active requests are flattened into 16-byte units and strided over every lane of the
     // grid.  (Dedicating a quarter of the CTAs to row moves that overlap the logits stream was measured slower,
@@ -547,6 +757,26 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
             }
         }
     }
+    if constexpr (kTopK) {
+        if (A.recycle_table_dev) {                              // barrier C, wait; then the owners write their entries
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                while (*reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_C]) != epoch) __nanosleep(100);
+                __threadfence();
+            }
+            __syncthreads();
+            const int n_rows_total = A.batch * T;
+            for (int row = gwarp; row < n_rows_total; row += n_warps) {
+                const int b = row / T, tt = row - b * T;
+                if (tt >= (A.n_nodes_dev ? A.n_nodes_dev[b] : T)) continue;
+                const int tok = A.tree_tokens_dev[row];
+                if (tok < 0 || tok >= A.vocab || __ldcg(&A.recycle_owner_dev[tok]) != row) continue;
+                if (lane < TOPK) A.recycle_table_dev[(size_t)tok * TOPK + lane] = __ldcg(&A.out_topk_dev[(size_t)row * TOPK + lane]);
+                __syncwarp();
+                if (lane == 0) A.recycle_owner_dev[tok] = -1;   // re-armed for the next launch
+            }
+        }
+    }
     if (dbg && lane == 0) dbg[2] = samd_globaltimer();
     // last CTA out: re-arm the work and active counters and bump the device-side epoch (every CTA read it before it
     // could change)
@@ -568,13 +798,15 @@ extern "C" int samd_verify_create(int max_batch, int max_nodes, samd_verify_t *o
     samd_verify_s *h = new samd_verify_s();
     h->max_batch = max_batch;
     h->max_nodes = max_nodes;
-    h->occ_per_sm[0] = h->occ_per_sm[1] = h->occ_per_sm[2] = 0;
+    for (int &o : h->occ_per_sm) o = 0;
     SAMD_CUDA(cudaGetDevice(&h->device));
     SAMD_CUDA(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, h->device));
     SAMD_CUDA(cudaMalloc(&h->node_key, (size_t)max_batch * max_nodes * sizeof(unsigned long long)));
     SAMD_CUDA(cudaMalloc(&h->active, (size_t)max_batch * KV_REC * sizeof(int)));
     SAMD_CUDA(cudaMalloc(&h->counters, CN_WORDS * sizeof(int)));
     SAMD_CUDA(cudaMalloc(&h->kv_start, (size_t)max_batch * sizeof(int)));
+    h->topk_items = std::max<long long>((long long)max_batch * max_nodes * 16, 32768);
+    SAMD_CUDA(cudaMalloc(&h->topk_part, (size_t)h->topk_items * 8 * sizeof(unsigned long long)));
     SAMD_CUDA(cudaMemset(h->node_key, 0, (size_t)max_batch * max_nodes * sizeof(unsigned long long)));
     SAMD_CUDA(cudaMemset(h->active, 0, (size_t)max_batch * KV_REC * sizeof(int)));
     SAMD_CUDA(cudaMemset(h->counters, 0, CN_WORDS * sizeof(int)));
@@ -590,6 +822,7 @@ extern "C" int samd_verify_destroy(samd_verify_t h) {
     cudaFree(h->active);
     cudaFree(h->counters);
     cudaFree(h->kv_start);
+    cudaFree(h->topk_part);
     delete h;
     return 0;
 }
@@ -629,13 +862,18 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     P.max_nodes = h->max_nodes;
     P.stage_cap = move ? std::min(a->batch, 512) : 0;
     const size_t smem = ((size_t)VW * 2 * a->n_nodes + (size_t)P.stage_cap * (3 + KV_GROUP)) * sizeof(int);
-    auto kern = a->dtype == SAMD_DTYPE_BF16   ? verify_compact_kernel<SAMD_DTYPE_BF16>
-                : a->dtype == SAMD_DTYPE_FP16 ? verify_compact_kernel<SAMD_DTYPE_FP16>
-                                              : verify_compact_kernel<SAMD_DTYPE_FP32>;
-    int per_sm = h->occ_per_sm[a->dtype];
+    const bool topk = a->out_topk_dev != nullptr;
+    SAMD_REQUIRE(!a->recycle_table_dev || (topk && a->recycle_owner_dev),
+                 "samd_verify_compact: a recycle table needs out_topk_dev and recycle_owner_dev");
+    SAMD_REQUIRE(!topk || a->vocab >= TOPK, "samd_verify_compact: top-8 needs a vocabulary of at least 8");
+    P.topk_part = h->topk_part;
+    auto kern = a->dtype == SAMD_DTYPE_BF16   ? (topk ? verify_compact_kernel<SAMD_DTYPE_BF16, true> : verify_compact_kernel<SAMD_DTYPE_BF16, false>)
+                : a->dtype == SAMD_DTYPE_FP16 ? (topk ? verify_compact_kernel<SAMD_DTYPE_FP16, true> : verify_compact_kernel<SAMD_DTYPE_FP16, false>)
+                                              : (topk ? verify_compact_kernel<SAMD_DTYPE_FP32, true> : verify_compact_kernel<SAMD_DTYPE_FP32, false>);
+    int per_sm = h->occ_per_sm[a->dtype + (topk ? 3 : 0)];
     if (per_sm <= 0 || smem > 8192) {                           // cached for the common (small) shared-memory sizes
         SAMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, VT, smem > 8192 ? smem : 8192));
-        if (smem <= 8192) h->occ_per_sm[a->dtype] = per_sm;
+        if (smem <= 8192) h->occ_per_sm[a->dtype + (topk ? 3 : 0)] = per_sm;
     }
     SAMD_REQUIRE(per_sm > 0, "samd_verify_compact: kernel does not fit on an SM");
     // persistent grid: every CTA must be resident (the kernel has grid-wide barriers)
@@ -651,6 +889,7 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     P.chunk = chunk;
     P.chunks_per_row = (a->vocab + chunk - 1) / chunk;
     P.n_items1 = (int)rows * P.chunks_per_row;
+    SAMD_REQUIRE(!topk || P.n_items1 <= h->topk_items, "samd_verify_compact: top-8 scratch too small for this shape");
     P.n_items2 = move ? a->batch * a->n_kv : 0;
     P.vec_ok = ((uintptr_t)a->logits_dev % 16 == 0) && (a->batch_stride % 8 == 0) && (a->row_stride % 8 == 0);
     const long long grid = move ? std::max<long long>(1, (long long)h->n_sms * per_sm)
@@ -728,6 +967,53 @@ extern "C" int samd_kv_compact(void *const *kv_ptrs_dev, int32_t n_kv, int32_t n
         SAMD_CUDA(cudaGetLastError());
     }
     kv_bump_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cache_len_dev, accept_len_dev, batch);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// TokenRecycle.gen_draft (samd/tree_model/token_recycle/token_recycle.py:49-59): one warp per request fills the
+// static tree level by level from the [vocab][8] successor table (a node's token is known once its parent's is).
+// ---------------------------------------------------------------------------------------
+__global__ void recycle_tree_kernel(const int32_t *table, int vocab, const int32_t *parent, const int32_t *rank, int n_nodes,
+                                    const int32_t *start_tok, const int32_t *type, int only_type, int batch, int32_t *out) {
+    extern __shared__ int s_tree[];                            // [warps][n_nodes]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= batch || (type && type[b] != only_type)) return;
+    int *tok = s_tree + warp * n_nodes;
+    for (int i = lane; i < n_nodes; i += 32) tok[i] = i == 0 ? start_tok[b] : -1;    // -1 = not filled yet
+    __syncwarp();
+    // parents precede children, so each sweep settles at least one more level; depth <= n_nodes sweeps, 6 for the
+    // reference's 61-node tree
+    for (bool again = true; again;) {
+        bool pending = false;
+        for (int i = lane; i < n_nodes; i += 32) {
+            if (tok[i] >= 0) continue;
+            const int pt = tok[parent[i]];
+            if (pt < 0) {
+                pending = true;
+                continue;
+            }
+            int v = 0;                                          // no entry for the parent's token: stays 0
+            if (pt < vocab && rank[i] < TOPK && __ldg(table + (size_t)pt * TOPK) >= 0) v = __ldg(table + (size_t)pt * TOPK + rank[i]);
+            tok[i] = v;
+        }
+        __syncwarp();
+        again = __any_sync(SAMD_FULL, pending);
+    }
+    for (int i = lane; i < n_nodes; i += 32) out[(size_t)b * n_nodes + i] = tok[i];
+}
+
+extern "C" int samd_recycle_gen_tree(const int32_t *table_dev, int32_t vocab, const int32_t *parent_dev, const int32_t *rank_dev,
+                                     int32_t n_nodes, const int32_t *start_tok_dev, const int32_t *type_dev, int32_t only_type,
+                                     int32_t batch, int32_t *out_tokens_dev, void *stream) {
+    SAMD_REQUIRE(table_dev && parent_dev && rank_dev && start_tok_dev && out_tokens_dev, "samd_recycle_gen_tree: bad arguments");
+    SAMD_REQUIRE(vocab > 0 && n_nodes > 0 && n_nodes <= 4096 && batch > 0, "samd_recycle_gen_tree: bad shape");
+    const int warps = 4;
+    recycle_tree_kernel<<<(batch + warps - 1) / warps, warps * 32, (size_t)warps * n_nodes * sizeof(int), (cudaStream_t)stream>>>(
+        table_dev, vocab, parent_dev, rank_dev, n_nodes, start_tok_dev, type_dev, only_type, batch, out_tokens_dev);
     samd_count_launch();
     SAMD_CUDA(cudaGetLastError());
     return 0;

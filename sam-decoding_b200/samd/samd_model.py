@@ -112,8 +112,10 @@ class SamdModel(nn.Module):
             self._verifier = E.Verifier(1, 256, self.device)
             self._verifier.bind_kv(self.cache.kv_tensors())
         toks = tree_tokens.to(torch.int32).contiguous()
+        # Token Recycle: the table update (TokenRecycle.update) rides on the verify launch's pass over the logits
+        recycle = getattr(getattr(self.draft, "tree_model", None), "table", None)
         out = self._verifier.verify(tree_logits, toks, None if is_seq else self._retrieve_i32, cache_len=self.cache.cache_len,
-                                    move_kv=not is_seq, out=self._verify_out)
+                                    move_kv=not is_seq, out=self._verify_out, recycle=recycle)
         self._verify_out = out
         # next step's sample_p = logits row of the last accepted node (samd/utils.py:141)
         acc_idx = (out["accept_len"] - 1).to(torch.long)
@@ -122,7 +124,7 @@ class SamdModel(nn.Module):
         packed = torch.cat([out["accept_len"], out["tokens"][0]]).tolist()        # the step's one D2H copy
         k = packed[0]
         new_tokens = packed[1:1 + k]
-        self._draft_update(out["tokens"][0, :k], tree_tokens.squeeze(0), tree_logits.squeeze(0))
+        self._draft_update(out["tokens"][0, :k], tree_tokens.squeeze(0), None if recycle is not None else tree_logits.squeeze(0))
         self.cache.cache_length += k
         return sample_p, new_tokens
 

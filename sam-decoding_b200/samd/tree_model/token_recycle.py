@@ -1,7 +1,7 @@
 """Token-Recycle fallback drafter (reference: samd/tree_model/token_recycle/token_recycle.py:18-63,
 utils.py:37-99): remembers, per token, the top-8 successors the LM last predicted after it and fills
-a static 61-node tree from that table.  Host-side table like the reference; its top-k update fused
-into the verification pass is listed as a next step in DESIGN.md."""
+a static 61-node tree from that table.  The table is a device array; its update is fused into the
+verification pass (samd_verify_compact, out_topk_dev / recycle_table_dev)."""
 from typing import Dict, List
 
 import torch
@@ -46,13 +46,22 @@ def gen_buffers(tree: List[List[int]], device) -> Dict[str, torch.Tensor]:
 
 
 class TokenRecycle(TreeModel):
+    """Same surface as the reference class; the token -> top-8 table lives on the device (engine.RecycleTable).
+    `update` is one launch over the [T, V] logits (or nothing at all when SamdModel already updated the table inside
+    its verify launch), `gen_draft` one small launch + one copy of the 61 tree tokens."""
+
     def __init__(self, config: SamdConfig, lm=None, dtype: torch.dtype = None, device: str = "cuda") -> None:
         super().__init__()
+        from samd_b200 import engine as E
         self.samd_config = config
         self.dtype = dtype
         self.device = device
         self.tree = config.tree
-        self.cache: Dict[int, List[int]] = {}
+        self.table = E.RecycleTable(self.tree)
+
+    @property
+    def cache(self) -> Dict[int, List[int]]:
+        return self.table.as_dict()
 
     def reset(self):
         pass                                   # the table survives across requests, as in the reference
@@ -60,19 +69,13 @@ class TokenRecycle(TreeModel):
     def update(self, tree_tokens: torch.Tensor = None, tree_logits: torch.Tensor = None, **kwargs):
         if tree_tokens is None or tree_logits is None:
             return
-        topk = tree_logits.topk(k=TOPK).indices.tolist()
-        for token, best in zip(tree_tokens.tolist(), topk):
-            self.cache[token] = best
+        self.table.update(tree_tokens.reshape(-1), tree_logits.reshape(-1, tree_logits.shape[-1]))
 
     def gen_draft(self, start_token: int):
-        tokens = [start_token] + [0] * (len(self.tree) - 1)
-        for node, childs in enumerate(self.tree):
-            best = self.cache.get(tokens[node])
-            if best is None:
-                continue
-            for k, child in enumerate(childs):
-                tokens[child] = best[k]
-        return tokens, {}
+        if self.table.table is None:           # nothing learnt yet: the reference's empty-cache tree
+            return [int(start_token)] + [0] * (len(self.tree) - 1), {}
+        start = torch.tensor([int(start_token)], dtype=torch.int32, device=self.table.device)
+        return self.table.gen_tree(start)[0].tolist(), {}
 
     def gen_buffers(self) -> Dict[str, torch.Tensor]:
         return gen_buffers(self.samd_config.tree, self.device)

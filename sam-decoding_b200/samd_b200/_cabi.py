@@ -47,6 +47,7 @@ class VerifyArgs(C.Structure):
         ("kv_batch_stride", C.c_int64), ("kv_head_stride", C.c_int64), ("kv_pos_stride", C.c_int64),
         ("move_kv", C.c_int32), ("cache_len_dev", vp), ("out_best_dev", vp), ("out_accept_len_dev", vp),
         ("out_next_token_dev", vp), ("out_tokens_dev", vp), ("out_indices_dev", vp), ("out_node_argmax_dev", vp),
+        ("out_topk_dev", vp), ("recycle_table_dev", vp), ("recycle_owner_dev", vp),
     ]
 
 
@@ -95,6 +96,7 @@ SYMBOLS = {
     "samd_verify_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
     "samd_verify_destroy": (C.c_int, [vp]),
     "samd_verify_compact": (C.c_int, [vp, C.POINTER(VerifyArgs), vp]),
+    "samd_recycle_gen_tree": (C.c_int, [vp, C.c_int32, vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "samd_verify_set_chunk": (None, [C.c_int]),
     "samd_verify_set_debug_times": (None, [C.c_void_p]),
 }
@@ -119,7 +121,7 @@ def lib():
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
-        if _lib.samd_abi_version() != 1:
+        if _lib.samd_abi_version() != 2:
             raise SamdError("libsamd_b200.so ABI version mismatch")
     return _lib
 

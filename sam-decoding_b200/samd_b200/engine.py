@@ -352,11 +352,19 @@ class Verifier:
 
     def verify(self, logits: torch.Tensor, tree_tokens: torch.Tensor, retrieve: Optional[torch.Tensor],
                cache_len: Optional[torch.Tensor] = None, move_kv: bool = True, n_nodes: Optional[torch.Tensor] = None,
-               n_paths: Optional[torch.Tensor] = None, out: Optional[dict] = None, want_argmax: bool = False) -> dict:
+               n_paths: Optional[torch.Tensor] = None, out: Optional[dict] = None, want_argmax: bool = False,
+               want_topk: bool = False, recycle: Optional["RecycleTable"] = None) -> dict:
+        """`want_topk`: also return out["topk"] [B, T, 8], the 8 largest logits of every row as indices (value
+        descending, index ascending).  `recycle`: additionally update that Token-Recycle table in the same launch
+        (TokenRecycle.update, token_recycle.py:39-47)."""
+        want_topk = want_topk or recycle is not None
+        if recycle is not None:
+            recycle.ensure(logits.shape[-1], logits.device)
         # fast path: identical buffers as the previous call -> relaunch with the argument block as it is
         key = (logits.data_ptr(), logits.shape, logits.stride(), logits.dtype, tree_tokens.data_ptr(),
                None if retrieve is None else (retrieve.data_ptr(), retrieve.shape), K.ptr(cache_len), bool(move_kv),
-               K.ptr(n_nodes), K.ptr(n_paths), None if out is None else out["tokens"].data_ptr(), want_argmax, self._kv_key)
+               K.ptr(n_nodes), K.ptr(n_paths), None if out is None else out["tokens"].data_ptr(), want_argmax, self._kv_key,
+               want_topk, None if recycle is None else recycle.table.data_ptr())
         if key == getattr(self, "_last_key", None) and out is self._last_out:
             with torch.cuda.device(self.device):
                 K.check(K.lib().samd_verify_compact(self._h, C.byref(self._args), K.stream_ptr()), "samd_verify_compact")
@@ -404,6 +412,13 @@ class Verifier:
             out["best"].data_ptr(), out["accept_len"].data_ptr(), out["next_token"].data_ptr()
         a.out_tokens_dev, a.out_indices_dev = out["tokens"].data_ptr(), out["indices"].data_ptr()
         a.out_node_argmax_dev = out["node_argmax"].data_ptr() if want_argmax else None
+        if want_topk and ("topk" not in out or out["topk"].shape[:2] != (B, T)):
+            out["topk"] = torch.empty(B, T, 8, dtype=torch.int32, device=logits.device)
+        a.out_topk_dev = out["topk"].data_ptr() if want_topk else None
+        if recycle is not None:
+            a.recycle_table_dev, a.recycle_owner_dev = recycle.table.data_ptr(), recycle.owner.data_ptr()
+        else:
+            a.recycle_table_dev, a.recycle_owner_dev = None, None
         with torch.cuda.device(self.device):
             K.check(K.lib().samd_verify_compact(self._h, C.byref(a), K.stream_ptr()), "samd_verify_compact")
         # remember the argument block for the fast path (keyed on the caller-provided `out`, if any)
@@ -421,6 +436,76 @@ class Verifier:
             self.close()
         except Exception:
             pass
+
+
+class RecycleTable:
+    """Token-Recycle successor table on the device (samd/tree_model/token_recycle/token_recycle.py:18-63):
+    table[token] = the 8 most likely next tokens the LM last predicted after `token` (-1 row = no entry), plus the
+    static draft tree it fills.  Updated inside the verify launch (Verifier.verify(recycle=...)) or from any
+    [N, V] logits block (update()); gen_tree() is TokenRecycle.gen_draft for a batch."""
+
+    def __init__(self, tree: List[List[int]], vocab: Optional[int] = None, device: Optional[torch.device] = None):
+        n = len(tree)
+        parent, rank = [0] * n, [0] * n
+        for node, childs in enumerate(tree):
+            for j, c in enumerate(childs):
+                if not node < c < n:
+                    raise K.SamdError("RecycleTable: children must be numbered after their parent")
+                parent[c], rank[c] = node, j
+        self.tree, self.n_nodes = tree, n
+        self._parent_host, self._rank_host = parent, rank
+        self.table = self.owner = None
+        self.vocab = 0
+        self._ver = None
+        if vocab is not None:
+            self.ensure(vocab, device)
+
+    def ensure(self, vocab: int, device=None):
+        if self.table is not None:
+            if vocab != self.vocab:
+                raise K.SamdError(f"RecycleTable: vocabulary changed from {self.vocab} to {vocab}")
+            return
+        K.require_device()
+        self.device = torch.device(device if device is not None else "cuda")
+        self.vocab = int(vocab)
+        self.table = torch.full((self.vocab, 8), -1, dtype=torch.int32, device=self.device)
+        self.owner = torch.full((self.vocab,), -1, dtype=torch.int32, device=self.device)
+        self.parent = torch.tensor(self._parent_host, dtype=torch.int32, device=self.device)
+        self.rank = torch.tensor(self._rank_host, dtype=torch.int32, device=self.device)
+
+    def update(self, tokens: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:
+        """table[tokens[i]] = top-8 of logits[i] for i in order (last occurrence of a token wins); [N] and [N, V].
+        One launch: every row is a one-node request of the verify kernel.  Returns the [N, 8] top-8 indices."""
+        assert logits.dim() == 2 and tokens.numel() == logits.shape[0]
+        N, V = logits.shape
+        self.ensure(V, logits.device)
+        if self._ver is None or self._ver_cap < N:
+            self._ver_cap = max(N, 256)
+            self._ver = Verifier(self._ver_cap, 1, self.device)
+        out = self._ver.verify(logits.view(N, 1, V), _i32(tokens.to(torch.int32).contiguous().view(N, 1)), None, recycle=self)
+        return out["topk"].view(N, 8)
+
+    def gen_tree(self, start_tok: torch.Tensor, types: Optional[torch.Tensor] = None, only_type: int = 0,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[B, n_nodes] tree tokens: node 0 = start_tok[b], node c = table[token(parent(c))][rank(c)] or 0."""
+        if self.table is None:
+            raise K.SamdError("RecycleTable.gen_tree before the vocabulary is known (ensure(vocab) or an update first)")
+        B = start_tok.numel()
+        if out is None:
+            out = torch.zeros(B, self.n_nodes, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_recycle_gen_tree(self.table.data_ptr(), self.vocab, self.parent.data_ptr(), self.rank.data_ptr(),
+                                                  self.n_nodes, _i32(start_tok).data_ptr(), K.ptr(types), int(only_type), B,
+                                                  out.data_ptr(), K.stream_ptr()), "samd_recycle_gen_tree")
+        return out
+
+    def as_dict(self) -> dict:
+        """The reference's `cache` view: {token: [8 successors]} for every token with an entry."""
+        if self.table is None:
+            return {}
+        t = self.table.cpu()
+        have = (t[:, 0] >= 0).nonzero().flatten().tolist()
+        return {k: t[k].tolist() for k in have}
 
 
 def launch_count() -> int:

@@ -632,3 +632,87 @@ def test_step_host_matches_device_step(zero_copy):
         gd, wd = got[6 * B:].reshape(B, -1), want[6 * B:].reshape(B, -1)
         for r in range(B):
             assert np.array_equal(gd[r, :dl[r]], wd[r, :dl[r]]), (s, r)
+
+
+# --------------------------------------------------------------------------------------
+def test_token_recycle_golden():
+    """TokenRecycle.update fused into the verify launch + gen_draft, against the reference's own class
+    (tests/golden/recycle.npz: tie-free rows, tokens repeating inside and across steps, starts without an entry)."""
+    E, K = _engine_mod()
+    z = load("recycle.npz")
+    tree = unragged(z["tree_flat"], z["tree_offs"])
+    steps, T, V = z["logits_bits"].shape
+    table = E.RecycleTable(tree)
+    ver = E.Verifier(1, T)
+    from samd_b200 import synth
+    ri = _dev_i32(synth.tree_retrieve_indices(tree))
+    for s in range(steps):
+        lg = torch.from_numpy(z["logits_bits"][s].view(np.int16)).view(torch.bfloat16).cuda().view(1, T, V)
+        out = ver.verify(lg, _dev_i32(z["tokens"][s][None]), ri, recycle=table, want_argmax=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(out["topk"][0].cpu().numpy(), z["topk"][s])
+        assert np.array_equal(out["node_argmax"][0].cpu().numpy(), z["topk"][s][:, 0])
+        got = table.gen_tree(_dev_i32(z["starts"][s])).cpu().numpy()
+        assert np.array_equal(got, z["drafts"][s])
+    d = table.as_dict()
+    assert sorted(d) == z["cache_keys"].tolist()
+    assert [d[k] for k in sorted(d)] == z["cache_vals"].tolist()
+    # the stand-alone entry (rows as one-node requests) builds the same table from the same rows
+    t2 = E.RecycleTable(tree)
+    for s in range(steps):
+        lg = torch.from_numpy(z["logits_bits"][s].view(np.int16)).view(torch.bfloat16).cuda()
+        topk = t2.update(_dev_i32(z["tokens"][s]), lg)
+        assert np.array_equal(topk.cpu().numpy(), z["topk"][s])
+    assert t2.as_dict() == d
+
+
+@pytest.mark.parametrize("B,T,V,dt", [(2, 5, 16, "bf16"), (3, 7, 1001, "fp16"), (4, 9, 32001, "bf16"), (64, 3, 4099, "bf16"),
+                                      (5, 6, 2500, "fp32"), (1, 61, 151936, "bf16"), (300, 2, 64, "fp16")])
+def test_verify_topk_random(B, T, V, dt):
+    """Top-8 per row with heavy ties, NaNs, -inf floods and ragged trees, every load path (vector / scalar, chunked
+    rows): indices must equal the oracle's (value descending, index ascending) refinement, the selected values must
+    equal torch.topk's, and the recycle table must equal the reference's zip-order overwrite."""
+    E, K = _engine_mod()
+    rng = np.random.default_rng(V + B)
+    tdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[dt]
+    for padded in (True, False):
+        Vp = (V + 7) // 8 * 8 if padded else V
+        # coarse values: about 40 distinct levels -> ties everywhere, also inside the top 8
+        store = (torch.randint(-20, 20, (B, T, Vp), device="cuda").float() * 0.5).to(tdt)
+        logits = store[:, :, :V]
+        # -inf floods (fewer than 8 finite values in some rows), NaNs, +inf
+        for _ in range(max(1, B * T // 3)):
+            b, t = int(rng.integers(B)), int(rng.integers(T))
+            kind = int(rng.integers(4))
+            if kind == 0:
+                logits[b, t, :] = float("-inf")
+                keep = rng.choice(V, size=int(rng.integers(0, 7)), replace=False)
+                logits[b, t, torch.as_tensor(keep, device="cuda", dtype=torch.long)] = 1.5
+            elif kind == 1:
+                logits[b, t, torch.as_tensor(rng.choice(V, size=3, replace=False), device="cuda")] = float("nan")
+            elif kind == 2:
+                logits[b, t, int(rng.integers(V))] = float("inf")
+        n_nodes = rng.integers(1, T + 1, size=B).astype(np.int32)
+        tokens = rng.integers(0, min(V, 40), size=(B, T)).astype(np.int32)       # repeats inside and across requests
+        table = E.RecycleTable([[]], V)
+        ver = E.Verifier(B, T)
+        want = O.row_topk(logits, 8)
+        for rep in range(2):
+            out = ver.verify(logits, _dev_i32(tokens), None, n_nodes=_dev_i32(n_nodes), recycle=table)
+            torch.cuda.synchronize()
+            got = out["topk"].cpu().numpy()
+            for b in range(B):
+                assert np.array_equal(got[b, :n_nodes[b]], want[b, :n_nodes[b]]), (padded, b)
+                assert (got[b, n_nodes[b]:] == -1).all()
+        lf = logits.float()
+        for b in range(min(B, 8)):
+            nn = int(n_nodes[b])
+            vals = torch.gather(lf[b, :nn], 1, torch.as_tensor(got[b, :nn], device="cuda", dtype=torch.long))
+            ref = lf[b, :nn].topk(8).values
+            assert torch.equal(torch.nan_to_num(vals, nan=1e30), torch.nan_to_num(ref, nan=1e30))
+        cache = {}
+        for b in range(B):
+            O.recycle_update(cache, tokens[b, :n_nodes[b]], want[b, :n_nodes[b]])
+        assert table.as_dict() == cache
+        assert (table.owner == -1).all()
+        ver.close()

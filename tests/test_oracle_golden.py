@@ -240,3 +240,32 @@ def test_c_oracle_static_and_selection_match_reference():
             if kind != 2:
                 assert seq == z["samd_seq"][k].tolist()
             k += 1
+
+
+def test_token_recycle_oracle_matches_reference():
+    """row_topk / recycle_update / recycle_gen_draft against the reference's TokenRecycle (tie-free rows)."""
+    z = load("recycle.npz")
+    tree = unragged(z["tree_flat"], z["tree_offs"])
+    cache = {}
+    for s in range(z["tokens"].shape[0]):
+        logits = torch.from_numpy(z["logits_bits"][s].view(np.int16)).view(torch.bfloat16)
+        topk = O.row_topk(logits)
+        assert np.array_equal(topk, z["topk"][s])
+        assert np.array_equal(topk[:, 0], O.row_argmax(logits))
+        O.recycle_update(cache, z["tokens"][s], topk)
+        for q, st in enumerate(z["starts"][s]):
+            assert O.recycle_gen_draft(cache, tree, int(st)) == z["drafts"][s, q].tolist()
+    assert sorted(cache) == z["cache_keys"].tolist()
+    assert [cache[k] for k in sorted(cache)] == z["cache_vals"].tolist()
+
+
+def test_row_topk_refinement_on_ties():
+    """Equal values: lowest indices first; NaN above +inf; the selected VALUES equal torch.topk's."""
+    x = torch.tensor([[1.0, 5.0, 5.0, float("nan"), 5.0, -0.0, 0.0, float("inf"), 2.0, 5.0, 1.0, 1.0]])
+    got = O.row_topk(x, 8)[0].tolist()
+    assert got == [3, 7, 1, 2, 4, 9, 8, 0]
+    rng = np.random.default_rng(5)
+    y = torch.from_numpy(rng.integers(0, 12, size=(50, 40)).astype(np.float32))
+    idx = O.row_topk(y, 8)
+    vals = np.take_along_axis(y.numpy(), idx, axis=1)
+    assert np.array_equal(vals, y.topk(8).values.numpy())
