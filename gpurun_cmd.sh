@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:.*bool\)1.*' --launch-skip 6 -c 1 -f -o gpurun_out/prof_verify_topk python bench.py --only-verify --kv-len 256 > gpurun_out/ncu_vt.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_vt.log
+python -m pytest tests/test_gpu_dropin.py -m gpu -x -q 2>&1 | tail -30

@@ -10,10 +10,14 @@ requests in lockstep, with everything that the reference does on the host kept o
            one tiny device->host read (all-finished flag) per step
 
 Drafts are sequences of `n_predicts` tokens (the samd flavour's sequence type).  A request whose suffix match is
-below `len_threshold` - where the reference would fall back to its tree model - simply verifies its start token
-(draft = [start, pad...]); greedy verification makes any draft lossless, so the output stream equals plain
-greedy decoding token for token.  KV rows are written at per-request offsets, so no compaction is needed for
-sequence drafts (cache.py:123-126,133).
+below `len_threshold` - where the reference falls back to its tree model - either simply verifies its start token
+(draft = [start, pad...], the default) or, with `tree=<children lists>`, drafts the reference's Token-Recycle tree
+(samd/tree_model/token_recycle/token_recycle.py) from a device-side successor table that the verify launch itself
+keeps up to date.  In that mode every request carries T = max(n_predicts, len(tree)) nodes: a sequence request is
+a chain (one path), a tree request uses the tree's ancestor mask and path table; node counts, path counts, masks,
+positions and path tables are selected per request on the device, and samd_verify_compact moves the accepted
+rows into place (cache.py:118-133).  Greedy verification makes any draft lossless, so the output stream equals
+plain greedy decoding token for token.
 """
 from __future__ import annotations
 
@@ -87,15 +91,53 @@ class RaggedKVCache(Cache):
 class BatchedSamdDecoder:
     def __init__(self, lm, batch: int, max_cache_len: int, n_predicts: int = 16, len_bias: int = 5, len_threshold: int = 5,
                  static: Optional[E.StaticSamDevice] = None, eos_token_id: Optional[int] = None, max_tokens: int = 16384,
-                 dtype=torch.float16, device="cuda"):
+                 dtype=torch.float16, device="cuda", tree: Optional[List[List[int]]] = None):
         self.lm, self.B, self.T = lm, batch, n_predicts
+        self.n_seq = n_predicts
         self.device, self.dtype, self.eos = torch.device(device), dtype, eos_token_id
         self.cache = RaggedKVCache(lm.config, batch, max_cache_len, dtype, self.device)
         self.dyn = E.DynSamBatch(batch, max_tokens, self.device)
         self.eng = E.DraftEngine(self.dyn, static, K.FLAVOUR_SAMD, n_predicts=n_predicts, len_bias=len_bias,
                                  len_threshold=len_threshold)
-        self.ver = E.Verifier(batch, n_predicts, self.device)
-        self._ar = torch.arange(n_predicts, device=self.device)
+        self.tree = tree
+        if tree is not None:
+            self._init_tree(tree)
+        self.ver = E.Verifier(batch, self.T, self.device)
+        self._ar = torch.arange(self.T, device=self.device)
+
+    def _init_tree(self, tree):
+        """Per-type tables, selected per request each step: ancestor masks, depths, path tables."""
+        from . import synth
+        dev, n_tree, n_seq = self.device, len(tree), self.n_seq
+        T = self.T = max(n_seq, n_tree)
+        self.table = E.RecycleTable(tree, self.lm.config.vocab_size, dev)
+        parent = self.table._parent_host
+        depth = [0] * n_tree
+        for i in range(1, n_tree):
+            depth[i] = depth[parent[i]] + 1
+        anc = torch.eye(T, dtype=torch.bool)
+        for i in range(n_tree):
+            j = i
+            while j != 0:
+                j = parent[j]
+                anc[i, j] = True
+        chain = torch.eye(T, dtype=torch.bool)
+        chain[:n_seq, :n_seq] = torch.tril(torch.ones(n_seq, n_seq, dtype=torch.bool))
+        self._allow = torch.stack([chain, anc]).to(dev)                         # [2, T, T] (0 = sequence, 1 = tree)
+        pos = torch.zeros(2, T, dtype=torch.long)
+        pos[0, :n_seq] = torch.arange(n_seq)
+        pos[1, :n_tree] = torch.tensor(depth)
+        self._pos = pos.to(dev)
+        ri = synth.tree_retrieve_indices(tree)                                   # [P, D_tree], -1 padded
+        P, D = ri.shape[0], max(ri.shape[1], n_seq)
+        ret = torch.full((2, P, D), -1, dtype=torch.int32)
+        ret[0, 0, :n_seq] = torch.arange(n_seq, dtype=torch.int32)
+        ret[1, :, :ri.shape[1]] = torch.as_tensor(ri, dtype=torch.int32)
+        self._ret = ret.to(dev)
+        self._n_nodes = torch.tensor([n_seq, n_tree], dtype=torch.int32, device=dev)
+        self._n_paths = torch.tensor([1, P], dtype=torch.int32, device=dev)
+        self._tree_tokens = torch.zeros(self.B, n_tree, dtype=torch.int32, device=dev)
+        self.ver_bound = False
 
     def _mask(self, n_new: int, kv_len: int, base: torch.Tensor) -> torch.Tensor:
         """[B, 1, n_new, kv_len] additive mask: token t of request b sees keys j <= base[b] + t."""
@@ -104,6 +146,39 @@ class BatchedSamdDecoder:
         m = torch.zeros(self.B, n_new, kv_len, dtype=self.dtype, device=self.device)
         m.masked_fill_(j > lim, torch.finfo(self.dtype).min)
         return m[:, None]
+
+    def _tree_step(self, start, kv_len, res):
+        """One decode step with per-request draft shapes: sequence (chain) or Token-Recycle tree."""
+        B, T, dev = self.B, self.T, self.device
+        is_tree = (self.eng.out_type == K.DRAFT_TREE_MODEL)
+        kind = is_tree.long()                                                      # 0 = sequence, 1 = tree
+        self.table.gen_tree(start, types=self.eng.out_type, only_type=K.DRAFT_TREE_MODEL, out=self._tree_tokens)
+        draft = torch.zeros(B, T, dtype=torch.int32, device=dev)
+        draft[:, :self.n_seq] = self.eng.draft
+        draft[:, 0] = start
+        nt = self._tree_tokens.shape[1]
+        draft[:, :nt] = torch.where(is_tree[:, None], self._tree_tokens, draft[:, :nt])
+        if nt < T:
+            draft[:, nt:] = torch.where(is_tree[:, None], torch.zeros_like(draft[:, nt:]), draft[:, nt:])
+        base = self.cache.cache_len
+        pos = base.long()[:, None] + self._pos[kind]
+        # [B, 1, T, kv_len]: the past up to base[b], then the node's ancestors (chain or tree) at base[b] + j
+        j = torch.arange(kv_len, device=dev)[None, None, :]
+        rel = j - base.long()[:, None, None]                                       # [B, 1, kv_len] -> column's node id
+        allow = self._allow[kind]                                                  # [B, T, T]
+        in_new = (rel >= 0) & (rel < T)
+        node_ok = torch.gather(allow, 2, rel.clamp(0, T - 1).expand(B, T, kv_len))
+        ok = (rel < 0) | (in_new & node_ok)
+        mask = torch.zeros(B, T, kv_len, dtype=self.dtype, device=dev)
+        mask.masked_fill_(~ok, torch.finfo(self.dtype).min)
+        logits = self.lm(input_ids=draft.long(), position_ids=pos, past_key_values=self.cache,
+                         attention_mask=mask[:, None]).logits
+        if not self.ver_bound:
+            self.ver.bind_kv([self.cache.kv[i] for i in range(self.cache.kv.shape[0])])
+            self.ver_bound = True
+        return self.ver.verify(logits.contiguous(), draft, self._ret[kind].contiguous(), cache_len=self.cache.cache_len,
+                               move_kv=True, n_nodes=self._n_nodes[kind].contiguous(), n_paths=self._n_paths[kind].contiguous(),
+                               out=res, recycle=self.table)
 
     @torch.inference_mode()
     def generate(self, prompts: Sequence[Sequence[int]], max_new_tokens: int):
@@ -123,6 +198,9 @@ class BatchedSamdDecoder:
                          attention_mask=self._mask(n_max, n_max, torch.zeros(B, dtype=torch.int32, device=dev))).logits
         self.cache.cache_len.copy_(lens)
         self.eng.step(ids.to(torch.int32).contiguous(), lens, None)                # DraftModel.update(prompt), ragged counts
+        if self.tree is not None:                                                  # TokenRecycle.update over the prompt rows
+            valid = torch.arange(n_max, device=dev)[None, :] < lens[:, None]
+            self.table.update(ids[valid].to(torch.int32), logits[valid])
         start = logits[torch.arange(B, device=dev), lens.long() - 1].argmax(-1).to(torch.int32)
         out = torch.zeros(B, max_new_tokens + T, dtype=torch.int32, device=dev)
         out_len = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -133,25 +211,29 @@ class BatchedSamdDecoder:
         # ---- decode ---------------------------------------------------------------------------
         while True:
             self.eng.step(acc_tokens, acc_count, start)                            # update(accepted) + lookup(start): one launch
-            draft = self.eng.draft
-            draft[:, 0] = start                                                    # short matches verify the start token only
             kv_len = int(self.cache.cache_len.max()) + T
             self.cache.begin(T, kv_len)
-            pos = self.cache.cache_len.long()[:, None] + self._ar[None, :]
-            logits = self.lm(input_ids=draft.long(), position_ids=pos, past_key_values=self.cache,
-                             attention_mask=self._mask(T, kv_len, self.cache.cache_len)).logits
             saved_len = self.cache.cache_len.clone()
-            res = self.ver.verify(logits.contiguous(), draft, None, cache_len=self.cache.cache_len, out=res)
+            if self.tree is None:
+                draft = self.eng.draft
+                draft[:, 0] = start                                                # short matches verify the start token only
+                pos = self.cache.cache_len.long()[:, None] + self._ar[None, :]
+                logits = self.lm(input_ids=draft.long(), position_ids=pos, past_key_values=self.cache,
+                                 attention_mask=self._mask(T, kv_len, self.cache.cache_len)).logits
+                res = self.ver.verify(logits.contiguous(), draft, None, cache_len=self.cache.cache_len, out=res)
+            else:
+                res = self._tree_step(start, kv_len, res)
             n_acc = torch.where(done, torch.zeros_like(res["accept_len"]), res["accept_len"])
+            ar = self._ar[:res["tokens"].shape[1]]
             if self.eos is not None:                                               # truncate at the first EOS (samd_model.py:257-263)
-                is_eos = (res["tokens"] == self.eos) & (self._ar[None, :] < n_acc[:, None])
+                is_eos = (res["tokens"] == self.eos) & (ar[None, :] < n_acc[:, None])
                 first = torch.where(is_eos.any(1), is_eos.int().argmax(1).int() + 1, n_acc)
                 done = done | is_eos.any(1)
                 n_acc = torch.minimum(n_acc, first)
             room = (max_new_tokens - out_len).clamp(min=0)
             n_emit = torch.minimum(n_acc, room)
-            cols = out_len.long()[:, None] + self._ar[None, :]
-            keep = self._ar[None, :] < n_emit[:, None]
+            cols = out_len.long()[:, None] + ar[None, :]
+            keep = ar[None, :] < n_emit[:, None]
             out.scatter_(1, torch.where(keep, cols, torch.full_like(cols, max_new_tokens + T - 1)),
                          torch.where(keep, res["tokens"], torch.zeros_like(res["tokens"])))
             out_len = out_len + n_emit

@@ -244,3 +244,23 @@ def test_batched_decoder_is_lossless_on_a_tiny_llama():
     for g, w in zip(got2, want):
         cut = w.index(eos) + 1 if eos in w else len(w)
         assert g == w[:cut]
+
+
+def test_batched_decoder_with_token_recycle_tree_is_lossless():
+    """SURVEY section 8f rows 2 + 3 together: requests whose suffix match is short draft the reference's 61-node
+    Token-Recycle tree from the device table the verify launch maintains, the others draft sequences; per-request
+    node counts, masks, positions and path tables; samd_verify_compact moves the accepted rows.  The output must be
+    plain greedy decoding, and the tree must actually get accepted tokens."""
+    from samd_b200 import synth, _cabi as K
+    from samd_b200.batched import BatchedSamdDecoder
+    lm = _tiny_llama(torch.float32)
+    prompts = [synth.copy_mix(n, 96, 500 + i, p_copy=0.5).tolist() for i, n in enumerate((120, 90, 160, 70))]
+    n_new = 48
+    want = [_plain_greedy(lm, torch.as_tensor([p]).cuda(), n_new)[len(p):] for p in prompts]
+    # a high threshold sends most steps to the tree
+    dec = BatchedSamdDecoder(lm, 4, 512, n_predicts=8, len_bias=5, len_threshold=6, dtype=torch.float32,
+                             tree=synth.token_recycle_tree())
+    got, stats = dec.generate(prompts, n_new)
+    assert got == want
+    assert stats["steps"] < n_new
+    assert len(dec.table.as_dict()) > 0
