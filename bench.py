@@ -423,6 +423,12 @@ def run_ours(a):
             out["verify"]["roofline"]["traffic"] = traffic.get("verify_compact_kernel", {}).get("bytes_per_launch")
         except Exception as e:  # side measurement must not kill the headline line
             out["verify"] = {"error": repr(e)}
+        try:                                  # config c5's verification half: Llama-3 vocabulary and KV shape
+            torch.cuda.empty_cache()
+            out["verify_c5"] = bench_verify(a, dev, hbm_peak, vocab=128256, heads=8, kv_len=8192, name="c5", recycle=False)
+        except Exception as e:
+            out["verify_c5"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
         try:
             out["static"] = bench_static(a, dev, n_corpus=a.static_tokens)
         except Exception as e:
@@ -466,13 +472,13 @@ def run_ours(a):
         print(json.dumps(out))
 
 
-def bench_verify(a, dev, hbm_peak, iters=40, warm=5):
+def bench_verify(a, dev, hbm_peak, iters=40, warm=5, vocab=None, heads=32, kv_len=None, name="c4", recycle=True):
     """Config c4: fused verify + KV compaction, Vicuna-7B shape (B=64, T=61, V=32000, bf16;
     KV 64 tensors [64,32,kv_len,128] bf16).  Rotates 4 logits buffers (1 GB > L2) between iterations."""
     import torch
     from samd_b200 import engine as E, synth
-    B, T, V = 64, 61, a.verify_vocab
-    L, H, DH, ML = 32, 32, 128, max(a.kv_len, 256)
+    B, T, V = 64, 61, vocab or a.verify_vocab
+    L, H, DH, ML = 32, heads, 128, max(kv_len or a.kv_len, 256)
     ri_np = synth.tree_retrieve_indices(synth.token_recycle_tree())
     rng = np.random.default_rng(4000)
     tree_tokens = rng.integers(3, V, size=(B, T)).astype(np.int32)
@@ -527,16 +533,18 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5):
     # Token Recycle's top-8 table update riding on the same pass, and what it replaces: a second
     # full read of the logits by torch.topk
     table = E.RecycleTable(synth.token_recycle_tree(), V, dev)
-    t_rec, _ = run(n_graph, True, recycle=table)
+    t_rec = [float("nan")]
+    if recycle:
+        t_rec, _ = run(n_graph, True, recycle=table)
     tk = []
-    for i in range(6):
+    for i in range(6 if recycle else 0):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         logits[i % nbuf].topk(8)
         e1.record()
         tk.append((e0, e1))
     torch.cuda.synchronize()
-    us_torch_topk = float(np.median([x.elapsed_time(y) for x, y in tk][2:])) * 1e3
+    us_torch_topk = float(np.median([x.elapsed_time(y) for x, y in tk][2:])) * 1e3 if recycle else float("nan")
     cache_len.copy_(cache0)
     res = ver.verify(logits[0], d_tok, d_ri, cache_len=cache_len, move_kv=True, out=res)
     torch.cuda.synchronize()
@@ -564,7 +572,7 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5):
     us_full, us_nokv = float(np.median(t_full)) * 1e3, float(np.median(t_nokv)) * 1e3
     gbs_full = (logit_bytes + kv_bytes_moved) / (us_full * 1e-6) / 1e9
     gbs_nokv = logit_bytes / (us_nokv * 1e-6) / 1e9
-    return {"workload": f"c4: fused tree verification + KV compaction, B={B} T={T} V={V} bf16, 30x6 path table, "
+    return {"workload": f"{name}: fused tree verification + KV compaction, B={B} T={T} V={V} bf16, 30x6 path table, "
                         f"KV {2 * L}x[{B},{H},{ML},{DH}] bf16; 4 rotating logits buffers (1 GB > L2)",
             "us_per_step": us_full, "us_per_step_p10": float(np.percentile(t_full, 10)) * 1e3,
             "us_per_step_p90": float(np.percentile(t_full, 90)) * 1e3, "us_per_step_verify_only": us_nokv,

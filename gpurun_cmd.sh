@@ -1,2 +1,4 @@
-mkdir -p gpurun_out
-python -m pytest tests/test_gpu_dropin.py -m gpu -x -q 2>&1 | tail -30
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "recycle or topk or verify or kv" 2>&1 | tail -5
+python tools/verify_timeline.py 2>&1 | tail -5
+python tools/verify_timeline.py kv 2>&1 | tail -5
+python tools/verify_modes.py 2>&1 | tail -4
