@@ -219,7 +219,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": workload_config(a, n_sample),
+        "config": workload_config(a, a.requests),   # the GPU arm's config; the bounded sample is described in cpu_baseline
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": used, "kind": "port",
                          "sample": f"{n_sample} requests x {steps} steps of the c2 workload (prefill untimed), "
                                    f"oracle/samd_oracle.py Python port of samd DynSAM + DraftModel.lookup, one process per core"},
@@ -790,10 +790,17 @@ def bench_sharded_static(a, dev, rank, world, tokens_per_shard=2_000_000, n_q=40
 
 def main():
     a = parse()
+    # stdout carries exactly one JSON line: file descriptor 1 is re-pointed at stderr, so whatever a native library
+    # prints there (NCCL's version banner, ...) cannot get in front of it, and Python's own stdout keeps the real one
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
