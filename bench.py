@@ -609,6 +609,11 @@ def bench_c2_concurrent(a, dev, workload, n_streams=4):
                 eng.step(d_tokens[s], d_counts[s], d_start[s])
         engines.append(eng)
     torch.cuda.synchronize()
+    snaps = []
+    for eng in engines:
+        snap = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
+        snap.copy_from(eng.dyn)
+        snaps.append(snap)
     for eng, cs in zip(engines, cuda_streams):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=cs):
@@ -626,8 +631,34 @@ def bench_c2_concurrent(a, dev, workload, n_streams=4):
             ev.record()
     torch.cuda.synchronize()
     ms = max(e0.elapsed_time(ev) for ev in ends)
+    # the same through the host-buffer entry: per step every batch stages its inputs in its pinned buffer and calls
+    # step_host(sync=False) on its own stream; the streams are synchronised before the buffers are reused
+    for eng, snap in zip(engines, snaps):
+        eng.dyn.copy_from(snap)
+    del graphs, snaps
+    torch.cuda.synchronize()
+    h_in = torch.empty(W + S, R * 10, dtype=torch.int32).pin_memory()
+    h_in[:, :R] = torch.as_tensor(counts)
+    h_in[:, R:2 * R] = torch.as_tensor(start)
+    h_in[:, 2 * R:] = torch.as_tensor(tokens).reshape(W + S, R * 8)
+    bufs = [eng.host_buffers(8) for eng in engines]
+    for (inp, res), eng, cs in zip(bufs, engines, cuda_streams):          # capture the host graphs (zero counts: no appends)
+        with torch.cuda.stream(cs):
+            eng.step_host(inp, res)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(W, W + S):
+        for (inp, res), eng, cs in zip(bufs, engines, cuda_streams):
+            inp.copy_(h_in[s])
+            with torch.cuda.stream(cs):
+                eng.step_host(inp, res, sync=False)
+        for cs in cuda_streams:
+            cs.synchronize()
+    host_s = time.perf_counter() - t0
     return {"workload": f"{n_streams} independent c2 batches ({R} requests each) in flight on {n_streams} streams",
-            "queries_per_s": n_streams * R * S / (ms * 1e-3), "us_per_step_per_batch": ms / S * 1e3, "n_streams": n_streams}
+            "queries_per_s": n_streams * R * S / (ms * 1e-3), "us_per_step_per_batch": ms / S * 1e3, "n_streams": n_streams,
+            "e2e_queries_per_s": n_streams * R * S / host_s, "e2e_us_per_step": host_s / S * 1e6,
+            "e2e_note": "host buffers in and out every step for every batch (step_host, zero-copy), one host thread"}
 
 
 def bench_c1(a, dev, prompt=4096, steps=256):
