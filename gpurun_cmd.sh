@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --no-cpu > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "rc=$?"; tail -c 300 gpurun_out/bench_full.err
-python -c "
-import json;d=json.load(open('gpurun_out/bench_full.json'));print(d['value'],d['e2e']);print(d['c2_concurrent'])"
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "recycle or topk or verify" 2>&1 | tail -5
+python bench.py --only-verify --no-cpu 2>/dev/null | tail -1 | python -c "
+import json,sys
+v=json.loads(sys.stdin.read())['verify']; print({k:(round(x,1) if isinstance(x,float) else x) for k,x in v.items() if k.startswith('us_')}, v['token_recycle'])"

@@ -202,48 +202,70 @@ __device__ __forceinline__ void topk_insert(unsigned long long c, unsigned long 
     thrv = (uint32_t)(__shfl_sync(SAMD_FULL, t, TOPK - 1) >> 32);
 }
 
-__device__ __forceinline__ void clear_half(uint4 &x, int e, uint32_t ninf16) {
-    uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if ((e >> 1) == i) w[i] = (e & 1) ? ((w[i] & 0x0000FFFFu) | (ninf16 << 16)) : ((w[i] & 0xFFFF0000u) | ninf16);
-    x = make_uint4(w[0], w[1], w[2], w[3]);
+// raw bits of a value v such that {x > v} contains {key(x) > T} (and nothing that could displace a list entry)
+template <int kDtype>
+__device__ __forceinline__ uint32_t threshold_bits(uint32_t T) {
+    if (T == 0x7FFFu) return 0x8001u;                           // between the negatives and zero: just below -0
+    return (T & 0x8000u) ? (T ^ 0x8000u) : (~T & 0xFFFFu);
 }
 
-// Vector path: every element of the group above the threshold is pulled out, largest first, and inserted.
+// per-half "x > v or unordered" mask of one packed word (0xFFFF per true half)
+template <int kDtype>
+__device__ __forceinline__ uint32_t gtu_mask(uint32_t w, uint32_t v2) {
+    if (kDtype == SAMD_DTYPE_BF16)
+        return __hgtu2_mask(*reinterpret_cast<const __nv_bfloat162 *>(&w), *reinterpret_cast<const __nv_bfloat162 *>(&v2));
+    return __hgtu2_mask(*reinterpret_cast<const __half2 *>(&w), *reinterpret_cast<const __half2 *>(&v2));
+}
+
+// Vector path.  Most groups are rejected by their packed maximum.  In a group that passes, every lane marks its
+// elements above the threshold with packed compares (bit w = low half of its word w, bit 16 + w = high half; the
+// lane's G vectors are words 0 .. 4G-1), then the marked elements are inserted - in any order: the list keeps the
+// 8 largest composites of whatever it is fed.
 template <int kDtype, int G>
-__device__ __forceinline__ void fold_group_topk(uint4 (&x)[G], int v0, int nvec, int lane, int e0, unsigned long long &t,
+__device__ __forceinline__ void fold_group_topk(const uint4 (&x)[G], int v0, int nvec, int lane, int e0, unsigned long long &t,
                                                 uint32_t &thrv, uint32_t floorv) {
-    while (true) {
-        uint32_t m = vec_pair_max<kDtype>(x[0]);
+    static_assert(G == 4, "candidate masks hold 16 words per lane");
+    uint32_t m = vec_pair_max<kDtype>(x[0]);
 #pragma unroll
-        for (int u = 1; u < G; ++u) m = hmax2_bits<kDtype>(m, vec_pair_max<kDtype>(x[u]));
-        const uint32_t wk = __reduce_max_sync(SAMD_FULL, pair_key<kDtype>(m));
-        if (wk <= max(thrv, floorv)) return;                    // warp-uniform
-        bool found = false;
+    for (int u = 1; u < G; ++u) m = hmax2_bits<kDtype>(m, vec_pair_max<kDtype>(x[u]));
+    const uint32_t wk = __reduce_max_sync(SAMD_FULL, pair_key<kDtype>(m));
+    const uint32_t T = max(thrv, floorv);
+    if (wk <= T) return;                                        // warp-uniform
+    const uint32_t v = threshold_bits<kDtype>(T), v2 = v | (v << 16);
+    uint32_t cand = 0;
 #pragma unroll
-        for (int u = 0; u < G; ++u) {
-            if (found) continue;
-            const int vi = v0 + u * 32 + lane;
-            const unsigned bal = __ballot_sync(SAMD_FULL, vi < nvec && pair_key<kDtype>(vec_pair_max<kDtype>(x[u])) == wk);
-            if (bal) {                                         // lowest u, then lowest lane = lowest index
-                found = true;
-                const int src = __ffs(bal) - 1;
-                int e_first = 0;
-                if (lane == src) {
-                    const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
-                    e_first = 7;
+    for (int u = 0; u < G; ++u) {
+        const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+        const bool live = v0 + u * 32 + lane < nvec;           // (padding lanes hold -inf and never pass anyway)
 #pragma unroll
-                    for (int e = 7; e >= 0; --e)
-                        if (orderable16<kDtype>((w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu) == wk) e_first = e;
-                    clear_half(x[u], e_first, kDtype == SAMD_DTYPE_BF16 ? 0xFF80u : 0xFC00u);   // taken
-                }
-                e_first = __shfl_sync(SAMD_FULL, e_first, src);
-                const uint32_t idx = (uint32_t)(e0 + (v0 + u * 32 + src) * 8 + e_first);
-                topk_insert(((unsigned long long)wk << 32) | (0xFFFFFFFFu - idx), t, thrv, lane);
+        for (int i = 0; i < 4; ++i)
+            if (live) cand |= (gtu_mask<kDtype>(w[i], v2) & 0x00010001u) << (u * 4 + i);
+    }
+    while (__any_sync(SAMD_FULL, cand != 0)) {
+        // every lane with marks pops its lowest one and forms its composite
+        unsigned long long c = 0;
+        if (cand) {
+            const int p = __ffs(cand) - 1, wsel = p & 15;
+            cand &= cand - 1;
+            uint32_t word = 0;
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (wsel == u * 4 + i) word = w[i];
             }
+            const uint32_t key = orderable16<kDtype>((p & 16) ? word >> 16 : word & 0xFFFFu);
+            const uint32_t idx = (uint32_t)(e0 + (v0 + (wsel >> 2) * 32 + lane) * 8 + (wsel & 3) * 2 + (p >> 4));
+            c = ((unsigned long long)key << 32) | (0xFFFFFFFFu - idx);
         }
-        if (!found) return;                                     // (cannot happen: wk came from a live lane)
+        unsigned todo = __ballot_sync(SAMD_FULL, c != 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned long long cs = __shfl_sync(SAMD_FULL, c, src);
+            if (cs > __shfl_sync(SAMD_FULL, t, TOPK - 1)) topk_insert(cs, t, thrv, lane);
+        }
     }
 }
 
