@@ -1,5 +1,2 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "recycle or topk or verify" 2>&1 | tail -5
-python bench.py --only-verify --no-cpu 2>/dev/null | tail -1 | python -c "
-import json,sys
-v=json.loads(sys.stdin.read())['verify']; print({k:(round(x,1) if isinstance(x,float) else x) for k,x in v.items() if k.startswith('us_')}, v['token_recycle'])"
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:.*bool\)1.*' --launch-skip 6 -c 1 -f -o gpurun_out/prof_verify_topk2 python bench.py --only-verify --kv-len 256 > gpurun_out/ncu_vt.log 2>&1; echo "rc=$?"
