@@ -1,2 +1,5 @@
-mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum,lts__t_sectors.sum,lts__t_sector_hit_rate.pct,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,dram__bytes_read.sum,l1tex__t_sector_hit_rate.pct --clock-control none -k regex:sam_step_kernel --csv --log-file gpurun_out/lookup_only.csv python tools/lookup_only.py 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --no-cpu > gpurun_out/bench_l2.json 2> gpurun_out/bench_l2.err; echo "rc=$?"; tail -c 200 gpurun_out/bench_l2.err
+python -c "
+import json;d=json.load(open('gpurun_out/bench_l2.json'));print(d['value'],d['ms_per_step'],d['e2e']['value']);print(d['static']['queries_per_s'], d['c2_concurrent']['queries_per_s'], d['c1']['gpu_us_per_step'], d['step_kernel']['prefill_ms'])"
+python tools/step_time_distribution.py 2>&1 | tail -13

@@ -74,6 +74,9 @@ int samd_dyn_grow(samd_dyn_t old_handle, int new_max_tokens, samd_dyn_t *out);
 /* Sums over requests (synchronises): out[8] = {n_states, tokens, n_edges, n_clones, transition
  * probes spent in add_tokens, probes spent in lookups, overflowed requests, 0}. */
 int samd_dyn_stats(samd_dyn_t h, int64_t *out_host);
+/* Every request's 16 meta words {n_states, last, max_length, cur_index, cur_length, n_edges, overflow, n_clones,
+ * suffix-link hops, probes, ...} to the host (synchronises): per-request counters for profiling. */
+int samd_dyn_meta(samd_dyn_t h, int32_t *meta_host);
 /* Copy one request's automaton to the host (synchronises): meta[8] = {n_states, last,
  * max_length, cur_index, cur_length, n_edges, overflow, n_clones}; link/length/min_endpos
  * arrays of n_states entries (pass NULL to skip) and the token history text[0..max_length]. */

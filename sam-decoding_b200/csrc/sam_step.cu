@@ -105,6 +105,13 @@ extern "C" int samd_dyn_stats(samd_dyn_t h, int64_t *out) {
     return 0;
 }
 
+extern "C" int samd_dyn_meta(samd_dyn_t h, int32_t *meta_host) {
+    SAMD_REQUIRE(h && meta_host, "samd_dyn_meta: bad arguments");
+    SAMD_CUDA(cudaDeviceSynchronize());
+    SAMD_CUDA(cudaMemcpy(meta_host, h->a.meta, (size_t)h->a.n_requests * META_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int samd_dyn_reset(samd_dyn_t h, const uint8_t *mask_dev, void *stream) {
     SAMD_REQUIRE(h, "samd_dyn_reset: null handle");
     dyn_reset_kernel<<<h->a.n_requests, 256, 0, (cudaStream_t)stream>>>(h->a, mask_dev);

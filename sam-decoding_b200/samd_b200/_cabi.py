@@ -64,6 +64,7 @@ SYMBOLS = {
     "samd_dyn_copy": (C.c_int, [vp, vp, vp]),
     "samd_dyn_grow": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     "samd_dyn_stats": (C.c_int, [vp, c_i64p]),
+    "samd_dyn_meta": (C.c_int, [vp, c_i32p]),
     "samd_dyn_export": (C.c_int, [vp, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int64]),
     "samd_dyn_export_edges": (C.c_int, [vp, C.c_int, c_i32p, C.c_int64]),
     "samd_dyn_gen_draft": (C.c_int, [vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_double, vp, C.c_int32, vp, vp]),

@@ -10,10 +10,21 @@ eng.step(torch.as_tensor(streams[:, :8192]).to(dev), None, None)
 dt,dc,ds=(torch.as_tensor(x).to(dev) for x in (tokens,counts,start))
 cyc=torch.zeros(1024,dtype=torch.int64,device=dev)
 K.lib().samd_step_set_debug_cycles(cyc.data_ptr())
-allc=[]
+allc=[]; feats=[]
+import ctypes as C
+def meta():
+    m=np.zeros((1024,16),dtype=np.int32)
+    K.check(K.lib().samd_dyn_meta(dyn.handle, m.ctypes.data_as(C.POINTER(C.c_int32))))
+    return m.astype(np.int64)
+m0=meta()
 for s in range(40):
     eng.step(dt[s],dc[s],ds[s]); torch.cuda.synchronize()
-    if s>=8: allc.append((cyc.cpu().numpy().copy(), counts[s].copy()))
+    m1=meta()
+    if s>=8:
+        allc.append((cyc.cpu().numpy().copy(), counts[s].copy()))
+        d=m1-m0
+        feats.append(np.stack([np.ones(1024), counts[s], d[:,7], d[:,5], d[:,8], d[:,9]],1))   # 1, tokens, clones, edges, hops, probes
+    m0=m1
 K.lib().samd_step_set_debug_cycles(None)
 c=np.stack([a for a,_ in allc]).astype(float)/1.9e3   # us at ~1.9GHz
 k=np.stack([b for _,b in allc])
@@ -21,3 +32,10 @@ print("per-step max us: mean %.1f ; per-request mean %.1f p50 %.1f p90 %.1f p99 
 for kk in range(1,9):
     m=c[k==kk]; print("k=%d n=%d mean %.1f p99 %.1f max %.1f" % (kk, m.size, m.mean(), np.percentile(m,99), m.max()))
 print("us per token (k>=1): %.2f" % (c.sum()/k.sum()))
+
+# what a slow request is made of: least-squares fit of per-request time on the step's counters
+X=np.concatenate(feats).astype(float); y=c.reshape(-1)
+coef,*_=np.linalg.lstsq(X,y,rcond=None)
+print("fit us = %.2f + %.2f*tokens + %.2f*clones + %.2f*edges + %.2f*link_hops + %.2f*probes ; residual sd %.2f" % (*coef, (y-X@coef).std()))
+slow=y>np.percentile(y,99.5)
+print("slowest 0.5%%: mean tokens %.1f clones %.1f edges %.1f hops %.1f probes %.1f (all: %.1f %.1f %.1f %.1f %.1f)" % (*X[slow,1:].mean(0), *X[:,1:].mean(0)))
