@@ -716,3 +716,67 @@ def test_verify_topk_random(B, T, V, dt):
         assert table.as_dict() == cache
         assert (table.owner == -1).all()
         ver.close()
+
+
+# --------------------------------------------------------------------------------------
+def test_edge_cases_and_error_behaviour():
+    """Empty appends, a masked reset, an arena that fills up (flagged, never written past its end, and continued
+    exactly after samd_dyn_grow), and the status-code / message behaviour of bad arguments."""
+    E, K = _engine_mod()
+    from samd_b200 import synth
+    B = 6
+    streams = [synth.copy_mix(400, 50, 900 + r) for r in range(B)]
+    oracles = [O.Automaton() for _ in range(B)]
+    dyn = E.DynSamBatch(B, 256)                                               # too small on purpose
+    eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=8, len_bias=5, len_threshold=3)
+    tok = np.stack([s[:200] for s in streams]).astype(np.int32)
+    cnt = np.array([200, 0, 200, 13, 200, 1], dtype=np.int32)                  # ragged, two (nearly) empty
+    eng.step(_dev_i32(tok), _dev_i32(cnt), None)
+    for r in range(B):
+        oracles[r].extend(streams[r][:cnt[r]])
+    st = _dev_i32(np.array([int(s[200]) for s in streams]))
+    eng.step(None, None, st)                                                  # lookup only
+    torch.cuda.synchronize()
+    for r in range(B):
+        typ, seq, info = O.select_samd(oracles[r], None, int(st[r].item()), 8, 5, 3)
+        assert eng.match_dyn[r].item() == info["match_dyn"]
+    # masked reset: requests 0 and 3 start over, the others keep their automata
+    mask = torch.tensor([1, 0, 0, 1, 0, 0], dtype=torch.uint8, device="cuda")
+    dyn.reset(mask)
+    for r in (0, 3):
+        oracles[r] = O.Automaton()
+    # fill request 2 beyond its capacity: the overflow is flagged and nothing else is disturbed
+    more = np.stack([s[200:300] for s in streams]).astype(np.int32)
+    cnt2 = np.array([5, 5, 100, 5, 5, 5], dtype=np.int32)
+    snap = E.DynSamBatch(B, 256)
+    snap.copy_from(dyn)
+    eng.step(_dev_i32(more), _dev_i32(cnt2), None)
+    torch.cuda.synchronize()
+    assert dyn.stats()["overflowed"] >= 1
+    # the caller's recovery: grow the snapshot and replay the step - identical to an arena that was large enough
+    big = snap.grown(1024)
+    eng2 = E.DraftEngine(big, None, K.FLAVOUR_SAMD, n_predicts=8, len_bias=5, len_threshold=3)
+    eng2.step(_dev_i32(more), _dev_i32(cnt2), None)
+    for r in range(B):
+        oracles[r].extend(streams[r][200:200 + cnt2[r]])
+    torch.cuda.synchronize()
+    assert big.stats()["overflowed"] == 0
+    for r in range(B):
+        ex = big.export(r, with_text=False)
+        assert ex["n_states"] == oracles[r].n_states and ex["n_edges"] == oracles[r].n_edges, r
+        assert np.array_equal(ex["link"], np.array(oracles[r].link))
+    # bad arguments: a status code and a message, never a crash
+    ver = E.Verifier(2, 4)
+    lg = torch.zeros(3, 4, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(K.SamdError, match="batch exceeds"):
+        ver.verify(lg, torch.zeros(3, 4, dtype=torch.int32, device="cuda"), None)
+    lg = torch.zeros(2, 5, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(K.SamdError, match="n_nodes exceeds"):
+        ver.verify(lg, torch.zeros(2, 5, dtype=torch.int32, device="cuda"), None)
+    with pytest.raises(K.SamdError, match="dtype"):
+        ver.verify(torch.zeros(2, 4, 64, dtype=torch.float64, device="cuda"), torch.zeros(2, 4, dtype=torch.int32, device="cuda"), None)
+    with pytest.raises(K.SamdError, match="at least 8"):
+        ver.verify(torch.zeros(2, 4, 5, dtype=torch.bfloat16, device="cuda"), torch.zeros(2, 4, dtype=torch.int32, device="cuda"),
+                   None, want_topk=True)
+    with pytest.raises(K.SamdError):
+        E.DynSamBatch(0, 16)
