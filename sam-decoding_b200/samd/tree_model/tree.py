@@ -1,22 +1,26 @@
-from typing import Dict, List, Tuple
-
+"""Contract of the fallback tree drafter DraftModel falls back to when no suffix match is long enough
+(reference: samd/tree_model/tree.py:9-30).  Implementations: token_recycle.TokenRecycle."""
 import torch
 
 
 class TreeModel(torch.nn.Module):
-    """Interface of a fallback tree drafter (reference: samd/tree_model/tree.py:9-30)."""
+    """reset() per conversation, update(...) after every verified step, gen_draft(start) -> (tree tokens, buffer
+    overrides), gen_buffers() -> the static tree's mask / position / path tensors."""
 
-    def __init__(self, samd_config=None, lm_config=None, lm=None, dtype: torch.dtype = None, device: str = None) -> None:
+    def __init__(self, *args, **kwargs) -> None:
         super().__init__()
 
+    def _abstract(self, name):
+        raise NotImplementedError(f"{type(self).__name__}.{name}")
+
     def reset(self):
-        raise NotImplementedError
+        self._abstract("reset")
 
-    def update(self, tokens: List[int], topk_nest: List[List[int]]):
-        raise NotImplementedError
+    def update(self, **kwargs):
+        self._abstract("update")
 
-    def gen_draft(self, start_token: int) -> Tuple[List[int], Dict[str, torch.Tensor]]:
-        raise NotImplementedError
+    def gen_draft(self, start_token: int):
+        self._abstract("gen_draft")
 
     def gen_buffers(self):
-        raise NotImplementedError
+        self._abstract("gen_buffers")
