@@ -780,3 +780,57 @@ def test_edge_cases_and_error_behaviour():
                    None, want_topk=True)
     with pytest.raises(K.SamdError):
         E.DynSamBatch(0, 16)
+
+
+def test_c3_static_and_dynamic_against_c_oracle():
+    """BASELINE config 3's shape at a corpus the host builds in seconds (3 M tokens, ~5 M states): 512 persistent
+    cursors, 6 steps of 1-8 tokens + lookup, the samd selection rule over the dynamic AND the static automaton
+    (len_bias applied to the static match, ties to the dynamic one) - source, match lengths, state indices and
+    16-token drafts against the oracle's C restatement, and the automaton's size against the oracle's."""
+    E, K = _engine_mod()
+    from c_oracle import CSam
+    from samd_b200 import synth
+    vocab, Q, steps = 32000, 512, 6
+    docs = synth.make_corpus(3_000_000, vocab, 3100, singletons=True)
+    st = E.StaticSamDevice.build(docs, synth.EOS, with_counts=False)
+    ost = CSam.build(docs, synth.EOS)
+    assert st.n_states == ost.info()["n_states"] and st.n_edges == ost.info()["n_edges"]
+    q = synth.corpus_queries(docs, Q, 8 * steps + 1, vocab, 3101).astype(np.int32)
+    rng = np.random.default_rng(3102)
+    counts = rng.integers(1, 9, size=(steps, Q)).astype(np.int32)
+    # expected, query by query (the C oracle's static automaton has one cursor)
+    want = {}
+    for r in range(Q):
+        dyn = CSam(8 * steps + 16)
+        ost.reset_cursor()
+        pos = 0
+        for s in range(steps):
+            chunk = q[r, pos:pos + counts[s, r]]
+            dyn.extend(chunk)
+            ost.advance(chunk)
+            pos += counts[s, r]
+            want[(s, r)] = dyn.select_samd(ost, int(q[r, pos]), 16, 2, 4)
+    dynb = E.DynSamBatch(Q, 8 * steps + 16)
+    eng = E.DraftEngine(dynb, st, K.FLAVOUR_SAMD, n_predicts=16, len_bias=2, len_threshold=4)
+    pos = np.zeros(Q, dtype=np.int64)
+    seen = set()
+    for s in range(steps):
+        tok = np.zeros((Q, 8), dtype=np.int32)
+        for r in range(Q):
+            tok[r, :counts[s, r]] = q[r, pos[r]:pos[r] + counts[s, r]]
+        pos += counts[s]
+        start = q[np.arange(Q), pos]
+        eng.step(_dev_i32(tok), _dev_i32(counts[s]), _dev_i32(start))
+        torch.cuda.synchronize()
+        typ, draft = eng.out_type.cpu().numpy(), eng.draft.cpu().numpy()
+        md, ms = eng.match_dyn.cpu().numpy(), eng.match_static.cpu().numpy()
+        idd, ids = eng.index_dyn.cpu().numpy(), eng.index_static.cpu().numpy()
+        for r in range(Q):
+            kind, seq, info = want[(s, r)]
+            assert kind == typ[r], (s, r)
+            assert (info[0], info[1]) == (idd[r], md[r]), (s, r)
+            assert (info[2], info[3]) == (ids[r], ms[r]), (s, r)
+            if kind != 2:
+                assert seq == draft[r].tolist(), (s, r)
+            seen.add(kind)
+    assert {0, 1} <= seen                                      # both automata supplied drafts
