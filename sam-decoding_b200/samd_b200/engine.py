@@ -286,6 +286,8 @@ class DraftEngine:
             if sync:
                 torch.cuda.current_stream(self.dyn.device).synchronize()
             return
+        if not (inp.is_pinned() and out.is_pinned()):
+            raise K.SamdError("step_host needs pinned host buffers (DraftEngine.host_buffers())")
         dev_in, k = self._io
         B = self.dyn.n_requests
         key = (inp.data_ptr(), out.data_ptr(), self.dyn.handle.value, self.flavour, self.n_predicts, self.len_bias,
