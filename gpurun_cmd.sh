@@ -1,2 +1,3 @@
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropin.py -m gpu -x -q -k "verify or kv or recycle or topk or lossless or graph" 2>&1 | tail -4
-python tools/verify_modes.py 2>&1 | tail -3
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropin.py -m gpu -x -q -k "recycle or lossless" 2>&1 | tail -3
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or step_host or graph_replayable or recycle" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/sanitizer_racecheck.log

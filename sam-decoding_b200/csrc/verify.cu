@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <climits>
 
 #define VT 256                 // threads per CTA (8 warps)
 #define VW (VT / 32)
@@ -1004,28 +1005,33 @@ extern "C" int samd_kv_compact(void *const *kv_ptrs_dev, int32_t n_kv, int32_t n
 // ---------------------------------------------------------------------------------------
 __global__ void recycle_tree_kernel(const int32_t *table, int vocab, const int32_t *parent, const int32_t *rank, int n_nodes,
                                     const int32_t *start_tok, const int32_t *type, int only_type, int batch, int32_t *out) {
-    extern __shared__ int s_tree[];                            // [warps][n_nodes]
+    extern __shared__ int s_tree[];                            // [warps][2][n_nodes]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x * (blockDim.x >> 5) + warp;
     if (b >= batch || (type && type[b] != only_type)) return;
-    int *tok = s_tree + warp * n_nodes;
-    for (int i = lane; i < n_nodes; i += 32) tok[i] = i == 0 ? start_tok[b] : -1;    // -1 = not filled yet
+    int *tok = s_tree + warp * 2 * n_nodes, *nxt = tok + n_nodes;
+    constexpr int PENDING = INT_MIN;                            // (any real token id, even an invalid negative one, is final)
+    for (int i = lane; i < n_nodes; i += 32) tok[i] = i == 0 ? max(start_tok[b], PENDING + 1) : PENDING;
     __syncwarp();
     // parents precede children, so each sweep settles at least one more level; depth <= n_nodes sweeps, 6 for the
-    // reference's 61-node tree
+    // reference's 61-node tree.  A sweep reads `tok` and writes `nxt`; the two are merged between sweeps.
     for (bool again = true; again;) {
         bool pending = false;
         for (int i = lane; i < n_nodes; i += 32) {
-            if (tok[i] >= 0) continue;
-            const int pt = tok[parent[i]];
-            if (pt < 0) {
-                pending = true;
-                continue;
+            int v = tok[i];
+            if (v == PENDING) {
+                const int pt = tok[parent[i]];
+                if (pt == PENDING) {
+                    pending = true;
+                } else {
+                    v = 0;                                      // no entry for the parent's token: stays 0
+                    if (pt >= 0 && pt < vocab && rank[i] < TOPK && __ldg(table + (size_t)pt * TOPK) >= 0) v = __ldg(table + (size_t)pt * TOPK + rank[i]);
+                }
             }
-            int v = 0;                                          // no entry for the parent's token: stays 0
-            if (pt < vocab && rank[i] < TOPK && __ldg(table + (size_t)pt * TOPK) >= 0) v = __ldg(table + (size_t)pt * TOPK + rank[i]);
-            tok[i] = v;
+            nxt[i] = v;
         }
+        __syncwarp();
+        for (int i = lane; i < n_nodes; i += 32) tok[i] = nxt[i];
         __syncwarp();
         again = __any_sync(SAMD_FULL, pending);
     }
@@ -1038,7 +1044,7 @@ extern "C" int samd_recycle_gen_tree(const int32_t *table_dev, int32_t vocab, co
     SAMD_REQUIRE(table_dev && parent_dev && rank_dev && start_tok_dev && out_tokens_dev, "samd_recycle_gen_tree: bad arguments");
     SAMD_REQUIRE(vocab > 0 && n_nodes > 0 && n_nodes <= 4096 && batch > 0, "samd_recycle_gen_tree: bad shape");
     const int warps = 4;
-    recycle_tree_kernel<<<(batch + warps - 1) / warps, warps * 32, (size_t)warps * n_nodes * sizeof(int), (cudaStream_t)stream>>>(
+    recycle_tree_kernel<<<(batch + warps - 1) / warps, warps * 32, (size_t)warps * 2 * n_nodes * sizeof(int), (cudaStream_t)stream>>>(
         table_dev, vocab, parent_dev, rank_dev, n_nodes, start_tok_dev, type_dev, only_type, batch, out_tokens_dev);
     samd_count_launch();
     SAMD_CUDA(cudaGetLastError());
