@@ -1,3 +1,4 @@
-mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropin.py -m gpu -x -q -k "recycle or lossless" 2>&1 | tail -3
-timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or step_host or graph_replayable or recycle" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/sanitizer_racecheck.log
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropin.py -m gpu -x -q -k "dyn or c2_full or c3 or step_host or static or select or loop" 2>&1 | tail -3
+python bench.py --no-cpu --no-extras 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read());print(d['value'],d['ms_per_step'],d['e2e']['value'])"
+python tools/step_time_distribution.py 2>&1 | grep "fit us\|per-step max"

@@ -39,3 +39,7 @@ coef,*_=np.linalg.lstsq(X,y,rcond=None)
 print("fit us = %.2f + %.2f*tokens + %.2f*clones + %.2f*edges + %.2f*link_hops + %.2f*probes ; residual sd %.2f" % (*coef, (y-X@coef).std()))
 slow=y>np.percentile(y,99.5)
 print("slowest 0.5%%: mean tokens %.1f clones %.1f edges %.1f hops %.1f probes %.1f (all: %.1f %.1f %.1f %.1f %.1f)" % (*X[slow,1:].mean(0), *X[:,1:].mean(0)))
+order=np.argsort(-y)[:16]
+print("slowest request-steps: time us | fitted | tokens clones edges hops probes")
+for i in order:
+    print("  %5.1f | %5.1f | %d %d %d %d %d" % (y[i], X[i]@coef, *X[i,1:].astype(int)))
