@@ -170,7 +170,8 @@ typedef struct samd_step_args {
 
 int samd_step(const samd_step_args *args, void *stream);
 /* profiling hook: when non-NULL, every samd_step launch that performs a lookup writes each request's SM
- * cycle count to cycles_dev[n_requests] */
+ * cycle counts to cycles_dev[10][n_requests]: whole request, cursor transfers, appends, lookup + draft, then inside the
+ * appends: chain look-ups, edge inserts, (unused), target record, clone overflow copy, clone redirect walk */
 void samd_step_set_debug_cycles(int64_t *cycles_dev);
 /* tuning hook: 0 disables the scout (prefetcher) warps of samd_step; default 1 */
 void samd_step_set_scouts(int on);

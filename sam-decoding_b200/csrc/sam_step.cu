@@ -179,8 +179,9 @@ __device__ __forceinline__ void add_edge(int32_t *recs, uint4 *slots, uint32_t b
     }
 }
 
+template <bool kProf>                                       // kProf: the profiling build of the kernel (cycles by part in acc)
 __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t *text, uint32_t bmask, DynRegs &g, int tok,
-                                           int lane) {
+                                           int lane, long long *acc) {
     g.n += 1;
     const int cur = g.n_states++;
     if (lane < SAMD_REC) {                                  // the new state's record: one 64-byte store
@@ -204,15 +205,23 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
     }
     __syncwarp();
     while (p != -1) {
+        long long t0 = kProf ? clock64() : 0;
         Look r = warp_look<false>(recs, slots, bmask, p, tok, lane);
+        if constexpr (kProf) {
+            const long long t = clock64();
+            acc[0] += t - t0;                               // the chain's look-ups
+            t0 = t;
+        }
         if (!r.found) {
             add_edge(recs, slots, bmask, p, tok, cur, r, lane);
+            if constexpr (kProf) acc[1] += clock64() - t0;              // edge inserts
             g.n_edges++;
             __syncwarp();
             p = rec_word(r, R_LINK);
             continue;
         }
         const int q = r.target;
+        const long long tq0 = kProf ? clock64() : 0;
         // one request, two records: q's (lanes 0..15) and, speculatively, link(p)'s (lanes 16..31) - the
         // first state the redirect walk of a clone-on-split visits - so both DRAM reads overlap
         const int lp = rec_word(r, R_LINK);
@@ -221,7 +230,9 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
         else if (lp >= 0) qw = recs[(size_t)lp * SAMD_REC + (lane - SAMD_REC)];
         const int lpw = __shfl_sync(SAMD_FULL, qw, (lane + SAMD_REC) & 31);      // link(p)'s words in lanes 0..15
         const int len_p = rec_word(r, R_LEN);
-        if (len_p + 1 == __shfl_sync(SAMD_FULL, qw, R_LEN)) {
+        const int len_q = __shfl_sync(SAMD_FULL, qw, R_LEN);
+        if constexpr (kProf) acc[2] += clock64() - tq0;                 // the target's record (a dependent read)
+        if (len_p + 1 == len_q) {
             link_cur = q;
         } else {
             // clone-on-split: the clone is q's record (inline edges, link, min_endpos) with length
@@ -236,6 +247,7 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
             g.n_edges += __popc(__ballot_sync(SAMD_FULL, lane >= R_TOK && lane < R_TOK + SAMD_INLINE && (uint32_t)qw != SAMD_EMPTY));
             uint32_t e = (uint32_t)__shfl_sync(SAMD_FULL, qw, R_OHEAD);
             uint32_t head_c = SAMD_NIL, tail_c = SAMD_NIL;
+            const long long tc0 = kProf ? clock64() : 0;
             while (e != SAMD_NIL) {
                 const uint4 se = slots[e];
                 if (lane == 0 && se.w != SAMD_NIL) asm volatile("prefetch.global.L1 [%0];" ::"l"(slots + se.w));
@@ -256,6 +268,8 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
                 recs[(size_t)clone * SAMD_REC + R_OHEAD] = (int)head_c;
                 recs[(size_t)clone * SAMD_REC + R_OTAIL] = (int)tail_c;
             }
+            const long long tc1 = kProf ? clock64() : 0;
+            if constexpr (kProf) acc[3] += tc1 - tc0;                   // copy of q's overflow edges
             // redirect p's suffix chain from q to the clone
             Look cp = r;
             int pp = p;
@@ -276,6 +290,7 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
             }
             if (lane == 0) recs[(size_t)q * SAMD_REC + R_LINK] = clone;
             link_cur = clone;
+            if constexpr (kProf) acc[4] += clock64() - tc1;             // redirect walk
         }
         break;
     }
@@ -298,7 +313,7 @@ struct StepParams {
     double alpha;
     int32_t *out_type, *out_match_dyn, *out_match_static, *out_index_dyn, *out_index_static, *out_draft, *out_draft_len;
     int draft_stride;
-    long long *dbg_cycles;      // optional [n_requests] per-request SM cycles (profiling hook)
+    long long *dbg_cycles;      // optional [10][n_requests] per-request SM cycles by phase (profiling hook, see samd_b200.h)
 };
 
 // Scout warp: walks the cursor chain of the tokens this step will append (and of the final lookup) on the
@@ -342,6 +357,7 @@ __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slo
         asm volatile("prefetch.global.L1 [%0];" ::"l"(text + e + 1 + lane * 8));
 }
 
+template <bool kProf>
 __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31;
@@ -361,7 +377,9 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
         }
         return;
     }
-    const long long t_begin = P.dbg_cycles ? clock64() : 0;
+    const long long t_begin = kProf ? clock64() : 0;
+    long long c_transfer = 0, c_append = 0, t_mark = 0;
+    long long acc[5] = {0, 0, 0, 0, 0};
     int32_t *recs = P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC;
     uint4 *slots = P.dyn.slots + (size_t)r * P.dyn.h_cap;
     int32_t *text = P.dyn.text + (size_t)r * P.dyn.t_cap;
@@ -405,12 +423,19 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
                 }
                 // add_tokens: match first, then append (dyn_sam.py:84-88); StaticSAM.transfer_tokens
                 // (static_sam.py:102-104) walks an independent structure, so it goes first too
+                if constexpr (kProf) t_mark = clock64();
                 warp_transfer<false>(recs, slots, bmask, g.cur, g.cur_len, tok, lane, g.hops);
                 if (P.has_static) warp_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, s_idx, s_len, tok, lane, s_hops);
+                if constexpr (kProf) {
+                    const long long t = clock64();
+                    c_transfer += t - t_mark;
+                    t_mark = t;
+                }
                 // the records the NEXT token (or the final lookup) starts from are known now
                 prefetch_rec(recs, g.cur, lane);
                 if (P.has_static) prefetch_rec(P.st.recs, s_idx, lane);
-                dyn_append(recs, slots, text, bmask, g, tok, lane);
+                dyn_append<kProf>(recs, slots, text, bmask, g, tok, lane, acc);
+                if constexpr (kProf) c_append += clock64() - t_mark;
             }
             if (overflow) break;
         }
@@ -432,6 +457,7 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
         }
     }
     if (!P.start_tok) return;
+    const long long t_lookup = kProf ? clock64() : 0;
 
     // ---- phase 2: DraftModel.lookup (draft.py:52-63 / samd_sam_only/draft.py:49-59) -------
     const int tok = P.start_tok[r];
@@ -511,7 +537,12 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
         if (P.out_index_static) P.out_index_static[r] = t_idx;
         if (P.out_draft_len) P.out_draft_len[r] = n_out;
         meta[META_PROBES] += q_hops;          // probes spent in lookups (the extend-side count is META_HOPS)
-        if (P.dbg_cycles) P.dbg_cycles[r] = clock64() - t_begin;
+        if constexpr (kProf) {
+            const long long t = clock64();
+            const size_t n = (size_t)P.dyn.n_requests;
+            const long long v[10] = {t - t_begin, c_transfer, c_append, t - t_lookup, acc[0], acc[1], 0, acc[2], acc[3], acc[4]};
+            for (int i = 0; i < 10; ++i) P.dbg_cycles[i * n + r] = v[i];
+        }
     }
 }
 
@@ -554,7 +585,8 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     SAMD_REQUIRE(!a->out_draft_dev || a->draft_stride >= a->n_predicts, "samd_step: draft_stride < n_predicts");
     // warp 0 builds, warp 1 scouts the dynamic automaton, warp 2 (if any) scouts the static one
     const int threads = g_scouts ? (P.has_static ? 96 : 64) : 32;
-    sam_step_kernel<<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
+    if (P.dbg_cycles) sam_step_kernel<true><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
+    else sam_step_kernel<false><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
     samd_count_launch();
     SAMD_CUDA(cudaGetLastError());
     return 0;

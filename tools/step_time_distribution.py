@@ -8,9 +8,9 @@ dyn=E.DynSamBatch(1024, 8192+8*40+16, dev)
 eng=E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=16, len_bias=5, len_threshold=5)
 eng.step(torch.as_tensor(streams[:, :8192]).to(dev), None, None)
 dt,dc,ds=(torch.as_tensor(x).to(dev) for x in (tokens,counts,start))
-cyc=torch.zeros(1024,dtype=torch.int64,device=dev)
+cyc=torch.zeros(10,1024,dtype=torch.int64,device=dev)
 K.lib().samd_step_set_debug_cycles(cyc.data_ptr())
-allc=[]; feats=[]
+allc=[]; feats=[]; phases=[]
 import ctypes as C
 def meta():
     m=np.zeros((1024,16),dtype=np.int32)
@@ -21,7 +21,7 @@ for s in range(40):
     eng.step(dt[s],dc[s],ds[s]); torch.cuda.synchronize()
     m1=meta()
     if s>=8:
-        allc.append((cyc.cpu().numpy().copy(), counts[s].copy()))
+        allc.append((cyc[0].cpu().numpy().copy(), counts[s].copy())); phases.append(cyc.cpu().numpy().copy())
         d=m1-m0
         feats.append(np.stack([np.ones(1024), counts[s], d[:,7], d[:,5], d[:,8], d[:,9]],1))   # 1, tokens, clones, edges, hops, probes
     m0=m1
@@ -43,3 +43,12 @@ order=np.argsort(-y)[:16]
 print("slowest request-steps: time us | fitted | tokens clones edges hops probes")
 for i in order:
     print("  %5.1f | %5.1f | %d %d %d %d %d" % (y[i], X[i]@coef, *X[i,1:].astype(int)))
+ph=np.stack(phases).astype(float)/1.9e3            # [steps, 4, requests] us
+tot,tr,ap,lk=ph[:,0].reshape(-1),ph[:,1].reshape(-1),ph[:,2].reshape(-1),ph[:,3].reshape(-1)
+print("phase means us: total %.1f = cursor transfers %.1f + appends %.1f + lookup/draft %.1f + rest %.1f" % (tot.mean(), tr.mean(), ap.mean(), lk.mean(), (tot-tr-ap-lk).mean()))
+sl=tot>np.percentile(tot,99.5)
+print("slowest 0.5%%:    total %.1f = cursor transfers %.1f + appends %.1f + lookup/draft %.1f + rest %.1f" % (tot[sl].mean(), tr[sl].mean(), ap[sl].mean(), lk[sl].mean(), (tot-tr-ap-lk)[sl].mean()))
+lkc,adc,miss=ph[:,4].reshape(-1),ph[:,5].reshape(-1),(ph[:,6].reshape(-1)*1.9e3)
+print("inside the append loop (mean | slowest): look-ups %.2f | %.2f us, edge inserts %.2f | %.2f us" % (lkc.mean(), lkc[sl].mean(), adc.mean(), adc[sl].mean()))
+qr,oc,rd=ph[:,7].reshape(-1),ph[:,8].reshape(-1),ph[:,9].reshape(-1)
+print("at the chain's end (mean | slowest): target record %.2f | %.2f us, clone overflow copy %.2f | %.2f us, clone redirect walk %.2f | %.2f us" % (qr.mean(), qr[sl].mean(), oc.mean(), oc[sl].mean(), rd.mean(), rd[sl].mean()))
