@@ -338,6 +338,12 @@ __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slo
         while (true) {                                                       // transfer_state, no bookkeeping
             const Look r = warp_look<kStatic>(recs, slots, bmask, idx, tok, lane);
             if (r.found) {
+                if (!kStatic && i < k) {
+                    // the builder reads the target's record together with the record of the stop above this one (the
+                    // first stop of a clone's redirect walk): request that one too, without waiting for it
+                    const int up = rec_word(r, R_LINK);
+                    if (up > 0 && (unsigned long long)up < (unsigned long long)cap) prefetch_rec(recs, up, lane);
+                }
                 idx = r.target;
                 if ((unsigned long long)idx >= (unsigned long long)cap) idx = 0;
                 break;
