@@ -915,8 +915,13 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     SAMD_REQUIRE(!topk || P.n_items1 <= h->topk_items, "samd_verify_compact: top-8 scratch too small for this shape");
     P.n_items2 = move ? a->batch * a->n_kv : 0;
     P.vec_ok = ((uintptr_t)a->logits_dev % 16 == 0) && (a->batch_stride % 8 == 0) && (a->row_stride % 8 == 0);
-    const long long grid = move ? std::max<long long>(1, (long long)h->n_sms * per_sm)
-                                : std::max<long long>(1, std::min<long long>((long long)h->n_sms * per_sm, ((long long)P.n_items1 + VW - 1) / VW));
+    // One warp per item up to the resident grid.  With row moves, a small batch keeps a small grid too (every CTA
+    // takes part in the barriers, whose cost grows with their number: 20.6 -> 19.1 us per launch at batch 1) as long as
+    // each moved request still finds about 32 CTAs' worth of lanes for its 16-byte units.
+    const long long full = std::max<long long>(1, (long long)h->n_sms * per_sm);
+    long long grid = std::min<long long>(full, ((long long)P.n_items1 + VW - 1) / VW);
+    if (move) grid = std::max<long long>(grid, std::min<long long>(full, (long long)a->batch * 32));
+    grid = std::max<long long>(grid, 1);
     // Cooperative launch: the kernel's barriers need every CTA resident at once, and only a cooperative launch makes
     // the driver guarantee it - two overlapping launches (two handles on two streams) would otherwise each hold part
     // of the machine and wait for the rest forever.

@@ -7,6 +7,9 @@ import torch
 from samd_b200 import _cabi as K, engine as E, synth
 dev = torch.device("cuda")
 B, T, V = 64, 61, 32000
+for arg in sys.argv[1:]:
+    if arg.startswith("B="):
+        B = int(arg[2:])
 move = len(sys.argv) > 1 and sys.argv[1] == "kv"
 ri_np = synth.tree_retrieve_indices(synth.token_recycle_tree())
 rng = np.random.default_rng(4000)
@@ -16,7 +19,7 @@ ver = E.Verifier(B, T, dev)
 d_tok, d_ri = torch.as_tensor(tree_tokens).to(dev), torch.as_tensor(ri_np).to(dev)
 cache_len = torch.full((B,), 300, dtype=torch.int32, device=dev)
 if move:
-    kv_all = torch.empty(64, B, 32, 2048, 128, dtype=torch.bfloat16, device=dev)
+    kv_all = torch.empty(64, B, 32, 1024 if B < 64 else 2048, 128, dtype=torch.bfloat16, device=dev)
     ver.bind_kv([kv_all[i] for i in range(64)])
 n_warps = 148 * 4 * 8
 times = torch.zeros(n_warps, 3, dtype=torch.int64, device=dev)
