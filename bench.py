@@ -794,29 +794,66 @@ def bench_sharded_static(a, dev, rank, world, tokens_per_shard=2_000_000, n_q=40
     start = q[np.arange(n_q)[None, :], ends].astype(np.int32)
     d_tok, d_cnt, d_st = (torch.as_tensor(x).to(dev) for x in (tokens, counts, start))
 
-    def step(s):
-        sh.advance(d_tok[s], d_cnt[s])
-        return sh.lookup_draft(d_st[s], N_PREDICTS)
+    def timed(p2p, graph):
+        """warm-up steps, then `steps` timed steps; eager launches or one captured graph (p2p only: NCCL stays eager)"""
+        sh.reset()
+        out = (torch.empty(n_q, dtype=torch.int32, device=dev), torch.empty(n_q, N_PREDICTS, dtype=torch.int32, device=dev))
 
-    for s in range(warm):
-        step(s)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(warm, warm + steps):
-        match, draft = step(s)
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    return {"workload": f"c5 (reduced corpus): static SAM over {sh.n_corpus} tokens split by document over {world} GPUs "
-                        f"({sh.sam.n_tokens} tokens on rank 0), {n_q} queries/step advanced 1-8 tokens, packed-u64 NCCL "
-                        f"all-reduce-max ({n_q * 8} B) per step, draft {N_PREDICTS} from the replicated corpus",
-            "queries_per_s": n_q * steps / (ms * 1e-3), "us_per_step": ms / steps * 1e3, "host_build_s": build_s,
-            "mean_match": float(match.float().mean()), "gpu_launches_per_step": 3, "collectives_per_step": 1}
+        def step(s):
+            return sh.lookup_draft(d_st[s], N_PREDICTS, p2p=p2p, out=out if p2p else None, tokens=d_tok[s], counts=d_cnt[s])
+
+        for s in range(warm):
+            res = step(s)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g = None
+        if graph:
+            cur0 = sh.cursor.clone()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for s in range(warm, warm + steps):
+                    res = step(s)
+            sh.cursor.copy_(cur0)
+            torch.cuda.synchronize()
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if g is not None:
+            g.replay()
+        else:
+            for s in range(warm, warm + steps):
+                res = step(s)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), res[0].clone(), res[1].clone()
+
+    ms, match, draft = timed(False, False)
+    out = {"workload": f"c5 (reduced corpus): static SAM over {sh.n_corpus} tokens split by document over {world} GPUs "
+                       f"({sh.sam.n_tokens} tokens on rank 0), {n_q} queries/step advanced 1-8 tokens, packed-u64 "
+                       f"max-reduce ({n_q * 8} B) per step, draft {N_PREDICTS} from the replicated corpus",
+           "nccl": {"queries_per_s": n_q * steps / (ms * 1e-3), "us_per_step": ms / steps * 1e3, "gpu_launches_per_step": 3,
+                    "collectives_per_step": 1, "note": "cursor walk, look-up kernel, NCCL all-reduce-max, draft kernel; eager launches"},
+           "host_build_s": build_s, "mean_match": float(match.float().mean())}
+    try:                                      # the same step with the reduction done by the look-up kernel over NVLink peer memory
+        if not sh.connect_peers():
+            raise RuntimeError("peer mapping failed on some rank")
+        ms_p, match_p, draft_p = timed(True, False)
+        same = bool(torch.equal(match_p, match) and torch.equal(draft_p, draft))
+        ms_g, match_g, draft_g = timed(True, True)
+        same = same and bool(torch.equal(match_g, match) and torch.equal(draft_g, draft))
+        out["p2p"] = {"queries_per_s": n_q * steps / (ms_p * 1e-3), "us_per_step": ms_p / steps * 1e3,
+                      "graph_queries_per_s": n_q * steps / (ms_g * 1e-3), "graph_us_per_step": ms_g / steps * 1e3,
+                      "gpu_launches_per_step": 2, "collectives_per_step": 0, "identical_to_nccl": same, "peers_ok": sh.peers_ok(),
+                      "note": "cursor walk + look-up kernel with remote atomicMax into every rank's buffer, draft kernel waiting on "
+                              "peer flags; eager, and all steps captured in one CUDA graph"}
+        out["queries_per_s"] = max(out["nccl"]["queries_per_s"], out["p2p"]["queries_per_s"], out["p2p"]["graph_queries_per_s"])
+    except Exception as e:
+        out["p2p"] = {"error": repr(e)}
+        out["queries_per_s"] = out["nccl"]["queries_per_s"]
+    return out
 
 
 def main():

@@ -209,6 +209,28 @@ int samd_draft_from_keys(const int64_t *keys_dev, const int32_t *corpus_dev, int
                          const int32_t *start_tok_dev, int n_requests, int32_t n_predicts, int32_t *out_match_dev,
                          int32_t *out_draft_dev, int32_t draft_stride, void *stream);
 
+/* The same reduction without a collective library (one process per GPU, NVLink peer memory): every rank owns an
+ * exchange buffer, maps every peer's through CUDA IPC, and the look-up kernel itself max-reduces the packed keys into
+ * EVERY rank's buffer with remote atomics; the draft kernel waits for all shards' keys on the local buffer.
+ *   samd_xchg_create           this rank's buffer for n_queries queries (cudaMalloc)
+ *   samd_xchg_export           its 64-byte CUDA IPC handle, to be all-gathered by the caller (torch.distributed)
+ *   samd_xchg_connect          handles = [world][64] in rank order; opens the peers' buffers
+ *   samd_static_lookup_exchange / samd_draft_from_exchange   replace samd_static_lookup_keys + all-reduce-max +
+ *                              samd_draft_from_keys; every rank must issue the same sequence of pairs.  No argument
+ *                              depends on the step, so the pair can be captured in a CUDA graph. */
+typedef struct samd_xchg_s *samd_xchg_t;
+int samd_xchg_create(int rank, int world, int n_queries, samd_xchg_t *out);
+int samd_xchg_export(samd_xchg_t x, void *handle64_out);
+int samd_xchg_connect(samd_xchg_t x, const void *handles);
+int samd_xchg_destroy(samd_xchg_t x);
+int samd_xchg_status(samd_xchg_t x);   /* 0 ok; 1 = a draft kernel gave up waiting for a peer after 5 s (synchronises) */
+int samd_static_lookup_exchange(samd_static_t h, int32_t *static_cursor_dev, const int32_t *tokens_dev, int32_t token_stride,
+                                const int32_t *counts_dev, const int32_t *start_tok_dev, int64_t shard_offset, samd_xchg_t x,
+                                void *stream);   /* tokens_dev != NULL: StaticSAM.transfer_tokens first, same launch */
+int samd_draft_from_exchange(samd_xchg_t x, const int32_t *corpus_dev, int64_t n_corpus_tokens, const int32_t *start_tok_dev,
+                             int32_t n_predicts, int32_t *out_match_dev, int32_t *out_draft_dev, int32_t draft_stride,
+                             void *stream);
+
 /* ----------------------------------------------------------------------------------------
  * Fused greedy verification + KV-cache compaction
  *   (gather samd/samd_model.py:159-168, eval_posterior greedy samd/utils.py:127-141,

@@ -89,6 +89,13 @@ SYMBOLS = {
                                          vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "samd_static_lookup_keys": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, vp, vp]),
     "samd_draft_from_keys": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, C.c_int32, vp, vp, C.c_int32, vp]),
+    "samd_xchg_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "samd_xchg_export": (C.c_int, [vp, vp]),
+    "samd_xchg_connect": (C.c_int, [vp, vp]),
+    "samd_xchg_destroy": (C.c_int, [vp]),
+    "samd_xchg_status": (C.c_int, [vp]),
+    "samd_static_lookup_exchange": (C.c_int, [vp, vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp]),
+    "samd_draft_from_exchange": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int32, vp, vp, C.c_int32, vp]),
     "samd_static_walk": (C.c_int, [vp, vp, vp, C.c_int32, vp, vp, C.c_int, vp, vp, vp]),
     "samd_dyn_transfer": (C.c_int, [vp, vp, C.c_int32, vp, vp]),
     "samd_kv_compact": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32,

@@ -97,6 +97,47 @@ class ShardedStaticSam:
         self.cursor = self.sam.new_cursors(n_queries)
         self.keys = torch.zeros(n_queries, dtype=torch.int64, device=self.device)
         self.n_queries = n_queries
+        self._xchg = None
+
+    def connect_peers(self, group=None) -> bool:
+        """Set up the NVLink peer exchange (one process per GPU of one node): every rank allocates its exchange
+        buffer, the CUDA IPC handles are all-gathered through torch.distributed, and every rank maps its peers'
+        buffers.  Collective; returns True when EVERY rank succeeded (only then may lookup_draft(p2p=True) be used -
+        a rank that went ahead alone would wait for peers that never signal)."""
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _cabi as K
+        h, ok = K.vp(), 1
+        mine = (C.c_ubyte * 64)()
+        try:
+            with torch.cuda.device(self.device):
+                K.check(K.lib().samd_xchg_create(self.rank, self.world, self.n_queries, C.byref(h)), "samd_xchg_create")
+                K.check(K.lib().samd_xchg_export(h, C.cast(mine, K.vp)), "samd_xchg_export")
+        except K.SamdError:
+            ok = 0
+        mine_t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+        all_t = [torch.empty_like(mine_t) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(all_t, mine_t, group=group)
+        else:
+            all_t = [mine_t]
+        if ok:
+            flat = torch.stack(all_t).cpu().numpy().tobytes()
+            buf = (C.c_ubyte * len(flat)).from_buffer_copy(flat)
+            try:
+                with torch.cuda.device(self.device):
+                    K.check(K.lib().samd_xchg_connect(h, C.cast(buf, K.vp)), "samd_xchg_connect")
+            except K.SamdError:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        if self.world > 1:                              # also the barrier: nobody writes into an unmapped buffer
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self._xchg = h if int(flag.item()) == 1 else None
+        return self._xchg is not None
+
+    def peers_ok(self) -> bool:
+        from . import _cabi as K
+        return self._xchg is not None and K.lib().samd_xchg_status(self._xchg) == 0
 
     def reset(self):
         self.cursor.zero_()
@@ -125,7 +166,30 @@ class ShardedStaticSam:
                                                  K.stream_ptr()), "samd_draft_from_keys")
         return match, draft
 
-    def lookup_draft(self, start_tok: torch.Tensor, n_predicts: int, group=None):
-        """local keys -> all-reduce-max -> draft from the replicated corpus."""
-        keys = reduce_keys(self.local_keys(start_tok), group)
-        return self.draft(keys, start_tok, n_predicts)
+    def lookup_draft(self, start_tok: torch.Tensor, n_predicts: int, group=None, p2p: bool = False, out=None,
+                     tokens: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None):
+        """local keys -> max over the shards -> draft from the replicated corpus.  p2p=False: one NCCL all-reduce-max
+        between two kernels.  p2p=True (after connect_peers()): the look-up kernel max-reduces into every rank's
+        buffer over NVLink itself and the draft kernel waits for the shards' keys - two launches, no collective.
+        `tokens` / `counts`: advance the cursors first (StaticSAM.transfer_tokens; the same launch when p2p)."""
+        if not p2p:
+            if tokens is not None:
+                self.advance(tokens, counts)
+            keys = reduce_keys(self.local_keys(start_tok), group)
+            return self.draft(keys, start_tok, n_predicts)
+        from . import _cabi as K
+        if self._xchg is None:
+            raise K.SamdError("lookup_draft(p2p=True) before connect_peers()")
+        if out is None:
+            out = (torch.empty(self.n_queries, dtype=torch.int32, device=self.device),
+                   torch.empty(self.n_queries, n_predicts, dtype=torch.int32, device=self.device))
+        match, draft = out
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_static_lookup_exchange(self.sam.handle, self.cursor.data_ptr(), K.ptr(tokens),
+                                                        tokens.shape[1] if tokens is not None else 0, K.ptr(counts),
+                                                        start_tok.data_ptr(), self.offset, self._xchg, K.stream_ptr()),
+                    "samd_static_lookup_exchange")
+            K.check(K.lib().samd_draft_from_exchange(self._xchg, self.corpus.data_ptr(), self.n_corpus, start_tok.data_ptr(),
+                                                     n_predicts, match.data_ptr(), draft.data_ptr(), n_predicts, K.stream_ptr()),
+                    "samd_draft_from_exchange")
+        return match, draft
