@@ -834,3 +834,48 @@ def test_c3_static_and_dynamic_against_c_oracle():
                 assert seq == draft[r].tolist(), (s, r)
             seen.add(kind)
     assert {0, 1} <= seen                                      # both automata supplied drafts
+
+
+def test_peer_exchange_single_rank_matches_key_path():
+    """The NVLink peer-exchange kernels (csrc/xchg.cu) with one rank: the protocol (epoch parity, flags, re-armed key
+    buffers, cursor advance fused into the look-up launch) must give what look-up keys + draft-from-keys give, step
+    after step, also when the steps are captured in a CUDA graph.  (Several ranks: tools/p2p_check.py, bench.py.)"""
+    E, K = _engine_mod()
+    from samd_b200 import dist as D, synth
+    docs = [d.tolist() for d in synth.make_corpus(40000, 500, 71, doc_len=(16, 96), singletons=True)]
+    nq, qlen, steps = 96, 8 * 6 + 1, 6
+    q = synth.corpus_queries([np.array(d) for d in docs], nq, qlen, 500, 72).astype(np.int32)
+    a = D.ShardedStaticSam(docs, synth.EOS, 0, 1, nq, torch.device("cuda"))
+    b = D.ShardedStaticSam(docs, synth.EOS, 0, 1, nq, torch.device("cuda"))
+    assert b.connect_peers() and b.peers_ok()
+    rng = np.random.default_rng(73)
+    counts = rng.integers(0, 9, size=(steps, nq)).astype(np.int32)
+    pos = np.zeros(nq, dtype=np.int64)
+    toks, starts = [], []
+    for s in range(steps):
+        t = np.zeros((nq, 8), dtype=np.int32)
+        for i in range(nq):
+            t[i, :counts[s, i]] = q[i, pos[i]:pos[i] + counts[s, i]]
+        pos += counts[s]
+        toks.append(_dev_i32(t))
+        starts.append(_dev_i32(q[np.arange(nq), pos]))
+    d_cnt = [_dev_i32(c) for c in counts]
+    want = [tuple(x.clone() for x in a.lookup_draft(starts[s], 16, tokens=toks[s], counts=d_cnt[s])) for s in range(steps)]
+    out = (torch.empty(nq, dtype=torch.int32, device="cuda"), torch.empty(nq, 16, dtype=torch.int32, device="cuda"))
+    for s in range(steps):                                       # eager
+        m, d = b.lookup_draft(starts[s], 16, p2p=True, out=out, tokens=toks[s], counts=d_cnt[s])
+        torch.cuda.synchronize()
+        assert torch.equal(m, want[s][0]) and torch.equal(d, want[s][1]), s
+    b.reset()
+    outs = [(torch.empty_like(out[0]), torch.empty_like(out[1])) for _ in range(steps)]
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):                                     # all steps in one graph, replayed twice
+        for s in range(steps):
+            b.lookup_draft(starts[s], 16, p2p=True, out=outs[s], tokens=toks[s], counts=d_cnt[s])
+    for rep in range(2):
+        b.reset()
+        g.replay()
+        torch.cuda.synchronize()
+        for s in range(steps):
+            assert torch.equal(outs[s][0], want[s][0]) and torch.equal(outs[s][1], want[s][1]), (rep, s)
+    assert b.peers_ok()
