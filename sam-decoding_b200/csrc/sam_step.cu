@@ -1,5 +1,6 @@
 // Dynamic-SAM arenas and the per-step draft kernel (extend + advance + lookup + select + draft).
-// One warp per request; see include/samd_b200.h for the reference methods each entry replaces.
+// One CTA per request - a builder warp and one or two read-only scout warps that run ahead of it; see
+// include/samd_b200.h for the reference methods each entry replaces.
 #include "samd_common.cuh"
 #include "../../include/samd_b200.h"
 
