@@ -11,6 +11,15 @@ for p in (os.path.join(REPO, "sam-decoding_b200"), os.path.join(REPO, "oracle"),
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built library yet (it is git-ignored): build it the way __graft_entry__.build() does,
+    # so that the suite does not depend on the order the driver runs things in.  nvcc cross-compiles without a GPU.
+    lib = os.path.join(REPO, "sam-decoding_b200", "samd_b200", "libsamd_b200.so")
+    if not os.path.exists(lib):
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") and shutil.which("make"):
+            subprocess.run(["make", "-C", os.path.join(REPO, "sam-decoding_b200", "csrc")], check=False,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def pytest_collection_modifyitems(config, items):
