@@ -180,9 +180,79 @@ __device__ __forceinline__ void add_edge(int32_t *recs, uint4 *slots, uint32_t b
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// The cursor's fallback chain for a token (transfer_cur_state: follow suffix links until a state has an edge on the
+// token) visits exactly the states the append then gives that edge to (add_state walks the tail's suffix chain, and
+// the cursor IS link(tail), up to the pre-clone quirk: then the chain is one stop longer at the front).  The
+// transfer therefore leaves the chain in shared memory and the append inserts the edge at all of its stops at
+// once, one lane per state, instead of walking it a second time, one dependent stop after the other.
+// ---------------------------------------------------------------------------------------
+#define CHAIN_MAX 64
+
+// transfer_cur_state that records the states it visits (same walk as warp_transfer<false>); stopped_on_edge tells
+// whether the last recorded state has the edge (else the walk ended at the root without finding one)
+__device__ __forceinline__ void warp_transfer_chain(const int32_t *recs, const uint4 *slots, uint32_t bmask, int &index, int &length,
+                                                    int tok, int lane, int &hops, int *chain, int &n_chain, bool &stopped_on_edge) {
+    bool first = true;
+    n_chain = 0;
+    stopped_on_edge = false;
+    while (true) {
+        const Look r = warp_look<false>(recs, slots, bmask, index, tok, lane);
+        if (lane == 0 && n_chain < CHAIN_MAX) chain[n_chain] = index;
+        ++n_chain;                                           // > CHAIN_MAX: too long to replay, the append walks it itself
+        hops++;
+        if (!first) length = rec_word(r, R_LEN);
+        if (r.found) {
+            index = r.target;
+            length += 1;
+            stopped_on_edge = true;
+            break;
+        }
+        if (index == 0) {
+            length = 0;
+            break;
+        }
+        index = rec_word(r, R_LINK);
+        first = false;
+    }
+    __syncwarp();
+}
+
+// one lane, one state: give `state` the out-edge tok -> target (it has none on tok yet); the overflow slot is claimed
+// with a compare-and-swap because two lanes of the same append may hash into the same bucket
+__device__ __forceinline__ void lane_add_edge(int32_t *recs, uint4 *slots, uint32_t bmask, int state, int tok, int target) {
+    int32_t *rec = recs + (size_t)state * SAMD_REC;
+#pragma unroll
+    for (int i = 0; i < SAMD_INLINE; ++i) {
+        if ((uint32_t)rec[R_TOK + i] == SAMD_EMPTY) {
+            rec[R_TOK + i] = tok;
+            rec[R_TGT + i] = target;
+            return;
+        }
+    }
+    uint32_t b = samd_hash((uint32_t)state, (uint32_t)tok) & bmask;
+    while (true) {
+        for (int l = 0; l < SAMD_BUCKET; ++l) {
+            const uint32_t slot = b * SAMD_BUCKET + l;
+            uint32_t *sx = reinterpret_cast<uint32_t *>(slots + slot);
+            if (*reinterpret_cast<volatile uint32_t *>(sx) != SAMD_EMPTY) continue;
+            if (atomicCAS(sx, SAMD_EMPTY, (uint32_t)state) != SAMD_EMPTY) continue;
+            sx[1] = (uint32_t)tok;
+            sx[2] = (uint32_t)target;
+            sx[3] = SAMD_NIL;
+            const uint32_t tail = (uint32_t)rec[R_OTAIL];
+            if (tail != SAMD_NIL) slots[tail].w = slot;     // lists run oldest -> newest
+            else rec[R_OHEAD] = (int)slot;
+            rec[R_OTAIL] = (int)slot;
+            return;
+        }
+        b = (b + 1) & bmask;
+    }
+}
+
 template <bool kProf>                                       // kProf: the profiling build of the kernel (cycles by part in acc)
 __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t *text, uint32_t bmask, DynRegs &g, int tok,
-                                           int lane, long long *acc) {
+                                           int lane, long long *acc, const int *chain, int n_chain, bool chain_on_edge) {
     g.n += 1;
     const int cur = g.n_states++;
     if (lane < SAMD_REC) {                                  // the new state's record: one 64-byte store
@@ -205,6 +275,21 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
         p = g.last_link;
     }
     __syncwarp();
+    // the cursor's walk for this token already enumerated the stops that lack the edge: insert at all of them at once
+    if (n_chain > 0 && n_chain <= CHAIN_MAX) {
+        int s0 = -1;
+        if (chain[0] == p) s0 = 0;
+        else if (n_chain > 1 && chain[1] == p) s0 = 1;
+        if (s0 >= 0) {
+            const long long t0 = kProf ? clock64() : 0;
+            const int end = chain_on_edge ? n_chain - 1 : n_chain;           // [s0, end): states without the edge
+            for (int j = s0 + lane; j < end; j += 32) lane_add_edge(recs, slots, bmask, chain[j], tok, cur);
+            g.n_edges += end - s0;
+            __syncwarp();
+            p = chain_on_edge ? chain[n_chain - 1] : -1;                     // resume at the state that has the edge
+            if constexpr (kProf) acc[1] += clock64() - t0;
+        }
+    }
     while (p != -1) {
         long long t0 = kProf ? clock64() : 0;
         Look r = warp_look<false>(recs, slots, bmask, p, tok, lane);
@@ -384,6 +469,9 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
         }
         return;
     }
+    __shared__ int s_chain[CHAIN_MAX];
+    int n_chain = 0;
+    bool chain_on_edge = false;
     const long long t_begin = kProf ? clock64() : 0;
     long long c_transfer = 0, c_append = 0, t_mark = 0;
     long long acc[5] = {0, 0, 0, 0, 0};
@@ -431,7 +519,7 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
                 // add_tokens: match first, then append (dyn_sam.py:84-88); StaticSAM.transfer_tokens
                 // (static_sam.py:102-104) walks an independent structure, so it goes first too
                 if constexpr (kProf) t_mark = clock64();
-                warp_transfer<false>(recs, slots, bmask, g.cur, g.cur_len, tok, lane, g.hops);
+                warp_transfer_chain(recs, slots, bmask, g.cur, g.cur_len, tok, lane, g.hops, s_chain, n_chain, chain_on_edge);
                 if (P.has_static) warp_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, s_idx, s_len, tok, lane, s_hops);
                 if constexpr (kProf) {
                     const long long t = clock64();
@@ -441,7 +529,7 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
                 // the records the NEXT token (or the final lookup) starts from are known now
                 prefetch_rec(recs, g.cur, lane);
                 if (P.has_static) prefetch_rec(P.st.recs, s_idx, lane);
-                dyn_append<kProf>(recs, slots, text, bmask, g, tok, lane, acc);
+                dyn_append<kProf>(recs, slots, text, bmask, g, tok, lane, acc, s_chain, n_chain, chain_on_edge);
                 if constexpr (kProf) c_append += clock64() - t_mark;
             }
             if (overflow) break;
