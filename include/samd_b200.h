@@ -173,7 +173,7 @@ int samd_step(const samd_step_args *args, void *stream);
  * cycle counts to cycles_dev[10][n_requests]: whole request, cursor transfers, appends, lookup + draft, then inside the
  * appends: chain look-ups, edge inserts, (unused), target record, clone overflow copy, clone redirect walk */
 void samd_step_set_debug_cycles(int64_t *cycles_dev);
-/* tuning hook: 0 disables the scout (prefetcher) warps of samd_step; default 1 */
+/* tuning hook: scout (prefetcher) warps of samd_step - 0 none, 1 the cursor scouts, 2 (default) also the redirect scout */
 void samd_step_set_scouts(int on);
 
 /* Cursor-only walks.  samd_static_walk = StaticSAM.transfer_tokens (static_sam.py:102-104) when

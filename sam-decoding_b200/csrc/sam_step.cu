@@ -1,5 +1,5 @@
 // Dynamic-SAM arenas and the per-step draft kernel (extend + advance + lookup + select + draft).
-// One CTA per request - a builder warp and one or two read-only scout warps that run ahead of it; see
+// One CTA per request - a builder warp and up to three read-only scout warps that run ahead of it; see
 // include/samd_b200.h for the reference methods each entry replaces.
 #include "samd_common.cuh"
 #include "../../include/samd_b200.h"
@@ -402,6 +402,7 @@ struct StepParams {
     long long *dbg_cycles;      // optional [10][n_requests] per-request SM cycles by phase (profiling hook, see samd_b200.h)
 };
 
+#define SCOUT_MAX_TOKENS 64
 // Scout warp: walks the cursor chain of the tokens this step will append (and of the final lookup) on the
 // automaton AS IT IS - transfers only, nothing is written - one dependent read per token, i.e. faster than the
 // builder warp, whose chain also carries clone / redirect work.  Every record (and the draft's text lines) it
@@ -411,16 +412,17 @@ struct StepParams {
 template <bool kStatic>
 __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slots, uint32_t bmask, const int32_t *text,
                                            int idx, const int32_t *tk, int k, int peek, int n_predicts, long long text_n,
-                                           long long cap, int lane) {
+                                           long long cap, int lane, volatile int *mailbox = nullptr) {
     // `cap` bounds every state index before it is dereferenced: the scout races with the builder and may read a
     // record whose initialisation is not visible yet (stale memory), so nothing it reads is trusted as an address
-    if (k > 64) return;                                                      // long appends (prefill): nothing useful to scout
+    if (k > SCOUT_MAX_TOKENS) return;                                        // long appends (prefill): nothing useful to scout
     if ((unsigned long long)idx >= (unsigned long long)cap) return;
     const int total = k + (peek >= 0 ? 1 : 0);
     int mine = 0;
     for (int i = 0; i < total; ++i) {
         if ((i & 31) == 0) mine = (i + lane < k) ? tk[i + lane] : peek;      // tokens, then the lookup token
         const int tok = __shfl_sync(SAMD_FULL, mine, i & 31);
+        int up_state = 0, up_target = 0;                                     // for the redirect scout
         while (true) {                                                       // transfer_state, no bookkeeping
             const Look r = warp_look<kStatic>(recs, slots, bmask, idx, tok, lane);
             if (r.found) {
@@ -429,6 +431,8 @@ __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slo
                     // first stop of a clone's redirect walk): request that one too, without waiting for it
                     const int up = rec_word(r, R_LINK);
                     if (up > 0 && (unsigned long long)up < (unsigned long long)cap) prefetch_rec(recs, up, lane);
+                    up_state = up;
+                    up_target = r.target;
                 }
                 idx = r.target;
                 if ((unsigned long long)idx >= (unsigned long long)cap) idx = 0;
@@ -441,6 +445,13 @@ __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slo
                 break;
             }
         }
+        if (!kStatic && mailbox && i < k && lane == 0) {     // every token gets an entry (stop 0 = nothing to look up)
+            mailbox[4 * i + 0] = up_state;
+            mailbox[4 * i + 1] = tok;
+            mailbox[4 * i + 2] = up_target;
+            __threadfence_block();
+            mailbox[4 * SCOUT_MAX_TOKENS] = i + 1;
+        }
     }
     if (peek < 0) return;
     // the draft will be read right after the earliest end position of the matched state
@@ -449,11 +460,46 @@ __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slo
         asm volatile("prefetch.global.L1 [%0];" ::"l"(text + e + 1 + lane * 8));
 }
 
+// Redirect scout.  When the builder has to split the state an edge leads to (clone-on-split, 0.7 times per token on
+// copy-heavy streams) it re-points that edge at the states further up the suffix chain - a cold pointer chase that
+// neither the cursor's walk nor the first scout has touched.  This warp takes (stop above, token, target) hand-offs
+// from the first scout and looks the next few stops up, so that their records and buckets are in cache.
+__device__ __forceinline__ void redirect_scout(const int32_t *recs, const uint4 *slots, uint32_t bmask, volatile int *mailbox,
+                                               int k, long long cap, int lane) {
+    if (k > SCOUT_MAX_TOKENS) return;
+    for (int i = 0; i < k; ++i) {
+        int have = 0;
+        if (lane == 0) {
+            while (true) {
+                if (mailbox[4 * SCOUT_MAX_TOKENS] > i) {
+                    have = 1;
+                    break;
+                }
+                if (mailbox[4 * SCOUT_MAX_TOKENS + 1]) break;   // the first scout is done and never got this far
+                __nanosleep(40);
+            }
+        }
+        have = __shfl_sync(SAMD_FULL, have, 0);
+        if (!have) return;
+        __threadfence_block();
+        int pp = mailbox[4 * i + 0];
+        const int tok = mailbox[4 * i + 1], target = mailbox[4 * i + 2];
+        for (int up = 0; up < 6 && pp > 0 && (unsigned long long)pp < (unsigned long long)cap; ++up) {
+            const Look ru = warp_look<false>(recs, slots, bmask, pp, tok, lane);
+            if (!ru.found || ru.target != target) break;
+            pp = rec_word(ru, R_LINK);
+        }
+    }
+}
+
 template <bool kProf>
-__global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
+__global__ void __launch_bounds__(128) sam_step_kernel(StepParams P) {
+    __shared__ int s_mailbox[4 * SCOUT_MAX_TOKENS + 2];        // first scout -> redirect scout
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31;
     if (r >= P.dyn.n_requests) return;
+    if (threadIdx.x < 2) s_mailbox[4 * SCOUT_MAX_TOKENS + threadIdx.x] = 0;
+    __syncthreads();
     if (threadIdx.x >= 32) {
         const int k = P.tokens ? (P.counts ? P.counts[r] : P.token_stride) : 0;
         const int32_t *tk = P.tokens ? P.tokens + (size_t)r * P.token_stride : nullptr;
@@ -462,7 +508,14 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
             const int32_t *meta = P.dyn.meta + (size_t)r * META_WORDS;
             scout_walk<false>(P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC, P.dyn.slots + (size_t)r * P.dyn.h_cap, P.dyn.bmask,
                               P.dyn.text + (size_t)r * P.dyn.t_cap, meta[META_CUR], tk, k, peek, P.n_predicts, (long long)meta[META_N],
-                              (long long)P.dyn.s_cap, lane);
+                              (long long)P.dyn.s_cap, lane, blockDim.x > 96 ? s_mailbox : nullptr);
+            if (lane == 0) {                                  // whatever path the scout left by: no more hand-offs
+                __threadfence_block();
+                reinterpret_cast<volatile int *>(s_mailbox)[4 * SCOUT_MAX_TOKENS + 1] = 1;
+            }
+        } else if (threadIdx.x >= 96) {
+            redirect_scout(P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC, P.dyn.slots + (size_t)r * P.dyn.h_cap, P.dyn.bmask, s_mailbox,
+                           k, (long long)P.dyn.s_cap, lane);
         } else if (P.has_static) {
             scout_walk<true>(P.st.recs, P.st.slots, P.st.bmask, P.st.text, P.static_cursor[2 * r], tk, k, peek, P.n_predicts,
                              (long long)P.st.n_tokens, (long long)P.st.n_states, lane);
@@ -642,7 +695,7 @@ __global__ void __launch_bounds__(96) sam_step_kernel(StepParams P) {
 }
 
 static long long *g_dbg_cycles = nullptr;
-static int g_scouts = 1;
+static int g_scouts = 2;
 extern "C" void samd_step_set_scouts(int on) { g_scouts = on; }
 extern "C" void samd_step_set_debug_cycles(int64_t *cycles_dev) { g_dbg_cycles = (long long *)cycles_dev; }
 
@@ -678,8 +731,8 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     SAMD_REQUIRE(a->flavour == SAMD_FLAVOUR_SAMD || a->flavour == SAMD_FLAVOUR_SAM_ONLY, "samd_step: bad flavour");
     SAMD_REQUIRE(!a->tokens_dev || a->token_stride > 0, "samd_step: token_stride must be positive");
     SAMD_REQUIRE(!a->out_draft_dev || a->draft_stride >= a->n_predicts, "samd_step: draft_stride < n_predicts");
-    // warp 0 builds, warp 1 scouts the dynamic automaton, warp 2 (if any) scouts the static one
-    const int threads = g_scouts ? (P.has_static ? 96 : 64) : 32;
+    // warp 0 builds, warp 1 scouts the dynamic automaton, warp 2 the static one (if any), warp 3 the clones' redirect walks
+    const int threads = g_scouts ? (a->tokens_dev && g_scouts > 1 ? 128 : (P.has_static ? 96 : 64)) : 32;
     if (P.dbg_cycles) sam_step_kernel<true><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
     else sam_step_kernel<false><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
     samd_count_launch();
