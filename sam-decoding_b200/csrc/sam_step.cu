@@ -412,7 +412,7 @@ struct StepParams {
 template <bool kStatic>
 __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slots, uint32_t bmask, const int32_t *text,
                                            int idx, const int32_t *tk, int k, int peek, int n_predicts, long long text_n,
-                                           long long cap, int lane, volatile int *mailbox = nullptr) {
+                                           long long cap, int lane, int *mailbox = nullptr) {
     // `cap` bounds every state index before it is dereferenced: the scout races with the builder and may read a
     // record whose initialisation is not visible yet (stale memory), so nothing it reads is trusted as an address
     if (k > SCOUT_MAX_TOKENS) return;                                        // long appends (prefill): nothing useful to scout
@@ -446,11 +446,11 @@ __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slo
             }
         }
         if (!kStatic && mailbox && i < k && lane == 0) {     // every token gets an entry (stop 0 = nothing to look up)
-            mailbox[4 * i + 0] = up_state;
-            mailbox[4 * i + 1] = tok;
-            mailbox[4 * i + 2] = up_target;
+            atomicExch(&mailbox[4 * i + 0], up_state);       // (atomics: a defined hand-off between two warps of the CTA)
+            atomicExch(&mailbox[4 * i + 1], tok);
+            atomicExch(&mailbox[4 * i + 2], up_target);
             __threadfence_block();
-            mailbox[4 * SCOUT_MAX_TOKENS] = i + 1;
+            atomicExch(&mailbox[4 * SCOUT_MAX_TOKENS], i + 1);
         }
     }
     if (peek < 0) return;
@@ -464,26 +464,33 @@ __device__ __forceinline__ void scout_walk(const int32_t *recs, const uint4 *slo
 // copy-heavy streams) it re-points that edge at the states further up the suffix chain - a cold pointer chase that
 // neither the cursor's walk nor the first scout has touched.  This warp takes (stop above, token, target) hand-offs
 // from the first scout and looks the next few stops up, so that their records and buckets are in cache.
-__device__ __forceinline__ void redirect_scout(const int32_t *recs, const uint4 *slots, uint32_t bmask, volatile int *mailbox,
+__device__ __forceinline__ void redirect_scout(const int32_t *recs, const uint4 *slots, uint32_t bmask, int *mailbox,
                                                int k, long long cap, int lane) {
     if (k > SCOUT_MAX_TOKENS) return;
     for (int i = 0; i < k; ++i) {
         int have = 0;
         if (lane == 0) {
             while (true) {
-                if (mailbox[4 * SCOUT_MAX_TOKENS] > i) {
+                if (atomicAdd(&mailbox[4 * SCOUT_MAX_TOKENS], 0) > i) {
                     have = 1;
                     break;
                 }
-                if (mailbox[4 * SCOUT_MAX_TOKENS + 1]) break;   // the first scout is done and never got this far
+                if (atomicAdd(&mailbox[4 * SCOUT_MAX_TOKENS + 1], 0)) break;   // the first scout is done and never got this far
                 __nanosleep(40);
             }
         }
         have = __shfl_sync(SAMD_FULL, have, 0);
         if (!have) return;
         __threadfence_block();
-        int pp = mailbox[4 * i + 0];
-        const int tok = mailbox[4 * i + 1], target = mailbox[4 * i + 2];
+        int pp = 0, tok = 0, target = 0;
+        if (lane == 0) {
+            pp = atomicAdd(&mailbox[4 * i + 0], 0);
+            tok = atomicAdd(&mailbox[4 * i + 1], 0);
+            target = atomicAdd(&mailbox[4 * i + 2], 0);
+        }
+        pp = __shfl_sync(SAMD_FULL, pp, 0);
+        tok = __shfl_sync(SAMD_FULL, tok, 0);
+        target = __shfl_sync(SAMD_FULL, target, 0);
         for (int up = 0; up < 6 && pp > 0 && (unsigned long long)pp < (unsigned long long)cap; ++up) {
             const Look ru = warp_look<false>(recs, slots, bmask, pp, tok, lane);
             if (!ru.found || ru.target != target) break;
@@ -511,7 +518,7 @@ __global__ void __launch_bounds__(128) sam_step_kernel(StepParams P) {
                               (long long)P.dyn.s_cap, lane, blockDim.x > 96 ? s_mailbox : nullptr);
             if (lane == 0) {                                  // whatever path the scout left by: no more hand-offs
                 __threadfence_block();
-                reinterpret_cast<volatile int *>(s_mailbox)[4 * SCOUT_MAX_TOKENS + 1] = 1;
+                atomicExch(&s_mailbox[4 * SCOUT_MAX_TOKENS + 1], 1);
             }
         } else if (threadIdx.x >= 96) {
             redirect_scout(P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC, P.dyn.slots + (size_t)r * P.dyn.h_cap, P.dyn.bmask, s_mailbox,
