@@ -739,7 +739,9 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     SAMD_REQUIRE(!a->tokens_dev || a->token_stride > 0, "samd_step: token_stride must be positive");
     SAMD_REQUIRE(!a->out_draft_dev || a->draft_stride >= a->n_predicts, "samd_step: draft_stride < n_predicts");
     // warp 0 builds, warp 1 scouts the dynamic automaton, warp 2 the static one (if any), warp 3 the clones' redirect walks
-    const int threads = g_scouts ? (a->tokens_dev && g_scouts > 1 ? 128 : (P.has_static ? 96 : 64)) : 32;
+    // (with a static automaton the redirect scout is left out: measured on c3, 4096 mostly static-drafting requests, it
+    // costs more than it brings - 49.2 vs 43.2 us per step)
+    const int threads = g_scouts ? (P.has_static ? 96 : (a->tokens_dev && g_scouts > 1 ? 128 : 64)) : 32;
     if (P.dbg_cycles) sam_step_kernel<true><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
     else sam_step_kernel<false><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
     samd_count_launch();
