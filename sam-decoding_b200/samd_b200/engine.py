@@ -279,9 +279,9 @@ class DraftEngine:
         and replayed as one graph launch.  Measured on B200 at 1024 requests, host to host: 45.9 us per step
         zero-copy, 53.4 zero-copy in + copy out, 65.6 with both copies.  By default waits until `out` is complete."""
         # same buffers and settings as the last call: replay at once (the check below costs a few microseconds)
-        quick = (inp, out, self.n_predicts, self.len_bias, self.len_threshold, self.alpha, zero_copy)
-        last = getattr(self, "_host_quick", None)
-        if last is not None and all(x is y or x == y for x, y in zip(quick[2:], last[2:])) and inp is last[0] and out is last[1]:
+        quick = (self.n_predicts, self.len_bias, self.len_threshold, self.alpha, zero_copy)
+        last = self.__dict__.get("_host_quick")
+        if last is not None and inp is last[0] and out is last[1] and quick == last[2]:
             self._host_graph.replay()
             if sync:
                 torch.cuda.current_stream(self.dyn.device).synchronize()
@@ -304,7 +304,7 @@ class DraftEngine:
             with torch.cuda.graph(g):
                 work()
             self._host_graph, self._host_graph_key = g, key
-        self._host_quick = quick
+        self._host_quick = (inp, out, quick)
         self._host_graph.replay()
         if sync:
             torch.cuda.current_stream(self.dyn.device).synchronize()
