@@ -93,3 +93,26 @@ def test_reference_pickle_converter_host_side():
     out = np.zeros((sam.n_edges, 3), dtype=np.int32)
     K.check(K.lib().samd_static_export_edges(sam.handle, p(out), None))
     assert np.array_equal(out, edges)                     # per-state insertion order survives the round trip
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/samd_b200.h must compile as C99 on its own (no C++-isms, no torch / CUDA
+    types), and a C translation unit that references every declared entry point must link against the library."""
+    import shutil
+    import subprocess
+    from samd_b200 import _cabi as K
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    header = os.path.join(REPO, "include", "samd_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", header], check=True)
+    names = _declared_symbols()
+    src = tmp_path / "link_all.c"
+    src.write_text('#include "samd_b200.h"\n#include <stdio.h>\nint main(void) {\n    void *p[] = {%s};\n'
+                   '    printf("%%d %%d\\n", (int)(sizeof(p) / sizeof(p[0])), samd_abi_version());\n    return 0;\n}\n'
+                   % ", ".join("(void *)%s" % n for n in names))
+    exe = tmp_path / "link_all"
+    libdir = os.path.dirname(K.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lsamd_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == len(names) and int(out[1]) == K.lib().samd_abi_version()
