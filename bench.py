@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--only-static", action="store_true", help="run only the c3 static-SAM measurement (e.g. at 50M tokens)")
     ap.add_argument("--only-verify", action="store_true", help="profiling aid: run only the c4 verify loop")
     ap.add_argument("--only-step", action="store_true", help="profiling aid: run only the c2 device loop")
+    ap.add_argument("--variant", type=int, default=1, help="step kernel variant: 1 = one thread per request (default), 0 = warp-cooperative (round 1)")
     return ap.parse_args()
 
 
@@ -255,6 +256,7 @@ def run_ours(a):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     K.require_device()
+    K.lib().samd_step_set_variant(a.variant)
     launches0 = E.launch_count()
     if a.only_verify:                         # profiling aid (ncu): just the c4 loop
         print(json.dumps({"verify": bench_verify(a, dev, 6458.1, iters=6, warm=2)}))

@@ -72,7 +72,8 @@ int samd_dyn_copy(samd_dyn_t dst, samd_dyn_t src, void *stream);
  * old handle stays valid and must still be destroyed by the caller. */
 int samd_dyn_grow(samd_dyn_t old_handle, int new_max_tokens, samd_dyn_t *out);
 /* Sums over requests (synchronises): out[8] = {n_states, tokens, n_edges, n_clones, transition
- * probes spent in add_tokens, probes spent in lookups, overflowed requests, 0}. */
+ * probes spent in add_tokens, probes spent in lookups, requests whose arena was full when a token arrived (grow with
+ * samd_dyn_grow), requests that were handed a negative token (refused: -1 marks a free edge slot in the layout)}. */
 int samd_dyn_stats(samd_dyn_t h, int64_t *out_host);
 /* Every request's 16 meta words {n_states, last, max_length, cur_index, cur_length, n_edges, overflow, n_clones,
  * suffix-link hops, probes, ...} to the host (synchronises): per-request counters for profiling. */
@@ -175,6 +176,13 @@ int samd_step(const samd_step_args *args, void *stream);
 void samd_step_set_debug_cycles(int64_t *cycles_dev);
 /* tuning hook: scout (prefetcher) warps of samd_step - 0 none, 1 the cursor scouts, 2 (default) also the redirect scout */
 void samd_step_set_scouts(int on);
+/* kernel variant of samd_step: 1 (default) = one thread per request walks, records held in its registers
+ * (csrc/sam_scalar.cuh); 0 = the warp-cooperative probe of round 1.  Same results; kept for A/B measurements. */
+void samd_step_set_variant(int variant);
+/* profiling hook (variant 1): when non-NULL, every samd_step launch writes, per request, trace_dev[r][0] = the number of
+ * state records its builder read and trace_dev[r][1..] = their state indices in order (capacity `cap` words per
+ * request) - the request's dependent-load chain, replayed as bare loads by samd_debug_replay_trace. */
+void samd_step_set_trace(int32_t *trace_dev, int cap);
 
 /* Cursor-only walks.  samd_static_walk = StaticSAM.transfer_tokens (static_sam.py:102-104) when
  * tokens_dev != NULL, then StaticSAM.lookup (:106-109) when peek_tok_dev != NULL (non-mutating).
@@ -297,6 +305,11 @@ int samd_kv_compact(void *const *kv_ptrs_dev, int32_t n_kv, int32_t n_heads, int
 /* profiling aid: n_warps warps each chase `hops` dependent pointers through n_records 64-byte records
  * (record word 0 = next index); measures dependent-load latency at the step kernel's concurrency */
 int samd_debug_pointer_chase(const void *recs_dev, int64_t n_records, int n_warps, int hops, int32_t *sink_dev, void *stream);
+/* profiling aid: the floor of samd_step's dependent-load chain.  One thread per request of `h` reads the records listed
+ * in trace_dev (layout of samd_step_set_trace) one after the other, every address depending on the previous load's
+ * value; with_scout != 0 adds a second thread per request that runs ahead through the same list with independent
+ * loads (an ideal prefetcher).  cycles_dev[r] = SM cycles of request r's chain. */
+int samd_debug_replay_trace(samd_dyn_t h, const int32_t *trace_dev, int cap, int with_scout, int64_t *cycles_dev, void *stream);
 /* number of kernel launches the library has issued (for bench.py's gpu_launches) */
 int64_t samd_launch_count(void);
 

@@ -2,6 +2,7 @@
 // One CTA per request - a builder warp and up to three read-only scout warps that run ahead of it; see
 // include/samd_b200.h for the reference methods each entry replaces.
 #include "samd_common.cuh"
+#include "sam_scalar.cuh"
 #include "../../include/samd_b200.h"
 
 #include <cstdlib>
@@ -31,6 +32,7 @@ __global__ void dyn_reset_kernel(DynArena a, const uint8_t *mask) {
         for (int i = 0; i < META_WORDS; ++i) m[i] = 0;
         m[META_NSTATES] = 1;
         m[META_LASTLINK] = -1;
+        m[META_LLTWIN] = -1;
     }
 }
 
@@ -85,7 +87,8 @@ extern "C" int samd_dyn_copy(samd_dyn_t dst, samd_dyn_t src, void *stream) {
 }
 
 extern "C" int samd_dyn_stats(samd_dyn_t h, int64_t *out) {
-    // out[8] = sums over requests of {n_states, max_length, n_edges, n_clones, extend probes, lookup probes, overflow, 0}
+    // out[8] = sums over requests of {n_states, max_length, n_edges, n_clones, extend probes, lookup probes,
+    //          requests whose arena overflowed, requests that were handed a negative token}
     SAMD_REQUIRE(h && out, "samd_dyn_stats: bad arguments");
     SAMD_CUDA(cudaDeviceSynchronize());
     const size_t n = (size_t)h->a.n_requests * META_WORDS;
@@ -100,7 +103,8 @@ extern "C" int samd_dyn_stats(samd_dyn_t h, int64_t *out) {
         out[3] += q[META_NCLONES];
         out[4] += q[META_HOPS];
         out[5] += q[META_PROBES];
-        out[6] += q[META_OVERFLOW];
+        out[6] += q[META_OVERFLOW] & 1;
+        out[7] += (q[META_OVERFLOW] >> 1) & 1;
     }
     free(m);
     return 0;
@@ -154,7 +158,7 @@ extern "C" int samd_dyn_export(samd_dyn_t h, int request, int32_t *meta_host, in
 // online append with clone-on-split (dyn_sam.py:41-67); registers are warp-uniform
 // ---------------------------------------------------------------------------------------
 struct DynRegs {
-    int n_states, last, last_link, n, cur, cur_len, n_edges, n_clones, hops;
+    int n_states, last, last_link, n, cur, cur_len, n_edges, n_clones, hops, max_chain;
 };
 
 // add the out-edge state --tok--> target, given the (failed) look-up `r` of (state, tok)
@@ -400,6 +404,8 @@ struct StepParams {
     int32_t *out_type, *out_match_dyn, *out_match_static, *out_index_dyn, *out_index_static, *out_draft, *out_draft_len;
     int draft_stride;
     long long *dbg_cycles;      // optional [10][n_requests] per-request SM cycles by phase (profiling hook, see samd_b200.h)
+    int32_t *trace;             // optional [n_requests][trace_cap]: word 0 = count, then the states whose records the builder read
+    int trace_cap;
 };
 
 #define SCOUT_MAX_TOKENS 64
@@ -553,6 +559,7 @@ __global__ void __launch_bounds__(128) sam_step_kernel(StepParams P) {
         g.n_edges = __shfl_sync(SAMD_FULL, m, META_NEDGES);
         g.n_clones = __shfl_sync(SAMD_FULL, m, META_NCLONES);
         g.hops = __shfl_sync(SAMD_FULL, m, META_HOPS);
+        g.max_chain = __shfl_sync(SAMD_FULL, m, META_MAXCHAIN);
     }
     int s_idx = 0, s_len = 0, s_hops = 0;
     if (P.has_static) {
@@ -580,6 +587,7 @@ __global__ void __launch_bounds__(128) sam_step_kernel(StepParams P) {
                 // (static_sam.py:102-104) walks an independent structure, so it goes first too
                 if constexpr (kProf) t_mark = clock64();
                 warp_transfer_chain(recs, slots, bmask, g.cur, g.cur_len, tok, lane, g.hops, s_chain, n_chain, chain_on_edge);
+                g.max_chain = max(g.max_chain, n_chain);
                 if (P.has_static) warp_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, s_idx, s_len, tok, lane, s_hops);
                 if constexpr (kProf) {
                     const long long t = clock64();
@@ -604,6 +612,8 @@ __global__ void __launch_bounds__(128) sam_step_kernel(StepParams P) {
             meta[META_NEDGES] = g.n_edges;
             meta[META_NCLONES] = g.n_clones;
             meta[META_HOPS] = g.hops;
+            meta[META_LLTWIN] = -1;                  // (the one-thread kernel's hint; this kernel does not keep it)
+            meta[META_MAXCHAIN] = g.max_chain;
             if (overflow) meta[META_OVERFLOW] = 1;
             if (P.has_static) {
                 P.static_cursor[2 * r] = s_idx;
@@ -701,9 +711,281 @@ __global__ void __launch_bounds__(128) sam_step_kernel(StepParams P) {
     }
 }
 
+
+// =======================================================================================================
+// Kernel variant 1 (default): one THREAD per request builds, one thread per scout (sam_scalar.cuh).  Same CTA
+// shape as above - warp 0 the builder, warp 1 the cursor scout, warp 2 the redirect scout (or, with a static
+// automaton attached, the static cursor's scout) - but only lane 0 of every warp walks; the builder's other
+// lanes join for the coalesced draft copy.  Every record is four 128-bit loads into one thread's registers, a
+// probe is five compares: no ballot / shuffle between a record's arrival and the next address.
+// =======================================================================================================
+__device__ __forceinline__ bool sc_bad(long long idx, long long cap) { return (unsigned long long)idx >= (unsigned long long)cap; }
+
+// Cursor scout, one thread: transfers only, on the automaton as it is, writes nothing.  The record it loads after a
+// hit is the record the builder's append reads at the end of its chain (and the next token's cursor record).
+template <bool kStatic>
+__device__ __forceinline__ void sc_scout_walk(const int32_t *recs, const uint4 *slots, uint32_t bmask, const int32_t *text,
+                                              int idx, const int32_t *tk, int k, int peek, int n_predicts, long long text_n,
+                                              long long cap, int *mailbox) {
+    if (k > SCOUT_MAX_TOKENS) return;
+    if (sc_bad(idx, cap)) return;
+    const int total = k + (peek >= 0 ? 1 : 0);
+    Rec Y = rec_load<kStatic>(recs, idx);
+    for (int i = 0; i < total; ++i) {
+        const int tok = i < k ? tk[i] : peek;
+        int up_state = 0, up_target = 0;
+        while (true) {
+            const Probe pr = rec_probe<kStatic>(Y, slots, bmask, idx, tok, 4);
+            if (pr.found) {
+                if (!kStatic && i < k) {
+                    // the first stop of a clone's redirect walk: requested without waiting for it
+                    const int up = Y.w[R_LINK];
+                    if (up > 0 && !sc_bad(up, cap)) sc_prefetch_rec(recs, up);
+                    up_state = up;
+                    up_target = pr.target;
+                }
+                idx = sc_bad(pr.target, cap) ? 0 : pr.target;
+                Y = rec_load<kStatic>(recs, idx);
+                break;
+            }
+            if (idx == 0) break;
+            idx = Y.w[R_LINK];
+            if (sc_bad(idx, cap)) idx = 0;
+            Y = rec_load<kStatic>(recs, idx);
+        }
+        if (!kStatic && mailbox && i < k) {                  // every token gets an entry (stop 0 = nothing to look up)
+            atomicExch(&mailbox[4 * i + 0], up_state);
+            atomicExch(&mailbox[4 * i + 1], tok);
+            atomicExch(&mailbox[4 * i + 2], up_target);
+            __threadfence_block();
+            atomicExch(&mailbox[4 * SCOUT_MAX_TOKENS], i + 1);
+        }
+    }
+    if (peek < 0) return;
+    const long long e = Y.w[R_END];                          // the draft is read right after this position
+    if (e >= 0)
+        for (int j = 0; j < n_predicts + 8 && e + 1 + j <= text_n; j += 8) sc_prefetch(text + e + 1 + j);
+}
+
+__device__ __forceinline__ void sc_redirect_scout(const int32_t *recs, const uint4 *slots, uint32_t bmask, int *mailbox, int k,
+                                                  long long cap) {
+    if (k > SCOUT_MAX_TOKENS) return;
+    for (int i = 0; i < k; ++i) {
+        while (true) {
+            if (atomicAdd(&mailbox[4 * SCOUT_MAX_TOKENS], 0) > i) break;
+            if (atomicAdd(&mailbox[4 * SCOUT_MAX_TOKENS + 1], 0)) return;      // the cursor scout is done and never got this far
+            __nanosleep(40);
+        }
+        __threadfence_block();
+        int pp = atomicAdd(&mailbox[4 * i + 0], 0);
+        const int tok = atomicAdd(&mailbox[4 * i + 1], 0);
+        const int target = atomicAdd(&mailbox[4 * i + 2], 0);
+        for (int up = 0; up < 6 && pp > 0 && !sc_bad(pp, cap); ++up) {
+            const Rec Y = rec_load<false>(recs, pp);
+            const Probe pr = rec_probe<false>(Y, slots, bmask, pp, tok, 4);
+            if (!pr.found || pr.target != target) break;
+            pp = Y.w[R_LINK];
+        }
+    }
+}
+
+template <bool kProf>
+__global__ void __launch_bounds__(96, 7) sam_step_scalar_kernel(StepParams P) {
+    __shared__ int s_mailbox[4 * SCOUT_MAX_TOKENS + 2];
+    __shared__ int s_chain[SC_CHAIN_MAX];
+    __shared__ unsigned char s_cfree[SC_CHAIN_MAX];
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (r >= P.dyn.n_requests) return;
+    if (threadIdx.x < 2) s_mailbox[4 * SCOUT_MAX_TOKENS + threadIdx.x] = 0;
+    __syncthreads();
+    int32_t *recs = P.dyn.recs + (size_t)r * P.dyn.s_cap * SAMD_REC;
+    uint4 *slots = P.dyn.slots + (size_t)r * P.dyn.h_cap;
+    int32_t *text = P.dyn.text + (size_t)r * P.dyn.t_cap;
+    int32_t *meta = P.dyn.meta + (size_t)r * META_WORDS;
+    if (threadIdx.x >= 32) {
+        if (lane != 0) return;
+        const int k = P.tokens ? (P.counts ? P.counts[r] : P.token_stride) : 0;
+        const int32_t *tk = P.tokens ? P.tokens + (size_t)r * P.token_stride : nullptr;
+        const int peek = P.start_tok ? P.start_tok[r] : -1;
+        if (threadIdx.x < 64) {
+            sc_scout_walk<false>(recs, slots, P.dyn.bmask, text, meta[META_CUR], tk, k, peek, P.n_predicts, (long long)meta[META_N],
+                                 (long long)P.dyn.s_cap, (blockDim.x > 64 && !P.has_static) ? s_mailbox : nullptr);
+            __threadfence_block();
+            atomicExch(&s_mailbox[4 * SCOUT_MAX_TOKENS + 1], 1);         // whatever path the scout left by: no more hand-offs
+        } else if (P.has_static) {
+            sc_scout_walk<true>(P.st.recs, P.st.slots, P.st.bmask, P.st.text, P.static_cursor[2 * r], tk, k, peek, P.n_predicts,
+                                (long long)P.st.n_tokens, (long long)P.st.n_states, nullptr);
+        } else {
+            sc_redirect_scout(recs, slots, P.dyn.bmask, s_mailbox, k, (long long)P.dyn.s_cap);
+        }
+        return;
+    }
+    // ---- warp 0: lane 0 builds and looks up, then the warp copies the draft ----
+    int o_have = 0, o_n_out = 0, o_endpos = 0, o_text_n = 0, o_src = 0, o_tok = 0;
+    if (lane == 0) {
+        const long long t_begin = kProf ? clock64() : 0;
+        ScBuilder b;
+        b.d.recs = recs;
+        b.d.slots = slots;
+        b.d.text = text;
+        b.d.bmask = P.dyn.bmask;
+        b.d.max_tokens = P.dyn.max_tokens;
+        b.chain = s_chain;
+        b.cfree = s_cfree;
+        b.x_state = -1;
+        b.tr.trace = P.trace ? P.trace + (size_t)r * P.trace_cap + 1 : nullptr;
+        b.tr.cap = P.trace_cap - 1;
+        b.tr.n = 0;
+        {
+            const int4 m0 = *reinterpret_cast<const int4 *>(meta), m1 = *reinterpret_cast<const int4 *>(meta + 4);
+            const int4 m2 = *reinterpret_cast<const int4 *>(meta + 8), m3 = *reinterpret_cast<const int4 *>(meta + 12);
+            b.g.n_states = m0.x; b.g.last = m0.y; b.g.n = m0.z; b.g.cur = m0.w;
+            b.g.cur_len = m1.x; b.g.n_edges = m1.y; b.g.n_clones = m1.w;
+            b.g.hops = m2.x; b.g.last_link = m2.z; b.g.ll_twin = m2.w;
+            b.g.ll_len = m3.x; b.g.ll_link = m3.y; b.g.max_chain = m3.z;
+        }
+        int s_idx = 0, s_len = 0, s_hops = 0;
+        if (P.has_static) {
+            s_idx = P.static_cursor[2 * r];
+            s_len = P.static_cursor[2 * r + 1];
+        }
+        // ---- phase 1: DraftModel.update (draft.py:65-79) ----
+        if (P.tokens) {
+            const int k = P.counts ? P.counts[r] : P.token_stride;
+            const int32_t *tk = P.tokens + (size_t)r * P.token_stride;
+            int flags = 0;
+            for (int i = 0; i < k; ++i) {
+                if ((i & 31) == 0 && i + 32 < k) sc_prefetch(tk + i + 32);
+                const int tok = tk[i];
+                if (tok < 0) {                               // -1 marks a free edge slot in the layout: never a token
+                    flags |= 2;
+                    break;
+                }
+                if (P.has_static) sc_prefetch_rec(P.st.recs, s_idx);
+                if (b.g.n >= P.dyn.max_tokens) {
+                    // arena full: the token cannot be appended (the flag tells the caller to grow); the cursors still
+                    // follow the text so that the lookups keep returning what the automaton knows
+                    flags |= 1;
+                    b.transfer_one(tok);
+                } else {
+                    b.extend_one(tok);                       // add_tokens: match first, then append (dyn_sam.py:84-88)
+                }
+                if (P.has_static) sc_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, s_idx, s_len, tok, s_hops);
+            }
+            *reinterpret_cast<int4 *>(meta) = make_int4(b.g.n_states, b.g.last, b.g.n, b.g.cur);
+            meta[META_CURLEN] = b.g.cur_len;
+            meta[META_NEDGES] = b.g.n_edges;
+            meta[META_NCLONES] = b.g.n_clones;
+            meta[META_HOPS] = b.g.hops;
+            meta[META_LASTLINK] = b.g.last_link;
+            meta[META_LLTWIN] = b.g.ll_twin;
+            meta[META_LLLEN] = b.g.ll_len;
+            meta[META_LLLINK] = b.g.ll_link;
+            meta[META_MAXCHAIN] = b.g.max_chain;
+            if (flags) meta[META_OVERFLOW] |= flags;
+            if (P.has_static) {
+                P.static_cursor[2 * r] = s_idx;
+                P.static_cursor[2 * r + 1] = s_len;
+            }
+        }
+        const long long t_lookup = kProf ? clock64() : 0;
+        // ---- phase 2: DraftModel.lookup (draft.py:52-63 / samd_sam_only/draft.py:49-59) ----
+        if (P.start_tok) {
+            const int tok = P.start_tok[r];
+            int d_idx = 0, d_len = 0, q_hops = 0;
+            b.lookup(tok, d_idx, d_len, q_hops);
+            int t_idx = 0, t_len = 0;
+            if (P.has_static) {
+                t_idx = s_idx;
+                t_len = s_len;
+                sc_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, t_idx, t_len, tok, s_hops);
+            }
+            const int t_biased = t_len - P.len_bias;
+            int type, n_out, endpos = 0, text_n = 0, src = 0;
+            if (P.flavour == SAMD_FLAVOUR_SAMD) {
+                n_out = P.n_predicts;
+                if (max(d_len, t_biased) >= P.len_threshold) {
+                    if (d_len >= t_biased) {
+                        type = SAMD_DRAFT_DYN_SEQ;
+                        endpos = b.anchor_samd(d_idx, P.n_predicts);         // to_anc (dyn_sam.py:99-105)
+                        text_n = b.g.n;
+                    } else {
+                        type = SAMD_DRAFT_STATIC_SEQ;
+                        endpos = __ldg(P.st.recs + (size_t)t_idx * SAMD_REC + R_END);
+                        src = 1;
+                        text_n = (int)P.st.n_tokens;
+                    }
+                } else {
+                    type = SAMD_DRAFT_TREE_MODEL;
+                    n_out = 0;
+                }
+            } else {
+                if (d_len >= t_biased) {
+                    type = SAMD_DRAFT_DYN_SEQ;
+                    const int budget = min(P.n_predicts, 1 + (int)((double)d_len * P.alpha));
+                    endpos = recs[(size_t)d_idx * SAMD_REC + R_END];
+                    text_n = b.g.n;
+                    // [start] + text[e+1 : e+n]  (no padding; samd_sam_only/sam/dyn_sam.py:116-119)
+                    n_out = 1 + max(0, min(endpos + budget, text_n + 1) - (endpos + 1));
+                } else {
+                    type = SAMD_DRAFT_STATIC_TREE;
+                    n_out = 0;
+                }
+            }
+            if (P.out_type) P.out_type[r] = type;
+            if (P.out_match_dyn) P.out_match_dyn[r] = d_len;
+            if (P.out_match_static) P.out_match_static[r] = t_len;
+            if (P.out_index_dyn) P.out_index_dyn[r] = d_idx;
+            if (P.out_index_static) P.out_index_static[r] = t_idx;
+            if (P.out_draft_len) P.out_draft_len[r] = n_out;
+            meta[META_PROBES] += q_hops;
+            o_have = 1; o_n_out = n_out; o_endpos = endpos; o_text_n = text_n; o_src = src; o_tok = tok;
+        }
+        if (b.tr.trace) b.tr.trace[-1] = b.tr.n;
+        if constexpr (kProf) {
+            if (P.start_tok) {
+                const long long t = clock64();
+                const size_t n = (size_t)P.dyn.n_requests;
+                const long long v[10] = {t - t_begin, 0, t_lookup - t_begin, t - t_lookup, 0, 0, 0, 0, 0, 0};
+                for (int i = 0; i < 10; ++i) P.dbg_cycles[i * n + r] = v[i];
+            }
+        }
+    }
+    __syncwarp();
+    o_have = __shfl_sync(SAMD_FULL, o_have, 0);
+    if (!o_have || !P.out_draft) return;
+    o_n_out = __shfl_sync(SAMD_FULL, o_n_out, 0);
+    o_endpos = __shfl_sync(SAMD_FULL, o_endpos, 0);
+    o_text_n = __shfl_sync(SAMD_FULL, o_text_n, 0);
+    o_src = __shfl_sync(SAMD_FULL, o_src, 0);
+    o_tok = __shfl_sync(SAMD_FULL, o_tok, 0);
+    const int32_t *src = o_src ? P.st.text : text;
+    int32_t *dr = P.out_draft + (size_t)r * P.draft_stride;
+    for (int j = lane; j < P.draft_stride; j += 32) {
+        int v = 0;
+        if (j < o_n_out) {
+            if (j == 0) v = o_tok;
+            else {
+                const int pos = o_endpos + j;
+                v = (pos <= o_text_n) ? src[pos] : 0;         // zero padding past the end of the text
+            }
+        }
+        dr[j] = v;
+    }
+}
+
 static long long *g_dbg_cycles = nullptr;
 static int g_scouts = 2;
+static int g_variant = 1;
+static int32_t *g_trace = nullptr;
+static int g_trace_cap = 0;
 extern "C" void samd_step_set_scouts(int on) { g_scouts = on; }
+extern "C" void samd_step_set_variant(int v) { g_variant = v; }
+extern "C" void samd_step_set_trace(int32_t *trace_dev, int cap) {
+    g_trace = trace_dev;
+    g_trace_cap = trace_dev ? cap : 0;
+}
 extern "C" void samd_step_set_debug_cycles(int64_t *cycles_dev) { g_dbg_cycles = (long long *)cycles_dev; }
 
 extern "C" int samd_step(const samd_step_args *a, void *stream) {
@@ -735,12 +1017,23 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     P.out_draft_len = a->out_draft_len_dev;
     P.draft_stride = a->draft_stride;
     P.dbg_cycles = g_dbg_cycles;
+    P.trace = g_trace;
+    P.trace_cap = g_trace_cap;
     SAMD_REQUIRE(a->flavour == SAMD_FLAVOUR_SAMD || a->flavour == SAMD_FLAVOUR_SAM_ONLY, "samd_step: bad flavour");
     SAMD_REQUIRE(!a->tokens_dev || a->token_stride > 0, "samd_step: token_stride must be positive");
     SAMD_REQUIRE(!a->out_draft_dev || a->draft_stride >= a->n_predicts, "samd_step: draft_stride < n_predicts");
     // warp 0 builds, warp 1 scouts the dynamic automaton, warp 2 the static one (if any), warp 3 the clones' redirect walks
     // (with a static automaton the redirect scout is left out: measured on c3, 4096 mostly static-drafting requests, it
     // costs more than it brings - 49.2 vs 43.2 us per step)
+    if (g_variant == 1) {
+        // builder + cursor scout + (static cursor scout | redirect scout); one walking thread per warp
+        const int threads = g_scouts ? ((P.has_static || (a->tokens_dev && g_scouts > 1)) ? 96 : 64) : 32;
+        if (P.dbg_cycles) sam_step_scalar_kernel<true><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
+        else sam_step_scalar_kernel<false><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
+        samd_count_launch();
+        SAMD_CUDA(cudaGetLastError());
+        return 0;
+    }
     const int threads = g_scouts ? (P.has_static ? 96 : (a->tokens_dev && g_scouts > 1 ? 128 : 64)) : 32;
     if (P.dbg_cycles) sam_step_kernel<true><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
     else sam_step_kernel<false><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
@@ -1056,5 +1349,41 @@ extern "C" int samd_dyn_grow(samd_dyn_t old, int new_max_tokens, samd_dyn_t *out
     free(sl);
     free(nsl);
     *out = nw;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Floor of the step's dependent-load chain (profiling aid, tools/step_floor.py): replay a request's recorded
+// sequence of record reads as bare loads, each address made to depend on the previous load's value.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) replay_trace_kernel(DynArena a, const int32_t *trace, int cap, long long *cycles) {
+    const int r = blockIdx.x;
+    if (r >= a.n_requests || (threadIdx.x & 31) != 0) return;
+    const int32_t *recs = a.recs + (size_t)r * a.s_cap * SAMD_REC;
+    const int32_t *tr = trace + (size_t)r * cap;
+    const int n = min(tr[0], cap - 1);
+    if (threadIdx.x >= 32) {                               // the ideal scout: the same records, independent loads
+        for (int i = 0; i < n; ++i) {
+            const int s = tr[1 + i];
+            if (!sc_bad(s, a.s_cap)) sc_prefetch_rec(recs, s);
+        }
+        return;
+    }
+    const long long t0 = clock64();
+    int acc = 0;
+    for (int i = 0; i < n; ++i) {
+        const int s = tr[1 + i] + (acc & 0x40000000);      // always + 0 (record words are < 2^30), but the compiler cannot know
+        const Rec Y = rec_load<false>(recs, sc_bad(s, a.s_cap) ? 0 : s);
+        acc = Y.w[R_LEN] | Y.w[R_TOK + 4];
+    }
+    cycles[r] = clock64() - t0 + (acc & 0x40000000);
+}
+
+extern "C" int samd_debug_replay_trace(samd_dyn_t h, const int32_t *trace_dev, int cap, int with_scout, int64_t *cycles_dev,
+                                       void *stream) {
+    SAMD_REQUIRE(h && trace_dev && cap > 1 && cycles_dev, "samd_debug_replay_trace: bad arguments");
+    replay_trace_kernel<<<h->a.n_requests, with_scout ? 64 : 32, 0, (cudaStream_t)stream>>>(h->a, trace_dev, cap, (long long *)cycles_dev);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
     return 0;
 }

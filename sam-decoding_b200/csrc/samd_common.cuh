@@ -31,7 +31,11 @@
 enum { R_LINK = 0, R_LEN = 1, R_END = 2, R_OHEAD = 3, R_TOK = 4, R_TGT = 9, R_OTAIL = 14, R_AUX = 15 };
 
 enum { META_NSTATES = 0, META_LAST = 1, META_N = 2, META_CUR = 3, META_CURLEN = 4, META_NEDGES = 5,
-       META_OVERFLOW = 6, META_NCLONES = 7, META_HOPS = 8, META_PROBES = 9, META_LASTLINK = 10, META_WORDS = 16 };
+       META_OVERFLOW = 6, META_NCLONES = 7, META_HOPS = 8, META_PROBES = 9, META_LASTLINK = 10,
+       // when the newest append split a state: last_link is the clone, LLTWIN the state it copied (-1 = none), see sam_scalar.cuh
+       META_LLTWIN = 11, META_LLLEN = 12, META_LLLINK = 13,
+       META_MAXCHAIN = 14,    // longest cursor fallback chain any append of this request has seen (test / profiling counter)
+       META_WORDS = 16 };
 
 __host__ __device__ __forceinline__ uint32_t samd_hash(uint32_t state, uint32_t tok) {
     uint32_t h = state * 0x9E3779B1u + tok * 0x85EBCA77u;

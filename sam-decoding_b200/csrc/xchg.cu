@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(32) xchg_lookup_kernel(StaticDev st, int32_t *
         const long long e = shard_offset + (long long)__ldg(st.recs + (size_t)idx * SAMD_REC + R_END);
         key = ((unsigned long long)len << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)e);
     }
-    if (key != 0 && lane < X.world) atomicMax(X.keys[lane] + (size_t)par * X.n + r, key);   // one (remote) atomic per rank
+    // one atomic per rank, remote over NVLink for the peers: system scope, the only scope that is defined across GPUs
+    if (key != 0 && lane < X.world) atomicMax_system(X.keys[lane] + (size_t)par * X.n + r, key);
     __syncwarp();
     if (lane == 0) {
         __threadfence_system();                                               // this block's atomics, before it counts
@@ -154,7 +155,9 @@ __global__ void xchg_draft_kernel(XchgView X, const int32_t *corpus, long long n
         const volatile int *f = X.flags[X.rank] + threadIdx.x;
         unsigned long long t0 = 0, t = 0;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-        while (*f != epoch) {
+        // flags only ever grow, and a peer may already be one step ahead (its look-up of step e+1 can finish before this
+        // kernel starts polling; the two key buffers cover exactly that skew): wait until the flag has REACHED the epoch
+        while ((int)(*f - epoch) < 0) {
             __nanosleep(100);
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
             if (t - t0 > 5000000000ull) {                                     // a peer is gone: give up after 5 s, flag it

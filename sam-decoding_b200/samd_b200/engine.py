@@ -66,6 +66,23 @@ class DynSamBatch:
                     n_edges=int(meta[5]), overflow=int(meta[6]), n_clones=int(meta[7]), link=link[:ns], length=length[:ns],
                     min_endpos=endpos[:ns], text=text[:n + 1])
 
+    def export_edges(self, request: int) -> np.ndarray:
+        """[n_edges, 3] (state, token, target) of one request, per state in insertion order (synchronises)."""
+        n_edges = int(self.meta()[request, 5])
+        out = np.zeros((max(n_edges, 1), 3), dtype=np.int32)
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_dyn_export_edges(self._h, int(request), out.ctypes.data_as(K.c_i32p), n_edges), "samd_dyn_export_edges")
+        return out[:n_edges]
+
+    def meta(self) -> np.ndarray:
+        """[n_requests, 16] meta words of every request (synchronises): n_states, last, max_length, cur_index, cur_length,
+        n_edges, overflow flags (1 = arena full, 2 = negative token), n_clones, link hops, lookup probes, last_link, ...,
+        [14] = the longest cursor fallback chain seen."""
+        m = np.zeros((self.n_requests, 16), dtype=np.int32)
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_dyn_meta(self._h, m.ctypes.data_as(K.c_i32p)), "samd_dyn_meta")
+        return m
+
     def grown(self, new_max_tokens: int) -> "DynSamBatch":
         """A new batch with a larger capacity holding the same automata (samd_dyn_grow)."""
         new = DynSamBatch.__new__(DynSamBatch)
@@ -84,7 +101,7 @@ class DynSamBatch:
         out = np.zeros(8, dtype=np.int64)
         with torch.cuda.device(self.device):
             K.check(K.lib().samd_dyn_stats(self._h, out.ctypes.data_as(K.c_i64p)), "samd_dyn_stats")
-        keys = ("n_states", "tokens", "n_edges", "n_clones", "extend_probes", "lookup_probes", "overflowed")
+        keys = ("n_states", "tokens", "n_edges", "n_clones", "extend_probes", "lookup_probes", "overflowed", "bad_tokens")
         return {k: int(v) for k, v in zip(keys, out)}
 
     def close(self):
