@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--only-static", action="store_true", help="run only the c3 static-SAM measurement (e.g. at 50M tokens)")
     ap.add_argument("--only-verify", action="store_true", help="profiling aid: run only the c4 verify loop")
     ap.add_argument("--only-step", action="store_true", help="profiling aid: run only the c2 device loop")
+    ap.add_argument("--scouts", type=int, default=2, help="profiling aid: scout warps of the step kernel (0 none, 1 cursor scouts, 2 all)")
+    ap.add_argument("--prewalk", type=int, default=None, help="tuning aid: draft tokens the scouts walk ahead for the next step")
     ap.add_argument("--variant", type=int, default=1, help="step kernel variant: 1 = one thread per request (default), 0 = warp-cooperative (round 1)")
     return ap.parse_args()
 
@@ -169,6 +171,55 @@ def _cpu_worker(job):
     return run(w0, w1)
 
 
+class _NoTree:
+    """Stand-in for the tree-model fallback of samd's DraftModel (Token Recycle / EAGLE are outside the c2 metric; the GPU
+    arm also only reports `type = tree model` for those queries): gen_draft answers at once."""
+
+    def reset(self):
+        pass
+
+    def update(self, **kwargs):
+        pass
+
+    def gen_draft(self, start_token):
+        return [start_token], {}
+
+
+def _cpu_worker_ref(job):
+    """The same block of work through the reference's OWN classes (samd.DynSAM + samd.DraftModel.lookup), loaded
+    unmodified from baseline/_ref."""
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import ref_loader
+    assert ref_loader.use_staged(), "baseline/_ref is missing: python baseline/stage_reference.py"
+    with contextlib.redirect_stdout(io.StringIO()):
+        ns = ref_loader.load()
+        cfg = ns.samd_config.SamdConfig(n_predicts=N_PREDICTS, len_bias=LEN_BIAS, len_threshold=LEN_THRESHOLD)
+    streams, counts, tokens, start, prompt, w0, w1 = job
+    drafts = []
+    for s in streams:
+        d = ns.samd_draft.DraftModel(cfg, tree_model=_NoTree(), lm=None, device="cpu")     # NullStaticSAM, fresh DynSAM
+        d.reset()
+        d.sam_dyn.add_tokens(s[:prompt].tolist())
+        drafts.append(d)
+    R = len(drafts)
+
+    def run(step_lo, step_hi):
+        t0 = time.perf_counter()
+        for s in range(step_lo, step_hi):
+            for r in range(R):
+                d = drafts[r]
+                tk = tokens[s, r, :counts[s, r]].tolist()
+                d.sam_dyn.add_tokens(tk)               # DraftModel.update (samd/draft.py:65-79) minus the tree model
+                d.sam_static.transfer_tokens(tk)
+                d.lookup(int(start[s, r]))             # samd/draft.py:52-63
+        return time.perf_counter() - t0
+
+    run(0, w0)
+    return run(w0, w1)
+
+
 def _cpu_worker_c(job):
     """Same block of work through the oracle's C restatement (oracle/sam_oracle.c)."""
     import ctypes as C
@@ -205,25 +256,38 @@ def cpu_arm(n_sample, prompt, steps, warmup, seed0, cores, worker=None):
     return n_sample * steps / wall, wall, len(jobs)
 
 
+def have_staged_reference():
+    return os.path.isdir(os.path.join(REPO, "baseline", "_ref", "samd", "sam"))
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = min(os.cpu_count() or 1, 32)
+    real = have_staged_reference()
     # bounded sample: a step of the reference arm is one pass over `n_sample` requests of the c2 workload
-    n_sample = cores * 64
+    n_sample = cores * (16 if real else 64)
     steps = min(a.steps, 256)
     warm = min(a.warmup, 4)
     t0 = time.time()
-    qps, wall, used = cpu_arm(n_sample, a.prompt, steps, warm, 2000, cores)
+    qps, wall, used = cpu_arm(n_sample, a.prompt, steps, warm, 2000, cores, worker=_cpu_worker_ref if real else None)
+    if real:
+        kind = "reference"
+        what = ("the reference's own classes, unmodified, from baseline/_ref: samd.DraftModel with a fresh samd.DynSAM and "
+                "NullStaticSAM per request - sam_dyn.add_tokens + sam_static.transfer_tokens + DraftModel.lookup per step (the "
+                "tree-model fallback stubbed out, as in the GPU arm), one Python process per core")
+    else:
+        kind = "port"
+        what = ("baseline/_ref not staged on this machine: oracle/samd_oracle.py, the Python port of samd DynSAM + "
+                "DraftModel.lookup, one process per core")
     out = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": workload_config(a, a.requests),   # the GPU arm's config; the bounded sample is described in cpu_baseline
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": used, "kind": "port",
-                         "sample": f"{n_sample} requests x {steps} steps of the c2 workload (prefill untimed), "
-                                   f"oracle/samd_oracle.py Python port of samd DynSAM + DraftModel.lookup, one process per core"},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": used, "kind": kind,
+                         "sample": f"{n_sample} requests x {steps} steps of the c2 workload (prefill untimed); {what}"},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.time() - t0,
     }
@@ -257,6 +321,9 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
     K.require_device()
     K.lib().samd_step_set_variant(a.variant)
+    K.lib().samd_step_set_scouts(a.scouts)
+    if a.prewalk is not None:
+        K.lib().samd_step_set_prewalk(a.prewalk)
     launches0 = E.launch_count()
     if a.only_verify:                         # profiling aid (ncu): just the c4 loop
         print(json.dumps({"verify": bench_verify(a, dev, 6458.1, iters=6, warm=2)}))

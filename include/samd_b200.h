@@ -171,14 +171,20 @@ typedef struct samd_step_args {
 
 int samd_step(const samd_step_args *args, void *stream);
 /* profiling hook: when non-NULL, every samd_step launch that performs a lookup writes each request's SM
- * cycle counts to cycles_dev[10][n_requests]: whole request, cursor transfers, appends, lookup + draft, then inside the
- * appends: chain look-ups, edge inserts, (unused), target record, clone overflow copy, clone redirect walk */
+ * cycle counts to cycles_dev[12][n_requests].  Variant 0: whole request, cursor transfers, appends, lookup + draft, then
+ * inside the appends: chain look-ups, edge inserts, (unused), target record, clone overflow copy, clone redirect walk.
+ * Variant 1: whole request, cycles waiting for record loads, update phase, lookup phase, number of record loads that took
+ * < 120 / < 500 / < 1100 / more cycles, overflow-probe cycles and count, then %globaltimer (ns) at the builder's start and
+ * end (rows 10, 11). */
 void samd_step_set_debug_cycles(int64_t *cycles_dev);
 /* tuning hook: scout (prefetcher) warps of samd_step - 0 none, 1 the cursor scouts, 2 (default) also the redirect scout */
 void samd_step_set_scouts(int on);
 /* kernel variant of samd_step: 1 (default) = one thread per request walks, records held in its registers
  * (csrc/sam_scalar.cuh); 0 = the warp-cooperative probe of round 1.  Same results; kept for A/B measurements. */
 void samd_step_set_variant(int variant);
+/* tuning hook (variant 1): after a step's lookup the cursor scouts keep walking along the first n draft tokens - the path
+ * the NEXT step's accepted tokens will most likely take - so that its records are in L2 by then.  0 = off. */
+void samd_step_set_prewalk(int n_tokens);
 /* profiling hook (variant 1): when non-NULL, every samd_step launch writes, per request, trace_dev[r][0] = the number of
  * state records its builder read and trace_dev[r][1..] = their state indices in order (capacity `cap` words per
  * request) - the request's dependent-load chain, replayed as bare loads by samd_debug_replay_trace. */
@@ -308,7 +314,7 @@ int samd_debug_pointer_chase(const void *recs_dev, int64_t n_records, int n_warp
 /* profiling aid: the floor of samd_step's dependent-load chain.  One thread per request of `h` reads the records listed
  * in trace_dev (layout of samd_step_set_trace) one after the other, every address depending on the previous load's
  * value; with_scout != 0 adds a second thread per request that runs ahead through the same list with independent
- * loads (an ideal prefetcher).  cycles_dev[r] = SM cycles of request r's chain. */
+ * loads (an ideal prefetcher).  cycles_dev[3][n_requests] = SM cycles of request r's chain, %globaltimer at its start / end. */
 int samd_debug_replay_trace(samd_dyn_t h, const int32_t *trace_dev, int cap, int with_scout, int64_t *cycles_dev, void *stream);
 /* number of kernel launches the library has issued (for bench.py's gpu_launches) */
 int64_t samd_launch_count(void);

@@ -1,7 +1,8 @@
 """Import the reference's on-path modules from /root/reference WITHOUT running its
 package __init__ (which pulls in the generate loop and fails on transformers >= 5;
-SURVEY.md §8c).  Build-container only: /root/reference does not exist on the GPU box,
-so nothing under tests -m gpu, smoke() or bench.py may call this.
+SURVEY.md §8c).  /root/reference exists in the build container only; on the GPU box the loader
+falls back to the verbatim copy under baseline/_ref (baseline/stage_reference.py), which is what
+bench.py's reference arm times.  tests -m gpu and smoke() never call this.
 
 Used by oracle/gen_golden.py (fixture generation) and by the optional
 `tests/test_oracle_vs_reference.py` differential tests, which skip when the
@@ -14,11 +15,24 @@ import os
 import sys
 import types
 
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED_ROOT = os.path.join(_REPO, "baseline", "_ref")      # verbatim copy made by baseline/stage_reference.py (travels to the GPU box)
 REF_ROOT = os.environ.get("SAMD_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "samd", "sam")) and os.path.isdir(os.path.join(STAGED_ROOT, "samd", "sam")):
+    REF_ROOT = STAGED_ROOT
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "samd", "sam"))
+
+
+def use_staged() -> bool:
+    """Point the loader at baseline/_ref (bench.py's reference arm: the copy that exists on the GPU box too)."""
+    global REF_ROOT
+    if os.path.isdir(os.path.join(STAGED_ROOT, "samd", "sam")):
+        REF_ROOT = STAGED_ROOT
+        return True
+    return False
 
 
 def load():

@@ -24,8 +24,6 @@
 #define SAMD_HD inline
 #endif
 
-#define SC_CHAIN_MAX 64
-
 struct Rec {
     int w[SAMD_REC];
 };
@@ -109,67 +107,58 @@ struct Probe {
     bool     found;
 };
 
-// number of inline edges = index of the first free inline slot (they fill in order); SAMD_INLINE when full
-SAMD_HD int rec_free_inline(const Rec &X) {
-    int f = SAMD_INLINE;
-#pragma unroll
-    for (int i = SAMD_INLINE - 1; i >= 0; --i)
-        if ((uint32_t)X.w[R_TOK + i] == SAMD_EMPTY) f = i;
-    return f;
-}
-
 // (state, tok) in the overflow table: found -> slot / target; else *free_slot = first free slot of its probe
-// sequence.  Nothing is ever deleted, so a probe sequence is a run of used slots followed by a free one.
-// `max_buckets` bounds the search of a reader that races with the writer (scouts); 0 = unbounded.
+// sequence (slot by slot from the first slot of the hashed bucket, wrapping: the same order as "the bucket's slots,
+// then the next bucket").  Nothing is ever deleted, so a probe sequence is a run of used slots followed by a free
+// one, and at the table's load factor (a few percent: only hubs and the root overflow) the first slot decides.
+// `max_slots` bounds the search of a reader that races with the writer (scouts); 0 = unbounded.
 template <bool kRO>
 SAMD_HD bool ovf_find(const uint4 *slots, uint32_t bmask, uint32_t state, uint32_t tok, Probe &r, uint32_t *free_slot,
-                      int max_buckets = 0) {
-    uint32_t b = samd_hash(state, tok) & bmask;
-    for (int nb = 0; max_buckets == 0 || nb < max_buckets; ++nb) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const size_t base = (size_t)b * SAMD_BUCKET + half * 4;
-            uint4 s[4];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) s[l] = slot_load<kRO>(slots, base + l);
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                if (s[l].x == state && s[l].y == tok) {
-                    r.found = true;
-                    r.slot = (uint32_t)(base + l);
-                    r.target = (int)s[l].z;
-                    return true;
-                }
-                if (s[l].x == SAMD_EMPTY) {
-                    if (free_slot) *free_slot = (uint32_t)(base + l);
-                    return false;
-                }
-            }
+                      int max_slots = 0) {
+    const uint32_t smask = (bmask + 1u) * SAMD_BUCKET - 1u;
+    uint32_t i = (samd_hash(state, tok) & bmask) * SAMD_BUCKET;
+    for (int n = 0; max_slots == 0 || n < max_slots; ++n) {
+        const uint4 s = slot_load<kRO>(slots, i);
+        if (s.x == state && s.y == tok) {
+            r.found = true;
+            r.slot = i;
+            r.target = (int)s.z;
+            return true;
         }
-        b = (b + 1) & bmask;
+        if (s.x == SAMD_EMPTY) {
+            if (free_slot) *free_slot = i;
+            return false;
+        }
+        i = (i + 1u) & smask;
     }
     return false;
 }
 
 template <bool kRO>
-SAMD_HD Probe rec_probe(const Rec &X, const uint4 *slots, uint32_t bmask, int state, int tok, int max_buckets = 0) {
+SAMD_HD Probe rec_probe(const Rec &X, const uint4 *slots, uint32_t bmask, int state, int tok, int max_slots = 0) {
+    // a state has at most one edge per token, so at most one of the five compares is true: the target and the index are
+    // OR-ed together from five independent selects (a shallow tree instead of a chain of five dependent ones)
     Probe r;
-    r.target = 0;
-    r.k = -1;
-    r.slot = SAMD_NIL;
-    r.found = false;
+    int tgt = 0, kk = 0;
 #pragma unroll
-    for (int i = 0; i < SAMD_INLINE; ++i)
-        if (X.w[R_TOK + i] == tok) {
-            r.k = i;
-            r.target = X.w[R_TGT + i];
-            r.found = true;
-        }
-    if (!r.found && (uint32_t)X.w[R_OHEAD] != SAMD_NIL) ovf_find<kRO>(slots, bmask, (uint32_t)state, (uint32_t)tok, r, nullptr, max_buckets);
+    for (int i = 0; i < SAMD_INLINE; ++i) {
+        const bool e = X.w[R_TOK + i] == tok;
+        tgt |= e ? X.w[R_TGT + i] : 0;
+        kk |= e ? (i + 1) : 0;
+    }
+    r.target = tgt;
+    r.k = kk - 1;
+    r.slot = SAMD_NIL;
+    r.found = kk != 0;
+    if (!r.found && (uint32_t)X.w[R_OHEAD] != SAMD_NIL) ovf_find<kRO>(slots, bmask, (uint32_t)state, (uint32_t)tok, r, nullptr, max_slots);
     return r;
 }
 
 // ---- the builder -----------------------------------------------------------------------------------------
+// Arena invariants the builder relies on (dyn_reset_kernel / samd_dyn_create establish them, both kernel variants keep
+// them): every record beyond n_states holds the EMPTY TEMPLATE {link -1, length 0, min_endpos 0, no edges, no overflow
+// list, aux 0}, so a new state costs three 4-byte stores; and a record's spare word R_AUX counts its inline edges, so
+// the free inline slot of a state is known from its record without comparing anything.
 struct ScDyn {
     int32_t *recs;
     uint4   *slots;
@@ -178,16 +167,15 @@ struct ScDyn {
     int      max_tokens;
 };
 
-// warp-uniform in the old kernel, thread-private here.  ll_*: when the previous append split a state, last_link is
-// that clone and `ll_twin` the state it was copied from - their inline edges are identical, so a probe of the twin
-// (the cursor's state) answers for the clone as well.
+// ll_*: when the newest append split a state, last_link is that clone and `ll_twin` the state it was copied from -
+// their inline edges are identical, so a probe of the twin (the cursor's state) answers for the clone as well.
 struct ScRegs {
     int n_states, last, last_link, n, cur, cur_len, n_edges, n_clones, hops;
     int ll_twin, ll_len, ll_link;
     int max_chain;
 };
 
-struct ScCounters {            // optional per-request trace of the record reads (floor analysis), see tools/
+struct ScCounters {            // profiling build: per-request trace of the record reads (floor analysis), see tools/
     int32_t *trace;
     int      cap, n;
 };
@@ -200,7 +188,28 @@ struct ScCounters {            // optional per-request trace of the record reads
 enum { SC_ST_ALIGNED = 0, SC_ST_TWIN = 1, SC_ST_GENERIC = 2, SC_ST_LONGCHAIN = 3, SC_ST_OVF_INSERT = 4, SC_ST_OVF_CLONE = 5,
        SC_ST_CARRIED = 6, SC_ST_N = 8 };
 
-struct ScBuilder {
+// cycle counter + a consumer of a load's result, for the profiling build (the clock is read after the data arrived)
+SAMD_HD long long sc_clock() {
+#if defined(__CUDA_ARCH__)
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+#else
+    return 0;
+#endif
+}
+SAMD_HD void sc_consume(int a, int b) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{ .reg .s32 t; add.s32 t, %0, %1; }" ::"r"(a), "r"(b) : "memory");
+#else
+    (void)a; (void)b;
+#endif
+}
+enum { SC_PF_LOAD_CYC = 0, SC_PF_L1 = 1, SC_PF_L2 = 2, SC_PF_DRAM = 3, SC_PF_SLOW = 4, SC_PF_OVF_CYC = 5, SC_PF_OVF_N = 6, SC_PF_N = 8 };
+
+template <bool kProf>
+struct ScBuilderT {
+    long long pf[kProf ? SC_PF_N : 1];   // profiling build: cycles waiting for record loads, loads by latency class, overflow probes
 #ifdef SAMD_SCALAR_STATS
     long long stats[SC_ST_N];
 #endif
@@ -208,13 +217,37 @@ struct ScBuilder {
     ScRegs  g;
     Rec     X;                 // the cursor's record when x_state == g.cur (carried from token to token)
     int     x_state;
-    int    *chain;             // [SC_CHAIN_MAX] states the cursor's walk visited (shared memory on the device)
-    unsigned char *cfree;      // [SC_CHAIN_MAX] their first free inline slot at that time
     ScCounters tr;
 
     SAMD_HD Rec load(int state) {
-        if (tr.trace && tr.n < tr.cap) tr.trace[tr.n++] = state;
-        return rec_load<false>(d.recs, state);
+        if constexpr (kProf) {
+            if (tr.trace && tr.n < tr.cap) tr.trace[tr.n++] = state;
+            const long long t0 = sc_clock();
+            const Rec R = rec_load<false>(d.recs, state);
+            sc_consume(R.w[0], R.w[15]);
+            const long long dt = sc_clock() - t0;
+            pf[SC_PF_LOAD_CYC] += dt;
+            pf[SC_PF_L1] += dt < 120;
+            pf[SC_PF_L2] += dt >= 120 && dt < 500;
+            pf[SC_PF_DRAM] += dt >= 500 && dt < 1100;
+            pf[SC_PF_SLOW] += dt >= 1100;
+            return R;
+        } else {
+            return rec_load<false>(d.recs, state);
+        }
+    }
+    SAMD_HD Probe probe(const Rec &Y, int state, int tok) {
+        if constexpr (kProf) {
+            if ((uint32_t)Y.w[R_OHEAD] != SAMD_NIL) {
+                const long long t0 = sc_clock();
+                const Probe r = rec_probe<false>(Y, d.slots, d.bmask, state, tok);
+                sc_consume(r.target, r.k);
+                pf[SC_PF_OVF_CYC] += sc_clock() - t0;
+                pf[SC_PF_OVF_N] += 1;
+                return r;
+            }
+        }
+        return rec_probe<false>(Y, d.slots, d.bmask, state, tok);
     }
 
     // append (state, tok) -> target to the overflow table and to the state's list (lists run oldest -> newest)
@@ -232,112 +265,106 @@ struct ScBuilder {
         rec[R_OTAIL] = (int)slot;
     }
 
-    SAMD_HD void insert_edge(int state, int free_inline, int tok, int target) {
-        if (free_inline < SAMD_INLINE) {
+    // give `state` (which has `n_inline` inline edges and none on tok) the edge tok -> target
+    SAMD_HD void insert_edge(int state, int n_inline, int tok, int target) {
+        if (n_inline < SAMD_INLINE) {
             int32_t *rec = d.recs + (size_t)state * SAMD_REC;
-            rec[R_TOK + free_inline] = tok;
-            rec[R_TGT + free_inline] = target;
+            rec[R_TOK + n_inline] = tok;
+            rec[R_TGT + n_inline] = target;
+            rec[R_AUX] = n_inline + 1;
         } else {
             SC_STAT(SC_ST_OVF_INSERT);
             ovf_insert(state, tok, target);
         }
     }
 
-    // transfer_cur_state + add_state for one token (dyn_sam.py:84-88: match first, then append)
+    // transfer_cur_state + add_state for one token (dyn_sam.py:84-88: match first, then append).
+    //
+    // The cursor's fallback walk for the token (follow suffix links until a state has an edge on it) visits exactly
+    // the states add_state gives that edge to: add_state walks the suffix chain of `last` from link(last), and the
+    // cursor IS link(last) - or, right after a split, the pre-clone state one stop in front of it.  So the two walks
+    // are ONE: a stop that lacks the edge gets it on the spot, from the record the probe already holds.
     SAMD_HD void extend_one(int tok) {
-        // ---- the cursor's walk (dyn_sam.py:69-78), leaving the states it visits in chain[] ----
         int x = g.cur, len = g.cur_len;
         if (x_state != x) X = load(x);
         else SC_STAT(SC_ST_CARRIED);
-        int n_chain = 0;
+        const int cur = g.n_states;                          // the state this append creates
+        const int last = g.last;
+        const int p0 = last != 0 ? g.last_link : 0;          // first state of add_state's chain that has to be read
+        bool aligned = (x == p0);                            // the cursor's walk is (from here on) add_state's walk
         bool first = true, on_edge = false;
+        int n_chain = 0, n_ins = 0;
         Probe pr;
         while (true) {
-            pr = rec_probe<false>(X, d.slots, d.bmask, x, tok);
-            if (n_chain < SC_CHAIN_MAX) {
-                chain[n_chain] = x;
-                cfree[n_chain] = (unsigned char)rec_free_inline(X);
-            }
+            pr = probe(X, x, tok);
             ++n_chain;
-            ++g.hops;
-            if (!first) len = X.w[R_LEN];                  // length = states[index].length after a link hop
+            if (!first) len = X.w[R_LEN];                    // length = states[index].length after a link hop
             if (pr.found) {
                 on_edge = true;
                 break;
             }
-            if (x == 0) break;
-            x = X.w[R_LINK];
-            X = load(x);
+            if (x == 0) {
+                if (aligned) {
+                    insert_edge(0, X.w[R_AUX], tok, cur);
+                    ++n_ins;
+                }
+                break;
+            }
+            const int nx = X.w[R_LINK];
+            const Rec Xn = load(nx);                         // requested before this stop's stores are issued
+            if (aligned) {
+                insert_edge(x, X.w[R_AUX], tok, cur);
+                ++n_ins;
+            } else if (first && nx == p0) {
+                aligned = true;                              // x was the pre-clone state in front of the chain
+            }
+            x = nx;
+            X = Xn;
             first = false;
         }
+        g.hops += n_chain;
+        if (n_chain > g.max_chain) g.max_chain = n_chain;
         const int new_cur = on_edge ? pr.target : 0;
         const int new_len = on_edge ? len + 1 : 0;
-        if (on_edge) sc_prefetch_rec(d.recs, new_cur);      // the record the append reads at the end of its chain
 
         // ---- add_state (dyn_sam.py:41-67) ----
         g.n += 1;
-        const int cur = g.n_states++;
-        {
-            Rec N;
-#pragma unroll
-            for (int i = 0; i < SAMD_REC; ++i) N.w[i] = 0;
-            N.w[R_LINK] = -1;                               // written at the end
-            N.w[R_LEN] = g.n;
-            N.w[R_END] = g.n;
-            N.w[R_OHEAD] = N.w[R_OTAIL] = -1;
-#pragma unroll
-            for (int i = 0; i < SAMD_INLINE; ++i) N.w[R_TOK + i] = -1;
-            rec_store(d.recs, cur, N);
-        }
-        d.text[g.n] = tok;
-        int p = g.last;
-        if (p != 0) {
+        g.n_states = cur + 1;
+        if (last != 0) {
             // `last` was created by the previous append and has no out-edge yet: its first inline edge needs no read
-            d.recs[(size_t)p * SAMD_REC + R_TOK] = tok;
-            d.recs[(size_t)p * SAMD_REC + R_TGT] = cur;
-            g.n_edges++;
-            p = g.last_link;
+            int32_t *rl = d.recs + (size_t)last * SAMD_REC;
+            rl[R_TOK] = tok;
+            rl[R_TGT] = cur;
+            rl[R_AUX] = 1;
+            ++n_ins;
         }
-        // The cursor's walk visits exactly the states the append gives the edge to - the cursor is link(last), or,
-        // after a split, the pre-clone state one stop in front of it (sam_step.cu) - so the edge is written at all of
-        // them from what the walk saw, without reading anything again.
-        int p_len = 0, p_link = -1;
-        Probe pp;
-        pp.found = false;
-        int s0 = -1;
-        if (n_chain <= SC_CHAIN_MAX) {
-            if (chain[0] == p) s0 = 0;
-            else if (n_chain > 1 && chain[1] == p) s0 = 1;
-        }
-        if (n_chain > SC_CHAIN_MAX) SC_STAT(SC_ST_LONGCHAIN);
-        if (n_chain > g.max_chain) g.max_chain = n_chain;
-        if (s0 >= 0) {
+        g.n_edges += n_ins;
+        int p = -1, p_len = 0, p_link = -1;                  // the chain state that has the edge (-1: none, link -> root)
+        Probe pp = pr;
+        if (aligned) {
             SC_STAT(SC_ST_ALIGNED);
-            const int end = on_edge ? n_chain - 1 : n_chain;           // [s0, end): states without the edge
-            for (int j = s0; j < end; ++j) insert_edge(chain[j], cfree[j], tok, cur);
-            if (end > s0) g.n_edges += end - s0;
             if (on_edge) {
                 p = x;
                 p_len = X.w[R_LEN];
                 p_link = X.w[R_LINK];
-                pp = pr;
-            } else {
-                p = -1;
             }
-        } else if (on_edge && n_chain == 1 && p >= 0 && g.ll_twin == chain[0] && pr.k >= 0) {
-            // last_link is the clone the previous append made of the cursor's state: same inline edges, so the
-            // probe of the cursor's record stands for it
+        } else if (on_edge && n_chain == 1 && last != 0 && g.ll_twin == x && pr.k >= 0) {
+            // last_link is the clone the previous append made of the cursor's state: same inline edges, so the probe
+            // of the cursor's record stands for it
             SC_STAT(SC_ST_TWIN);
+            p = p0;
             p_len = g.ll_len;
             p_link = g.ll_link;
-            pp = pr;
         } else {
+            // the cursor is somewhere else (DynSAM.transfer_tokens moved it, or a kernel boundary dropped the twin
+            // hint): add_state's own walk
             SC_STAT(SC_ST_GENERIC);
+            p = p0;
             while (p != -1) {
                 const Rec P = load(p);
-                const Probe q = rec_probe<false>(P, d.slots, d.bmask, p, tok);
+                const Probe q = probe(P, p, tok);
                 if (!q.found) {
-                    insert_edge(p, rec_free_inline(P), tok, cur);
+                    insert_edge(p, P.w[R_AUX], tok, cur);
                     g.n_edges++;
                     p = P.w[R_LINK];
                     continue;
@@ -348,31 +375,40 @@ struct ScBuilder {
                 break;
             }
         }
+        const int q = pp.target;
+        if (p != -1) X = load(q);                            // after every store above (q may be `last` or a chain state)
+        {
+            // the new state: the empty template is already in place; these stores ride in the shadow of that load
+            int32_t *rc = d.recs + (size_t)cur * SAMD_REC;
+            rc[R_LEN] = g.n;
+            rc[R_END] = g.n;
+            d.text[g.n] = tok;
+        }
         int link_cur = 0;
         g.ll_twin = -1;
         x_state = -1;
         if (p != -1) {
-            const int q = pp.target;
-            Rec Q = load(q);                                // after every store above (q may be `last` or a chain state)
-            if (p_len + 1 == Q.w[R_LEN]) {
+            if (p_len + 1 == X.w[R_LEN]) {
                 link_cur = q;
             } else {
                 // clone-on-split: q's record with length len(p)+1; overflow edges re-inserted oldest first
                 const int clone = g.n_states++;
                 g.n_clones++;
-                Rec CL = Q;
-                CL.w[R_LEN] = p_len + 1;
-                CL.w[R_OHEAD] = CL.w[R_OTAIL] = -1;
-                rec_store(d.recs, clone, CL);
-                g.n_edges += rec_free_inline(Q);
-                for (uint32_t e = (uint32_t)Q.w[R_OHEAD]; e != SAMD_NIL;) {
+                const int q_len = X.w[R_LEN], q_oh = X.w[R_OHEAD], q_ot = X.w[R_OTAIL], q_link = X.w[R_LINK];
+                X.w[R_LEN] = p_len + 1;
+                X.w[R_OHEAD] = X.w[R_OTAIL] = -1;
+                rec_store(d.recs, clone, X);
+                X.w[R_LEN] = q_len;
+                X.w[R_OHEAD] = q_oh;
+                X.w[R_OTAIL] = q_ot;
+                g.n_edges += X.w[R_AUX];
+                for (uint32_t e = (uint32_t)q_oh; e != SAMD_NIL;) {
                     const uint4 se = slot_load<false>(d.slots, e);
                     ovf_insert(clone, (int)se.y, (int)se.z);
                     SC_STAT(SC_ST_OVF_CLONE);
                     g.n_edges++;
                     e = se.w;
                 }
-                sc_prefetch_rec(d.recs, clone);             // a fresh record is not in L1 (stores do not allocate)
                 // redirect p's suffix chain from q to the clone
                 int rp = p, rl = p_link;
                 Probe cp = pp;
@@ -382,21 +418,19 @@ struct ScBuilder {
                     rp = rl;
                     if (rp == -1) break;
                     const Rec R = load(rp);
-                    cp = rec_probe<false>(R, d.slots, d.bmask, rp, tok);
+                    cp = probe(R, rp, tok);
                     if (!(cp.found && cp.target == q)) break;
                     rl = R.w[R_LINK];
                 }
                 d.recs[(size_t)q * SAMD_REC + R_LINK] = clone;
-                Q.w[R_LINK] = clone;
+                X.w[R_LINK] = clone;
+                sc_prefetch_rec(d.recs, clone);             // a record that was only written is not in L1 (stores do not allocate)
                 link_cur = clone;
                 g.ll_twin = q;
                 g.ll_len = p_len + 1;
-                g.ll_link = CL.w[R_LINK];
+                g.ll_link = q_link;
             }
-            if (on_edge && q == new_cur) {                  // the cursor moved to q: its record is the next token's
-                X = Q;
-                x_state = q;
-            }
+            if (on_edge && q == new_cur) x_state = q;       // the cursor moved to q: X is the next token's cursor record
         }
         d.recs[(size_t)cur * SAMD_REC + R_LINK] = link_cur;
         g.last = cur;
@@ -411,7 +445,7 @@ struct ScBuilder {
         if (x_state != x) X = load(x);
         bool first = true;
         while (true) {
-            const Probe pr = rec_probe<false>(X, d.slots, d.bmask, x, tok);
+            const Probe pr = probe(X, x, tok);
             ++g.hops;
             if (!first) len = X.w[R_LEN];
             if (pr.found) {
@@ -438,7 +472,7 @@ struct ScBuilder {
         Rec Y = (x_state == x) ? X : load(x);
         bool first = true;
         while (true) {
-            const Probe pr = rec_probe<false>(Y, d.slots, d.bmask, x, tok);
+            const Probe pr = probe(Y, x, tok);
             ++probes;
             if (!first) len = Y.w[R_LEN];
             if (pr.found) {
@@ -459,18 +493,21 @@ struct ScBuilder {
 
     // to_anc (dyn_sam.py:99-105) + the draft's anchor: returns min_endpos of the state the draft is read after
     SAMD_HD int anchor_samd(int index, int n_predicts) {
-        if (tr.trace && tr.n < tr.cap) tr.trace[tr.n++] = index;
+        if constexpr (kProf)
+            if (tr.trace && tr.n < tr.cap) tr.trace[tr.n++] = index;
         int4 h = rec_head<false>(d.recs, index);
         if (index != 0) {
             while (h.x != 0 && n_predicts > g.n - h.z) {
                 index = h.x;
-                if (tr.trace && tr.n < tr.cap) tr.trace[tr.n++] = index;
+                if constexpr (kProf)
+                    if (tr.trace && tr.n < tr.cap) tr.trace[tr.n++] = index;
                 h = rec_head<false>(d.recs, index);
             }
         }
         return h.z;
     }
 };
+typedef ScBuilderT<false> ScBuilder;
 
 // ---- read-only cursor walk over the static automaton (static_sam.py:102-109) --------------------------------
 template <bool kRO>

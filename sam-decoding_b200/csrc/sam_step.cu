@@ -13,18 +13,18 @@
 // arena management
 // ---------------------------------------------------------------------------------------
 __global__ void dyn_reset_kernel(DynArena a, const uint8_t *mask) {
-    // one CTA per request: clear the overflow table (0xFF = free), write the root and the meta block
+    // one CTA per request: clear the overflow table (0xFF = free), fill EVERY record with the empty template {link -1,
+    // length 0, min_endpos 0, no edges, no overflow list, aux 0} - which is also the root (dyn_sam.py:19) - so that
+    // creating a state later only has to store its lengths (sam_scalar.cuh), and write the meta block
     int r = blockIdx.x;
     if (mask && !mask[r]) return;
     uint4 *slots = a.slots + (size_t)r * a.h_cap;
     const uint4 e = make_uint4(SAMD_EMPTY, SAMD_EMPTY, SAMD_EMPTY, SAMD_EMPTY);
     for (uint32_t i = threadIdx.x; i < a.h_cap; i += blockDim.x) slots[i] = e;
-    if (threadIdx.x < SAMD_REC) {
-        // root (dyn_sam.py:19): link -1, length 0, min_endpos 0, no edges
-        const int t = threadIdx.x;
-        int v = 0;
-        if (t == R_LINK || t == R_OHEAD || t == R_OTAIL || (t >= R_TOK && t < R_TOK + SAMD_INLINE)) v = -1;
-        a.recs[(size_t)r * a.s_cap * SAMD_REC + t] = v;
+    int4 *recs4 = reinterpret_cast<int4 *>(a.recs + (size_t)r * a.s_cap * SAMD_REC);
+    for (size_t i = threadIdx.x; i < (size_t)a.s_cap * 4; i += blockDim.x) {
+        const int q = (int)(i & 3);          // words {-1,0,0,-1 | -1,-1,-1,-1 | -1,0,0,0 | 0,0,-1,0}
+        recs4[i] = q == 0 ? make_int4(-1, 0, 0, -1) : q == 1 ? make_int4(-1, -1, -1, -1) : q == 2 ? make_int4(-1, 0, 0, 0) : make_int4(0, 0, -1, 0);
     }
     if (threadIdx.x == 0) {
         a.text[(size_t)r * a.t_cap] = -1;                                       // sentinel (dyn_sam.py:20)
@@ -171,6 +171,7 @@ __device__ __forceinline__ void add_edge(int32_t *recs, uint4 *slots, uint32_t b
         if (lane == 0) {
             rec[l] = tok;
             rec[l + (R_TGT - R_TOK)] = target;
+            rec[R_AUX] = l - R_TOK + 1;                     // inline-edge count (arena invariant, sam_scalar.cuh)
         }
         return;
     }
@@ -231,6 +232,7 @@ __device__ __forceinline__ void lane_add_edge(int32_t *recs, uint4 *slots, uint3
         if ((uint32_t)rec[R_TOK + i] == SAMD_EMPTY) {
             rec[R_TOK + i] = tok;
             rec[R_TGT + i] = target;
+            rec[R_AUX] = i + 1;
             return;
         }
     }
@@ -274,6 +276,7 @@ __device__ __forceinline__ void dyn_append(int32_t *recs, uint4 *slots, int32_t 
         if (lane == 0) {
             recs[(size_t)p * SAMD_REC + R_TOK] = tok;
             recs[(size_t)p * SAMD_REC + R_TGT] = cur;
+            recs[(size_t)p * SAMD_REC + R_AUX] = 1;
         }
         g.n_edges++;
         p = g.last_link;
@@ -404,6 +407,7 @@ struct StepParams {
     int32_t *out_type, *out_match_dyn, *out_match_static, *out_index_dyn, *out_index_static, *out_draft, *out_draft_len;
     int draft_stride;
     long long *dbg_cycles;      // optional [10][n_requests] per-request SM cycles by phase (profiling hook, see samd_b200.h)
+    int prewalk;                // draft tokens the cursor scouts walk ahead for the next step (0 = off)
     int32_t *trace;             // optional [n_requests][trace_cap]: word 0 = count, then the states whose records the builder read
     int trace_cap;
 };
@@ -726,63 +730,96 @@ __device__ __forceinline__ bool sc_bad(long long idx, long long cap) { return (u
 template <bool kStatic>
 __device__ __forceinline__ void sc_scout_walk(const int32_t *recs, const uint4 *slots, uint32_t bmask, const int32_t *text,
                                               int idx, const int32_t *tk, int k, int peek, int n_predicts, long long text_n,
-                                              long long cap, int *mailbox) {
+                                              long long cap, volatile int *mailbox, int prewalk) {
     if (k > SCOUT_MAX_TOKENS) return;
     if (sc_bad(idx, cap)) return;
     const int total = k + (peek >= 0 ? 1 : 0);
     Rec Y = rec_load<kStatic>(recs, idx);
+    int next_tok = total > 0 ? (k > 0 ? tk[0] : peek) : 0;
     for (int i = 0; i < total; ++i) {
-        const int tok = i < k ? tk[i] : peek;
+        const int tok = next_tok;
+        if (i + 1 < total) next_tok = i + 1 < k ? tk[i + 1] : peek;
         int up_state = 0, up_target = 0;
         while (true) {
-            const Probe pr = rec_probe<kStatic>(Y, slots, bmask, idx, tok, 4);
+            const Probe pr = rec_probe<kStatic>(Y, slots, bmask, idx, tok, 16);
             if (pr.found) {
+                const int up = Y.w[R_LINK];
+                idx = sc_bad(pr.target, cap) ? 0 : pr.target;
+                Y = rec_load<kStatic>(recs, idx);
                 if (!kStatic && i < k) {
                     // the first stop of a clone's redirect walk: requested without waiting for it
-                    const int up = Y.w[R_LINK];
                     if (up > 0 && !sc_bad(up, cap)) sc_prefetch_rec(recs, up);
                     up_state = up;
                     up_target = pr.target;
                 }
-                idx = sc_bad(pr.target, cap) ? 0 : pr.target;
-                Y = rec_load<kStatic>(recs, idx);
                 break;
             }
             if (idx == 0) break;
             idx = Y.w[R_LINK];
             if (sc_bad(idx, cap)) idx = 0;
             Y = rec_load<kStatic>(recs, idx);
+            // the stop's overflow slot for this token, should it turn out to be a hub: its address needs only the state's
+            // number, so it is requested together with the record instead of after it
+            sc_prefetch(slots + (size_t)(samd_hash((uint32_t)idx, (uint32_t)tok) & bmask) * SAMD_BUCKET);
         }
         if (!kStatic && mailbox && i < k) {                  // every token gets an entry (stop 0 = nothing to look up)
-            atomicExch(&mailbox[4 * i + 0], up_state);
-            atomicExch(&mailbox[4 * i + 1], tok);
-            atomicExch(&mailbox[4 * i + 2], up_target);
+            mailbox[4 * i + 0] = up_state;
+            mailbox[4 * i + 1] = tok;
+            mailbox[4 * i + 2] = up_target;
             __threadfence_block();
-            atomicExch(&mailbox[4 * SCOUT_MAX_TOKENS], i + 1);
+            mailbox[4 * SCOUT_MAX_TOKENS] = i + 1;
         }
     }
     if (peek < 0) return;
+    if (!kStatic && idx != 0) {
+        // to_anc (dyn_sam.py:99-105) moves the draft's anchor up the suffix chain while the occurrence is too close to the
+        // end of the text: walk it too, so that those records and the RIGHT text lines are what gets requested
+        const long long n_after = text_n + k;
+        for (int hop = 0; hop < 8 && Y.w[R_LINK] > 0 && !sc_bad(Y.w[R_LINK], cap) && n_predicts > n_after - Y.w[R_END]; ++hop) {
+            idx = Y.w[R_LINK];
+            Y = rec_load<kStatic>(recs, idx);
+        }
+    }
     const long long e = Y.w[R_END];                          // the draft is read right after this position
-    if (e >= 0)
-        for (int j = 0; j < n_predicts + 8 && e + 1 + j <= text_n; j += 8) sc_prefetch(text + e + 1 + j);
+    if (e < 0 || e > text_n) return;
+    for (int j = 0; j < n_predicts + 8 && e + 1 + j <= text_n; j += 8) sc_prefetch(text + e + 1 + j);
+    // Look-ahead for the NEXT step: the draft is what the next step will most likely be handed as accepted tokens
+    // (that is what a draft is), so the cursor's path along it is what the next launch will read first.  Walking it
+    // now brings those records into L2 (L1 does not survive the launch): next step's cold misses become L2 hits.
+    for (int j = 0; j < prewalk && e + 1 + j <= text_n; ++j) {
+        const int tok = kStatic ? __ldg(text + e + 1 + j) : text[e + 1 + j];
+        while (true) {
+            const Probe pr = rec_probe<kStatic>(Y, slots, bmask, idx, tok, 16);
+            if (pr.found) {
+                idx = sc_bad(pr.target, cap) ? 0 : pr.target;
+                Y = rec_load<kStatic>(recs, idx);
+                break;
+            }
+            if (idx == 0) return;                            // the draft left what the automaton knows
+            idx = Y.w[R_LINK];
+            if (sc_bad(idx, cap)) return;
+            Y = rec_load<kStatic>(recs, idx);
+        }
+        if (idx == 0) return;
+    }
 }
 
-__device__ __forceinline__ void sc_redirect_scout(const int32_t *recs, const uint4 *slots, uint32_t bmask, int *mailbox, int k,
-                                                  long long cap) {
+__device__ __forceinline__ void sc_redirect_scout(const int32_t *recs, const uint4 *slots, uint32_t bmask, volatile int *mailbox,
+                                                  int k, long long cap) {
     if (k > SCOUT_MAX_TOKENS) return;
     for (int i = 0; i < k; ++i) {
         while (true) {
-            if (atomicAdd(&mailbox[4 * SCOUT_MAX_TOKENS], 0) > i) break;
-            if (atomicAdd(&mailbox[4 * SCOUT_MAX_TOKENS + 1], 0)) return;      // the cursor scout is done and never got this far
+            if (mailbox[4 * SCOUT_MAX_TOKENS] > i) break;
+            if (mailbox[4 * SCOUT_MAX_TOKENS + 1]) return;                     // the cursor scout is done and never got this far
             __nanosleep(40);
         }
         __threadfence_block();
-        int pp = atomicAdd(&mailbox[4 * i + 0], 0);
-        const int tok = atomicAdd(&mailbox[4 * i + 1], 0);
-        const int target = atomicAdd(&mailbox[4 * i + 2], 0);
+        int pp = mailbox[4 * i + 0];
+        const int tok = mailbox[4 * i + 1];
+        const int target = mailbox[4 * i + 2];
         for (int up = 0; up < 6 && pp > 0 && !sc_bad(pp, cap); ++up) {
             const Rec Y = rec_load<false>(recs, pp);
-            const Probe pr = rec_probe<false>(Y, slots, bmask, pp, tok, 4);
+            const Probe pr = rec_probe<false>(Y, slots, bmask, pp, tok, 16);
             if (!pr.found || pr.target != target) break;
             pp = Y.w[R_LINK];
         }
@@ -790,10 +827,8 @@ __device__ __forceinline__ void sc_redirect_scout(const int32_t *recs, const uin
 }
 
 template <bool kProf>
-__global__ void __launch_bounds__(96, 7) sam_step_scalar_kernel(StepParams P) {
+__global__ void __maxnreg__(88) sam_step_scalar_kernel(StepParams P) {
     __shared__ int s_mailbox[4 * SCOUT_MAX_TOKENS + 2];
-    __shared__ int s_chain[SC_CHAIN_MAX];
-    __shared__ unsigned char s_cfree[SC_CHAIN_MAX];
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31;
     if (r >= P.dyn.n_requests) return;
@@ -804,18 +839,24 @@ __global__ void __launch_bounds__(96, 7) sam_step_scalar_kernel(StepParams P) {
     int32_t *text = P.dyn.text + (size_t)r * P.dyn.t_cap;
     int32_t *meta = P.dyn.meta + (size_t)r * META_WORDS;
     if (threadIdx.x >= 32) {
-        if (lane != 0) return;
         const int k = P.tokens ? (P.counts ? P.counts[r] : P.token_stride) : 0;
         const int32_t *tk = P.tokens ? P.tokens + (size_t)r * P.token_stride : nullptr;
+        if (lane != 0) {
+            // idle lanes of the third warp: the root's overflow slot of every token of the step (the root is where a
+            // cursor walk ends when the context is new, and it has far more than five edges) - requested up front
+            if (threadIdx.x >= 64 && lane <= 8 && lane <= k && k <= SCOUT_MAX_TOKENS)
+                sc_prefetch(slots + (size_t)(samd_hash(0u, (uint32_t)tk[lane - 1]) & P.dyn.bmask) * SAMD_BUCKET);
+            return;
+        }
         const int peek = P.start_tok ? P.start_tok[r] : -1;
         if (threadIdx.x < 64) {
             sc_scout_walk<false>(recs, slots, P.dyn.bmask, text, meta[META_CUR], tk, k, peek, P.n_predicts, (long long)meta[META_N],
-                                 (long long)P.dyn.s_cap, (blockDim.x > 64 && !P.has_static) ? s_mailbox : nullptr);
+                                 (long long)P.dyn.s_cap, (blockDim.x > 64 && !P.has_static) ? s_mailbox : nullptr, P.prewalk);
             __threadfence_block();
-            atomicExch(&s_mailbox[4 * SCOUT_MAX_TOKENS + 1], 1);         // whatever path the scout left by: no more hand-offs
+            *(volatile int *)&s_mailbox[4 * SCOUT_MAX_TOKENS + 1] = 1;   // whatever path the scout left by: no more hand-offs
         } else if (P.has_static) {
             sc_scout_walk<true>(P.st.recs, P.st.slots, P.st.bmask, P.st.text, P.static_cursor[2 * r], tk, k, peek, P.n_predicts,
-                                (long long)P.st.n_tokens, (long long)P.st.n_states, nullptr);
+                                (long long)P.st.n_tokens, (long long)P.st.n_states, nullptr, P.prewalk);
         } else {
             sc_redirect_scout(recs, slots, P.dyn.bmask, s_mailbox, k, (long long)P.dyn.s_cap);
         }
@@ -825,39 +866,50 @@ __global__ void __launch_bounds__(96, 7) sam_step_scalar_kernel(StepParams P) {
     int o_have = 0, o_n_out = 0, o_endpos = 0, o_text_n = 0, o_src = 0, o_tok = 0;
     if (lane == 0) {
         const long long t_begin = kProf ? clock64() : 0;
-        ScBuilder b;
+        unsigned long long g_begin = 0;
+        if constexpr (kProf) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
+        ScBuilderT<kProf> b;
+        if constexpr (kProf)
+            for (int i = 0; i < SC_PF_N; ++i) b.pf[i] = 0;
+        // the arena's base pointers stay in registers (otherwise every address is rebuilt from the constant bank)
+        asm volatile("" : "+l"(recs), "+l"(slots), "+l"(text));
         b.d.recs = recs;
         b.d.slots = slots;
         b.d.text = text;
         b.d.bmask = P.dyn.bmask;
         b.d.max_tokens = P.dyn.max_tokens;
-        b.chain = s_chain;
-        b.cfree = s_cfree;
         b.x_state = -1;
-        b.tr.trace = P.trace ? P.trace + (size_t)r * P.trace_cap + 1 : nullptr;
+        b.tr.trace = (kProf && P.trace) ? P.trace + (size_t)r * P.trace_cap + 1 : nullptr;
         b.tr.cap = P.trace_cap - 1;
         b.tr.n = 0;
+        // every input of the step is requested at once: the meta block, the step's first token, its count, the lookup
+        // token and the static cursor are independent loads - one round trip instead of a chain of them
+        const int32_t *tk = P.tokens ? P.tokens + (size_t)r * P.token_stride : nullptr;
+        int lookup_probes;
+        int next_tok = 0, k = 0, start_tok = 0, s_idx = 0, s_len = 0, s_hops = 0;
         {
             const int4 m0 = *reinterpret_cast<const int4 *>(meta), m1 = *reinterpret_cast<const int4 *>(meta + 4);
             const int4 m2 = *reinterpret_cast<const int4 *>(meta + 8), m3 = *reinterpret_cast<const int4 *>(meta + 12);
+            if (tk) {
+                next_tok = tk[0];
+                k = P.counts ? P.counts[r] : P.token_stride;
+            }
+            if (P.start_tok) start_tok = P.start_tok[r];
+            if (P.has_static) {
+                s_idx = P.static_cursor[2 * r];
+                s_len = P.static_cursor[2 * r + 1];
+            }
             b.g.n_states = m0.x; b.g.last = m0.y; b.g.n = m0.z; b.g.cur = m0.w;
             b.g.cur_len = m1.x; b.g.n_edges = m1.y; b.g.n_clones = m1.w;
-            b.g.hops = m2.x; b.g.last_link = m2.z; b.g.ll_twin = m2.w;
+            b.g.hops = m2.x; lookup_probes = m2.y; b.g.last_link = m2.z; b.g.ll_twin = m2.w;
             b.g.ll_len = m3.x; b.g.ll_link = m3.y; b.g.max_chain = m3.z;
-        }
-        int s_idx = 0, s_len = 0, s_hops = 0;
-        if (P.has_static) {
-            s_idx = P.static_cursor[2 * r];
-            s_len = P.static_cursor[2 * r + 1];
         }
         // ---- phase 1: DraftModel.update (draft.py:65-79) ----
         if (P.tokens) {
-            const int k = P.counts ? P.counts[r] : P.token_stride;
-            const int32_t *tk = P.tokens + (size_t)r * P.token_stride;
             int flags = 0;
             for (int i = 0; i < k; ++i) {
-                if ((i & 31) == 0 && i + 32 < k) sc_prefetch(tk + i + 32);
-                const int tok = tk[i];
+                const int tok = next_tok;
+                if (i + 1 < k) next_tok = tk[i + 1];         // one ahead: the next token is in a register when its turn comes
                 if (tok < 0) {                               // -1 marks a free edge slot in the layout: never a token
                     flags |= 2;
                     break;
@@ -892,7 +944,7 @@ __global__ void __launch_bounds__(96, 7) sam_step_scalar_kernel(StepParams P) {
         const long long t_lookup = kProf ? clock64() : 0;
         // ---- phase 2: DraftModel.lookup (draft.py:52-63 / samd_sam_only/draft.py:49-59) ----
         if (P.start_tok) {
-            const int tok = P.start_tok[r];
+            const int tok = start_tok;
             int d_idx = 0, d_len = 0, q_hops = 0;
             b.lookup(tok, d_idx, d_len, q_hops);
             int t_idx = 0, t_len = 0;
@@ -939,16 +991,24 @@ __global__ void __launch_bounds__(96, 7) sam_step_scalar_kernel(StepParams P) {
             if (P.out_index_dyn) P.out_index_dyn[r] = d_idx;
             if (P.out_index_static) P.out_index_static[r] = t_idx;
             if (P.out_draft_len) P.out_draft_len[r] = n_out;
-            meta[META_PROBES] += q_hops;
+            meta[META_PROBES] = lookup_probes + q_hops;
             o_have = 1; o_n_out = n_out; o_endpos = endpos; o_text_n = text_n; o_src = src; o_tok = tok;
         }
-        if (b.tr.trace) b.tr.trace[-1] = b.tr.n;
+        if constexpr (kProf)
+            if (b.tr.trace) b.tr.trace[-1] = b.tr.n;
         if constexpr (kProf) {
             if (P.start_tok) {
                 const long long t = clock64();
                 const size_t n = (size_t)P.dyn.n_requests;
-                const long long v[10] = {t - t_begin, 0, t_lookup - t_begin, t - t_lookup, 0, 0, 0, 0, 0, 0};
+                // whole request, cycles waiting for record loads, update phase, lookup phase, record loads that took
+                // < 120 / < 500 / < 1100 / more cycles (L1 / L2 / DRAM / slower), overflow-probe cycles and count
+                const long long v[10] = {t - t_begin, b.pf[SC_PF_LOAD_CYC], t_lookup - t_begin, t - t_lookup, b.pf[SC_PF_L1], b.pf[SC_PF_L2],
+                                         b.pf[SC_PF_DRAM], b.pf[SC_PF_SLOW], b.pf[SC_PF_OVF_CYC], b.pf[SC_PF_OVF_N]};
                 for (int i = 0; i < 10; ++i) P.dbg_cycles[i * n + r] = v[i];
+                unsigned long long g1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+                P.dbg_cycles[10 * n + r] = (long long)g_begin;       // ns, comparable across SMs: the step's span
+                P.dbg_cycles[11 * n + r] = (long long)g1;
             }
         }
     }
@@ -978,10 +1038,12 @@ __global__ void __launch_bounds__(96, 7) sam_step_scalar_kernel(StepParams P) {
 static long long *g_dbg_cycles = nullptr;
 static int g_scouts = 2;
 static int g_variant = 1;
+static int g_prewalk = 0;
 static int32_t *g_trace = nullptr;
 static int g_trace_cap = 0;
 extern "C" void samd_step_set_scouts(int on) { g_scouts = on; }
 extern "C" void samd_step_set_variant(int v) { g_variant = v; }
+extern "C" void samd_step_set_prewalk(int n) { g_prewalk = n < 0 ? 0 : n; }
 extern "C" void samd_step_set_trace(int32_t *trace_dev, int cap) {
     g_trace = trace_dev;
     g_trace_cap = trace_dev ? cap : 0;
@@ -1017,6 +1079,7 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     P.out_draft_len = a->out_draft_len_dev;
     P.draft_stride = a->draft_stride;
     P.dbg_cycles = g_dbg_cycles;
+    P.prewalk = g_prewalk;
     P.trace = g_trace;
     P.trace_cap = g_trace_cap;
     SAMD_REQUIRE(a->flavour == SAMD_FLAVOUR_SAMD || a->flavour == SAMD_FLAVOUR_SAM_ONLY, "samd_step: bad flavour");
@@ -1369,14 +1432,21 @@ __global__ void __launch_bounds__(64) replay_trace_kernel(DynArena a, const int3
         }
         return;
     }
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     const long long t0 = clock64();
     int acc = 0;
     for (int i = 0; i < n; ++i) {
-        const int s = tr[1 + i] + (acc & 0x40000000);      // always + 0 (record words are < 2^30), but the compiler cannot know
+        const int s = tr[1 + i] + (acc & 0x40000000);      // always + 0 (a record's length is < 2^28 and its last word 0), but the compiler cannot know
         const Rec Y = rec_load<false>(recs, sc_bad(s, a.s_cap) ? 0 : s);
-        acc = Y.w[R_LEN] | Y.w[R_TOK + 4];
+        acc = (Y.w[R_LEN] & 0x0FFFFFFF) | Y.w[R_AUX];
     }
-    cycles[r] = clock64() - t0 + (acc & 0x40000000);
+    const long long dt = clock64() - t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    const size_t nr = (size_t)a.n_requests;
+    cycles[r] = dt + (acc & 0x40000000);
+    cycles[nr + r] = (long long)g0;
+    cycles[2 * nr + r] = (long long)g1;
 }
 
 extern "C" int samd_debug_replay_trace(samd_dyn_t h, const int32_t *trace_dev, int cap, int with_scout, int64_t *cycles_dev,

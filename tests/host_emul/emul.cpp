@@ -14,8 +14,6 @@ struct Emul {
     ScBuilder b;
     std::vector<int32_t> recs, text;
     std::vector<uint4> slots;
-    int chain[SC_CHAIN_MAX];
-    unsigned char cfree[SC_CHAIN_MAX];
 };
 
 extern "C" {
@@ -27,7 +25,7 @@ Emul *emul_new(int max_tokens) {
     e->recs.assign((size_t)s_cap * SAMD_REC, 0);
     e->slots.assign(h_cap, make_uint4(SAMD_EMPTY, SAMD_EMPTY, SAMD_EMPTY, SAMD_EMPTY));
     e->text.assign((size_t)max_tokens + 4, 0);
-    samd_init_rec(e->recs.data(), -1, 0, 0);
+    for (uint32_t v = 0; v < s_cap; ++v) samd_init_rec(e->recs.data() + (size_t)v * SAMD_REC, -1, 0, 0);   // the arena invariant: empty templates
     e->text[0] = -1;
     ScBuilder &b = e->b;
     b.d.recs = e->recs.data();
@@ -38,8 +36,6 @@ Emul *emul_new(int max_tokens) {
     b.g = ScRegs{1, 0, -1, 0, 0, 0, 0, 0, 0, -1, 0, 0, 0};
     b.x_state = -1;
     for (int i = 0; i < SC_ST_N; ++i) b.stats[i] = 0;
-    b.chain = e->chain;
-    b.cfree = e->cfree;
     b.tr.trace = nullptr;
     b.tr.cap = b.tr.n = 0;
     return e;
@@ -82,7 +78,7 @@ void emul_info(Emul *e, int64_t *out) {
     out[4] = g.cur; out[5] = g.cur_len; out[6] = g.last; out[7] = g.last_link;
 }
 
-// which paths of extend_one ran: {aligned, twin, generic, chain > SC_CHAIN_MAX, overflow inserts, overflow edges cloned, carried record}
+// which paths of extend_one ran: {aligned, twin, generic, (unused), overflow inserts, overflow edges cloned, carried record}
 void emul_stats(Emul *e, int64_t *out) {
     for (int i = 0; i < SC_ST_N; ++i) out[i] = e->b.stats[i];
 }
