@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--only-verify", action="store_true", help="profiling aid: run only the c4 verify loop")
     ap.add_argument("--only-step", action="store_true", help="profiling aid: run only the c2 device loop")
     ap.add_argument("--scouts", type=int, default=2, help="profiling aid: scout warps of the step kernel (0 none, 1 cursor scouts, 2 all)")
+    ap.add_argument("--ngram", type=int, default=None, help="tuning aid: depth of the short-context scouts (-1 off)")
     ap.add_argument("--prewalk", type=int, default=None, help="tuning aid: draft tokens the scouts walk ahead for the next step")
     ap.add_argument("--variant", type=int, default=1, help="step kernel variant: 1 = one thread per request (default), 0 = warp-cooperative (round 1)")
     return ap.parse_args()
@@ -324,6 +325,8 @@ def run_ours(a):
     K.lib().samd_step_set_scouts(a.scouts)
     if a.prewalk is not None:
         K.lib().samd_step_set_prewalk(a.prewalk)
+    if a.ngram is not None:
+        K.lib().samd_step_set_ngram(a.ngram)
     launches0 = E.launch_count()
     if a.only_verify:                         # profiling aid (ncu): just the c4 loop
         print(json.dumps({"verify": bench_verify(a, dev, 6458.1, iters=6, warm=2)}))

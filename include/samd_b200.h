@@ -185,6 +185,10 @@ void samd_step_set_variant(int variant);
 /* tuning hook (variant 1): after a step's lookup the cursor scouts keep walking along the first n draft tokens - the path
  * the NEXT step's accepted tokens will most likely take - so that its records are in L2 by then.  0 = off. */
 void samd_step_set_prewalk(int n_tokens);
+/* tuning hook (variant 1): depth of the short-context scouts - one idle lane per token of the step walks from the root
+ * through that token and the next `depth` ones, requesting the records and overflow slots a falling-back cursor walk ends
+ * at.  -1 = off, 0 = only the root's slots, default 6. */
+void samd_step_set_ngram(int depth);
 /* profiling hook (variant 1): when non-NULL, every samd_step launch writes, per request, trace_dev[r][0] = the number of
  * state records its builder read and trace_dev[r][1..] = their state indices in order (capacity `cap` words per
  * request) - the request's dependent-load chain, replayed as bare loads by samd_debug_replay_trace. */

@@ -134,23 +134,34 @@ SAMD_HD bool ovf_find(const uint4 *slots, uint32_t bmask, uint32_t state, uint32
     return false;
 }
 
+// inline index of the edge on `tok` (which the record is known to have inline)
+SAMD_HD int rec_inline_index(const Rec &X, int tok) {
+    int kk = 0;
+#pragma unroll
+    for (int i = 0; i < SAMD_INLINE; ++i) kk |= X.w[R_TOK + i] == tok ? i : 0;
+    return kk;
+}
+
+// Transition probe.  A state has at most one edge per token, so at most one of the five compares is true: the target is
+// OR-ed together from five independent selects (a shallow tree instead of a chain of dependent ones).  r.k is only a
+// flag here (0 = inline hit, -1 = not inline): whoever needs the edge's position asks rec_inline_index afterwards - one
+// probe per chain needs it, every stop of every chain is probed.
 template <bool kRO>
 SAMD_HD Probe rec_probe(const Rec &X, const uint4 *slots, uint32_t bmask, int state, int tok, int max_slots = 0) {
-    // a state has at most one edge per token, so at most one of the five compares is true: the target and the index are
-    // OR-ed together from five independent selects (a shallow tree instead of a chain of five dependent ones)
     Probe r;
-    int tgt = 0, kk = 0;
+    int tgt = 0;
+    bool any = false;
 #pragma unroll
     for (int i = 0; i < SAMD_INLINE; ++i) {
         const bool e = X.w[R_TOK + i] == tok;
         tgt |= e ? X.w[R_TGT + i] : 0;
-        kk |= e ? (i + 1) : 0;
+        any |= e;
     }
     r.target = tgt;
-    r.k = kk - 1;
+    r.k = any ? 0 : -1;
     r.slot = SAMD_NIL;
-    r.found = kk != 0;
-    if (!r.found && (uint32_t)X.w[R_OHEAD] != SAMD_NIL) ovf_find<kRO>(slots, bmask, (uint32_t)state, (uint32_t)tok, r, nullptr, max_slots);
+    r.found = any;
+    if (!any && (uint32_t)X.w[R_OHEAD] != SAMD_NIL) ovf_find<kRO>(slots, bmask, (uint32_t)state, (uint32_t)tok, r, nullptr, max_slots);
     return r;
 }
 
@@ -310,16 +321,15 @@ struct ScBuilderT {
                 }
                 break;
             }
-            const int nx = X.w[R_LINK];
-            const Rec Xn = load(nx);                         // requested before this stop's stores are issued
+            const int nx = X.w[R_LINK], n_inline = X.w[R_AUX];
+            X = load(nx);                                    // requested before this stop's stores are issued
             if (aligned) {
-                insert_edge(x, X.w[R_AUX], tok, cur);
+                insert_edge(x, n_inline, tok, cur);
                 ++n_ins;
             } else if (first && nx == p0) {
                 aligned = true;                              // x was the pre-clone state in front of the chain
             }
             x = nx;
-            X = Xn;
             first = false;
         }
         g.hops += n_chain;
@@ -347,6 +357,7 @@ struct ScBuilderT {
                 p = x;
                 p_len = X.w[R_LEN];
                 p_link = X.w[R_LINK];
+                if (pp.k >= 0) pp.k = rec_inline_index(X, tok);
             }
         } else if (on_edge && n_chain == 1 && last != 0 && g.ll_twin == x && pr.k >= 0) {
             // last_link is the clone the previous append made of the cursor's state: same inline edges, so the probe
@@ -355,6 +366,7 @@ struct ScBuilderT {
             p = p0;
             p_len = g.ll_len;
             p_link = g.ll_link;
+            pp.k = rec_inline_index(X, tok);
         } else {
             // the cursor is somewhere else (DynSAM.transfer_tokens moved it, or a kernel boundary dropped the twin
             // hint): add_state's own walk
@@ -372,6 +384,7 @@ struct ScBuilderT {
                 p_len = P.w[R_LEN];
                 p_link = P.w[R_LINK];
                 pp = q;
+                if (pp.k >= 0) pp.k = rec_inline_index(P, tok);
                 break;
             }
         }
@@ -420,6 +433,7 @@ struct ScBuilderT {
                     const Rec R = load(rp);
                     cp = probe(R, rp, tok);
                     if (!(cp.found && cp.target == q)) break;
+                    if (cp.k >= 0) cp.k = rec_inline_index(R, tok);
                     rl = R.w[R_LINK];
                 }
                 d.recs[(size_t)q * SAMD_REC + R_LINK] = clone;

@@ -407,6 +407,7 @@ struct StepParams {
     int32_t *out_type, *out_match_dyn, *out_match_static, *out_index_dyn, *out_index_static, *out_draft, *out_draft_len;
     int draft_stride;
     long long *dbg_cycles;      // optional [10][n_requests] per-request SM cycles by phase (profiling hook, see samd_b200.h)
+    int ngram;                  // depth of the short-context scouts (-1 = off)
     int prewalk;                // draft tokens the cursor scouts walk ahead for the next step (0 = off)
     int32_t *trace;             // optional [n_requests][trace_cap]: word 0 = count, then the states whose records the builder read
     int trace_cap;
@@ -827,7 +828,7 @@ __device__ __forceinline__ void sc_redirect_scout(const int32_t *recs, const uin
 }
 
 template <bool kProf>
-__global__ void __maxnreg__(88) sam_step_scalar_kernel(StepParams P) {
+__global__ void __maxnreg__(96) sam_step_scalar_kernel(StepParams P) {
     __shared__ int s_mailbox[4 * SCOUT_MAX_TOKENS + 2];
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31;
@@ -842,10 +843,28 @@ __global__ void __maxnreg__(88) sam_step_scalar_kernel(StepParams P) {
         const int k = P.tokens ? (P.counts ? P.counts[r] : P.token_stride) : 0;
         const int32_t *tk = P.tokens ? P.tokens + (size_t)r * P.token_stride : nullptr;
         if (lane != 0) {
-            // idle lanes of the third warp: the root's overflow slot of every token of the step (the root is where a
-            // cursor walk ends when the context is new, and it has far more than five edges) - requested up front
-            if (threadIdx.x >= 64 && lane <= 8 && lane <= k && k <= SCOUT_MAX_TOKENS)
-                sc_prefetch(slots + (size_t)(samd_hash(0u, (uint32_t)tk[lane - 1]) & P.dyn.bmask) * SAMD_BUCKET);
+            // Idle lanes of the third warp, one per token of the step: short-context scouts.  A cursor walk that falls
+            // back (the token is new in its long context) ends at the states of the last one, two, three tokens - hubs
+            // with overflow lists, the most expensive stops of the chain - or at the root.  Lane j walks from the root
+            // through tokens j, j+1, j+2: their records and overflow slots are requested up front, all lanes at once.
+            if (threadIdx.x >= 64 && lane <= 8 && lane <= k && k <= SCOUT_MAX_TOKENS && P.ngram >= 0) {
+                const long long cap = (long long)P.dyn.s_cap;
+                const int i = lane - 1;
+                const int peek = P.start_tok ? P.start_tok[r] : -1;
+                const int total = k + (peek >= 0 ? 1 : 0);
+                Rec Y = rec_load<false>(recs, 0);
+                Probe pr = rec_probe<false>(Y, slots, P.dyn.bmask, 0, tk[i], 16);
+                int idx = (pr.found && !sc_bad(pr.target, cap)) ? pr.target : 0;
+                for (int d = 1; d <= P.ngram && idx != 0 && i + d < total; ++d) {
+                    const int tokn = i + d < k ? tk[i + d] : peek;
+                    sc_prefetch(slots + (size_t)(samd_hash((uint32_t)idx, (uint32_t)tokn) & P.dyn.bmask) * SAMD_BUCKET);
+                    Y = rec_load<false>(recs, idx);
+                    pr = rec_probe<false>(Y, slots, P.dyn.bmask, idx, tokn, 16);
+                    if (!pr.found || sc_bad(pr.target, cap)) break;
+                    idx = pr.target;
+                }
+                if (idx != 0) sc_prefetch_rec(recs, idx);
+            }
             return;
         }
         const int peek = P.start_tok ? P.start_tok[r] : -1;
@@ -1039,11 +1058,13 @@ static long long *g_dbg_cycles = nullptr;
 static int g_scouts = 2;
 static int g_variant = 1;
 static int g_prewalk = 0;
+static int g_ngram = 6;
 static int32_t *g_trace = nullptr;
 static int g_trace_cap = 0;
 extern "C" void samd_step_set_scouts(int on) { g_scouts = on; }
 extern "C" void samd_step_set_variant(int v) { g_variant = v; }
 extern "C" void samd_step_set_prewalk(int n) { g_prewalk = n < 0 ? 0 : n; }
+extern "C" void samd_step_set_ngram(int depth) { g_ngram = depth; }
 extern "C" void samd_step_set_trace(int32_t *trace_dev, int cap) {
     g_trace = trace_dev;
     g_trace_cap = trace_dev ? cap : 0;
@@ -1080,6 +1101,7 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     P.draft_stride = a->draft_stride;
     P.dbg_cycles = g_dbg_cycles;
     P.prewalk = g_prewalk;
+    P.ngram = g_ngram;
     P.trace = g_trace;
     P.trace_cap = g_trace_cap;
     SAMD_REQUIRE(a->flavour == SAMD_FLAVOUR_SAMD || a->flavour == SAMD_FLAVOUR_SAM_ONLY, "samd_step: bad flavour");
