@@ -51,9 +51,12 @@ def parse():
     ap.add_argument("--verify-vocab", type=int, default=32000)
     ap.add_argument("--static-tokens", type=int, default=50_000_000, help="corpus size of the c3 side measurement")
     ap.add_argument("--only-static", action="store_true", help="run only the c3 static-SAM measurement (e.g. at 50M tokens)")
+    ap.add_argument("--check-static", action="store_true", help="with --only-static: compare 4 steps x 4096 queries with the C oracle")
+    ap.add_argument("--l2-mb", type=int, default=0, help="with --only-static: also time with this many MB of state records pinned in L2")
     ap.add_argument("--only-verify", action="store_true", help="profiling aid: run only the c4 verify loop")
     ap.add_argument("--only-step", action="store_true", help="profiling aid: run only the c2 device loop")
     ap.add_argument("--scouts", type=int, default=2, help="profiling aid: scout warps of the step kernel (0 none, 1 cursor scouts, 2 all)")
+    ap.add_argument("--lean", type=int, default=None, help="tuning aid: 1 lean / 0 wide build of the step kernel (default: by batch size)")
     ap.add_argument("--ngram", type=int, default=None, help="tuning aid: depth of the short-context scouts (-1 off)")
     ap.add_argument("--prewalk", type=int, default=None, help="tuning aid: draft tokens the scouts walk ahead for the next step")
     ap.add_argument("--variant", type=int, default=1, help="step kernel variant: 1 = one thread per request (default), 0 = warp-cooperative (round 1)")
@@ -327,12 +330,14 @@ def run_ours(a):
         K.lib().samd_step_set_prewalk(a.prewalk)
     if a.ngram is not None:
         K.lib().samd_step_set_ngram(a.ngram)
+    if a.lean is not None:
+        K.lib().samd_step_set_lean(a.lean)
     launches0 = E.launch_count()
     if a.only_verify:                         # profiling aid (ncu): just the c4 loop
         print(json.dumps({"verify": bench_verify(a, dev, 6458.1, iters=6, warm=2)}))
         return
     if a.only_static:
-        print(json.dumps({"static": bench_static(a, dev, n_corpus=a.static_tokens)}))
+        print(json.dumps({"static": bench_static(a, dev, n_corpus=a.static_tokens, check=a.check_static, l2_mb=a.l2_mb)}))
         return
     if a.only_step:
         a.no_extras = a.no_cpu = True
@@ -474,8 +479,8 @@ def run_ours(a):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / S},
         "gpu_launches": None,
-        "roofline": {"kernel": "sam_step_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": traffic.get("sam_step_kernel", {}).get("bytes_per_launch"),
+        "roofline": {"kernel": "sam_step_scalar_kernel" if a.variant == 1 else "sam_step_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": traffic.get("sam_step_scalar_kernel" if a.variant == 1 else "sam_step_kernel", {}).get("bytes_per_launch"),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launch_us": launch_ms * 1e3,
                      "note": "latency-bound pointer chase: queries/s and probes/query are the figures of merit"},
@@ -490,7 +495,7 @@ def run_ours(a):
     }
     del g, snap, h_in, d_tokens
     torch.cuda.empty_cache()
-    if rank == 0 and not a.no_extras:
+    if rank == 0 and world == 1 and not a.no_extras:
         try:
             out["verify"] = bench_verify(a, dev, hbm_peak)
             out["verify"]["roofline"]["traffic"] = traffic.get("verify_compact_kernel", {}).get("bytes_per_launch")
@@ -514,13 +519,26 @@ def run_ours(a):
             out["c1"] = bench_c1(a, dev)
         except Exception as e:
             out["c1"] = {"error": repr(e)}
-    if rank == 0 and not a.no_cpu:
+    if rank == 0 and world == 1 and not a.no_cpu:
+        # the CPU baseline beside it (rank 0, N = 1 only): the reference's own classes when baseline/_ref is staged, on a
+        # bounded sample of the same workload; the Python port and the C restatement of the oracle follow for context
         cores = min(os.cpu_count() or 1, 32)
+        if have_staged_reference():
+            n_ref = cores * 16
+            qps, wall, used = cpu_arm(n_ref, N, 64, 2, 2000, cores, worker=_cpu_worker_ref)
+            out["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": used, "kind": "reference",
+                                   "sample": f"{n_ref} requests x 64 steps of the same workload (prefill untimed, {wall:.2f} s of work "
+                                             f"per core): the reference's own samd.DynSAM / samd.DraftModel, unmodified, from "
+                                             f"baseline/_ref, one Python process per core"}
         n_sample = cores * 64
-        qps, wall, used = cpu_arm(n_sample, N, 256, 4, 2000, cores)
-        out["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": used, "kind": "port",
-                               "sample": f"{n_sample} requests x 256 steps of the same workload (prefill untimed, {wall:.2f} s "
-                                         f"of work per core), Python port of the reference path (oracle/samd_oracle.py)"}
+        qps_p, wall_p, used_p = cpu_arm(n_sample, N, 256, 4, 2000, cores)
+        port = {"value": qps_p, "unit": UNIT, "cores": used_p, "kind": "port",
+                "sample": f"{n_sample} requests x 256 steps of the same workload (prefill untimed, {wall_p:.2f} s "
+                          f"of work per core), Python port of the reference path (oracle/samd_oracle.py)"}
+        if "cpu_baseline" in out:
+            out["cpu_baseline_port"] = port
+        else:
+            out["cpu_baseline"] = port
         try:
             qps_c, wall_c, used_c = cpu_arm(n_sample, N, 256, 4, 2000, cores, worker=_cpu_worker_c)
             out["cpu_baseline_c"] = {"value": qps_c, "unit": UNIT, "cores": used_c, "kind": "port",
@@ -536,6 +554,38 @@ def run_ours(a):
         except Exception as e:
             if rank == 0:
                 out["sharded_static"] = {"error": repr(e)}
+    # the whole metric inside `roofline` (BASELINE's metric is a triple: queries/s; verify+KV us/step; GB/s)
+    others = {}
+    v = out.get("verify")
+    if isinstance(v, dict) and "us_per_step" in v:
+        others["c4_verify_kv"] = {"us_per_step": v["us_per_step"], "achieved_gbs": v["roofline"]["achieved"], "frac": v["roofline"]["frac"],
+                                  "us_verify_only": v["us_per_step_verify_only"], "frac_verify_only": v["roofline_verify_only"]["frac"],
+                                  "us_with_token_recycle_top8": v["token_recycle"]["us_per_step_with_top8_table_update"],
+                                  "traffic": v["roofline"].get("traffic"), "traffic_note": traffic.get("verify_compact_kernel", {}).get("workload")}
+    v = out.get("verify_c5")
+    if isinstance(v, dict) and "us_per_step" in v:
+        others["c5_verify_kv"] = {"us_per_step": v["us_per_step"], "achieved_gbs": v["roofline"]["achieved"], "frac": v["roofline"]["frac"],
+                                  "us_verify_only": v["us_per_step_verify_only"], "frac_verify_only": v["roofline_verify_only"]["frac"]}
+    v = out.get("static")
+    if isinstance(v, dict) and "queries_per_s" in v:
+        others["c3_static_50m"] = {"queries_per_s": v["queries_per_s"], "us_per_step": v["us_per_step"],
+                                   "sectors_per_query": traffic.get("static_lookup", {}).get("l1_sectors_per_query"),
+                                   "l2_hit": traffic.get("static_lookup", {}).get("l2_hit_rate"),
+                                   "l2_window": v.get("l2_window")}
+    v = out.get("c2_concurrent")
+    if isinstance(v, dict) and "queries_per_s" in v:
+        others["c2_concurrent"] = {"queries_per_s": v["queries_per_s"], "us_per_step_per_batch": v["us_per_step_per_batch"],
+                                   "e2e_queries_per_s": v["e2e_queries_per_s"]}
+    v = out.get("c1")
+    if isinstance(v, dict) and "gpu_us_per_step" in v:
+        others["c1"] = {k: v[k] for k in v if k != "workload"}
+    v = out.get("sharded_static")
+    if isinstance(v, dict) and "queries_per_s" in v:
+        others["c5_sharded_static"] = {"queries_per_s": v["queries_per_s"], "p2p": v.get("p2p"), "nccl": v.get("nccl"),
+                                       "matches_oracle": v.get("matches_oracle")}
+    out["roofline"]["others"] = others
+    out["roofline"]["sectors_per_query"] = traffic.get("sam_step_lookup", {}).get("l1_sectors_per_query")
+    out["roofline"]["l2_hit"] = traffic.get("sam_step_lookup", {}).get("l2_hit_rate")
     out["gpu_launches"] = S          # kernels of ours inside the timed region: one sam_step_kernel per step
     out["gpu_launches_total_process"] = E.launch_count() - launches0
     if world > 1:
@@ -795,9 +845,11 @@ def bench_c1(a, dev, prompt=4096, steps=256):
             "cpu_c_port_build_tokens_per_s": prompt / c_build, "cores": 1}
 
 
-def bench_static(a, dev, n_corpus=2_000_000, n_q=4096, steps=64, warm=8):
-    """Config c3 at a corpus size the host builder finishes in seconds: static SAM lookups,
-    4096 persistent cursors advanced 1-8 tokens per step, then lookup + 16-token draft."""
+def bench_static(a, dev, n_corpus=2_000_000, n_q=4096, steps=64, warm=8, check=False, l2_mb=None):
+    """Config c3: static SAM lookups over a corpus built on the host inside the run, 4096 persistent cursors advanced
+    1-8 tokens per step, then lookup + 16-token draft.  `check`: the first 4 steps of all 4096 queries are compared with
+    the oracle's C restatement built over the same documents (state index, match length, draft).  `l2_mb`: the same
+    measurement again with the first l2_mb MB of the state records pinned in L2 (access-policy window)."""
     import torch
     from samd_b200 import _cabi as K, engine as E, synth
     t0 = time.time()
@@ -816,33 +868,73 @@ def bench_static(a, dev, n_corpus=2_000_000, n_q=4096, steps=64, warm=8):
     dyn = E.DynSamBatch(n_q, 8 * (steps + warm) * 2 + 64, dev)
     eng = E.DraftEngine(dyn, st, K.FLAVOUR_SAMD, n_predicts=N_PREDICTS, len_bias=0, len_threshold=0)
     d_tok, d_cnt, d_st = (torch.as_tensor(x).to(dev) for x in (tokens, counts, start))
+    parity = None
+    if check:
+        sys.path.insert(0, os.path.join(REPO, "oracle"))
+        import c_oracle as CO
+        t1 = time.time()
+        ref = CO.CSam.build(docs, synth.EOS)
+        ref_build_s = time.time() - t1
+        cur = np.zeros((n_q, 2), dtype=np.int32)
+        n_cmp = n_static = 0
+        for s in range(4):
+            eng.step(d_tok[s], d_cnt[s], d_st[s])
+            torch.cuda.synchronize()
+            ref.batch_advance(cur, tokens[s], counts[s])
+            r_state, r_len, r_draft = ref.batch_lookup(cur, start[s], N_PREDICTS)
+            assert np.array_equal(eng.index_static.cpu().numpy(), r_state), f"c3 parity: static state index differs at step {s}"
+            assert np.array_equal(eng.match_static.cpu().numpy(), r_len), f"c3 parity: static match length differs at step {s}"
+            assert np.array_equal(eng.static_cursor.cpu().numpy(), cur), f"c3 parity: static cursor differs at step {s}"
+            is_static = (eng.out_type == K.DRAFT_STATIC_SEQ).cpu().numpy()
+            assert np.array_equal(eng.draft.cpu().numpy()[is_static], r_draft[is_static]), f"c3 parity: draft differs at step {s}"
+            n_cmp += n_q
+            n_static += int(is_static.sum())
+        parity = {"queries_compared": n_cmp, "static_drafts_compared": n_static, "oracle": "oracle/sam_oracle.c built over the same documents",
+                  "oracle_build_s": ref_build_s, "identical": True}
+        del ref
+        eng.reset()
     for s in range(warm):
         eng.step(d_tok[s], d_cnt[s], d_st[s])
     torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
     snap_cur = eng.static_cursor.clone()
     snap = E.DynSamBatch(n_q, dyn.max_tokens, dev)
     snap.copy_from(dyn)
-    with torch.cuda.graph(g):
-        for s in range(warm, warm + steps):
-            eng.step(d_tok[s], d_cnt[s], d_st[s])
-    g.replay()
-    torch.cuda.synchronize()
-    dyn.copy_from(snap)
-    eng.static_cursor.copy_(snap_cur)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+
+    def timed():
+        dyn.copy_from(snap)
+        eng.static_cursor.copy_(snap_cur)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for s in range(warm, warm + steps):
+                eng.step(d_tok[s], d_cnt[s], d_st[s])
+        g.replay()
+        torch.cuda.synchronize()
+        dyn.copy_from(snap)
+        eng.static_cursor.copy_(snap_cur)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), int(eng.draft.sum().item())
+
+    ms, checksum = timed()
     src = torch.bincount(eng.out_type, minlength=4).tolist()
-    return {"workload": f"c3: static SAM over {st.n_tokens} tokens ({st.n_states} states, {st.n_edges} edges, "
-                        f"{st.nbytes / 1e9:.2f} GB flat) + per-request dynamic SAM, {n_q} cursors, 1-8 tokens/step, draft 16",
-            "queries_per_s": n_q * steps / (ms * 1e-3), "us_per_step": ms / steps * 1e3, "host_build_s": build_s,
-            "host_build_tokens_per_s": st.n_tokens / build_s, "mean_match_static": float(eng.match_static.float().mean()),
-            "draft_source_hist": {"dyn": src[0], "static": src[1], "tree_model": src[2]}}
+    out = {"workload": f"c3: static SAM over {st.n_tokens} tokens ({st.n_states} states, {st.n_edges} edges, "
+                       f"{st.nbytes / 1e9:.2f} GB flat) + per-request dynamic SAM, {n_q} cursors, 1-8 tokens/step, draft 16",
+           "queries_per_s": n_q * steps / (ms * 1e-3), "us_per_step": ms / steps * 1e3, "host_build_s": build_s,
+           "host_build_tokens_per_s": st.n_tokens / build_s, "mean_match_static": float(eng.match_static.float().mean()),
+           "draft_source_hist": {"dyn": src[0], "static": src[1], "tree_model": src[2]}}
+    if parity is not None:
+        out["parity"] = parity
+    if l2_mb:
+        st.set_l2_window(int(l2_mb) << 20)
+        ms_w, checksum_w = timed()
+        st.set_l2_window(0)
+        out["l2_window"] = {"mb_requested": int(l2_mb), "us_per_step": ms_w / steps * 1e3, "queries_per_s": n_q * steps / (ms_w * 1e-3),
+                            "us_per_step_without": ms / steps * 1e3, "results_identical": checksum_w == checksum}
+    return out
 
 
 def bench_sharded_static(a, dev, rank, world, tokens_per_shard=2_000_000, n_q=4096, steps=64, warm=8):
@@ -903,6 +995,36 @@ def bench_sharded_static(a, dev, rank, world, tokens_per_shard=2_000_000, n_q=40
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), res[0].clone(), res[1].clone()
 
+    def oracle_check():
+        """The merged result of 4 steps x all queries against ONE automaton over the whole corpus (the oracle's C
+        restatement, built on rank 0): match length and draft must be identical - the queries are EOS-free, so no match can
+        span a shard boundary.  Both exchange paths are checked, not against each other but against the oracle."""
+        ok = {"nccl": True, "p2p": None}
+        ref = cur = None
+        if rank == 0:
+            sys.path.insert(0, os.path.join(REPO, "oracle"))
+            import c_oracle as CO
+            ref = CO.CSam.build(docs, synth.EOS)
+        for path in ("nccl", "p2p"):
+            if path == "p2p" and sh._xchg is None:
+                continue
+            sh.reset()
+            cur = np.zeros((n_q, 2), dtype=np.int32)
+            good = True
+            for s in range(4):
+                m, d = sh.lookup_draft(d_st[s], N_PREDICTS, p2p=(path == "p2p"), tokens=d_tok[s], counts=d_cnt[s])
+                torch.cuda.synchronize()
+                if rank == 0:
+                    ref.batch_advance(cur, tokens[s], counts[s])
+                    r_state, r_len, r_draft = ref.batch_lookup(cur, start[s], N_PREDICTS)
+                    hit = r_len > 0
+                    good = good and bool(np.array_equal(m.cpu().numpy(), r_len)) and \
+                        bool(np.array_equal(d.cpu().numpy()[hit], r_draft[hit]))
+            flag = torch.tensor([1 if good else 0], device=dev, dtype=torch.int32)
+            dist.broadcast(flag, 0)
+            ok[path] = bool(flag.item())
+        return ok
+
     ms, match, draft = timed(False, False)
     out = {"workload": f"c5 (reduced corpus): static SAM over {sh.n_corpus} tokens split by document over {world} GPUs "
                        f"({sh.sam.n_tokens} tokens on rank 0), {n_q} queries/step advanced 1-8 tokens, packed-u64 "
@@ -926,6 +1048,10 @@ def bench_sharded_static(a, dev, rank, world, tokens_per_shard=2_000_000, n_q=40
     except Exception as e:
         out["p2p"] = {"error": repr(e)}
         out["queries_per_s"] = out["nccl"]["queries_per_s"]
+    try:
+        out["matches_oracle"] = oracle_check()
+    except Exception as e:
+        out["matches_oracle"] = {"error": repr(e)}
     return out
 
 

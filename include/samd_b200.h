@@ -189,6 +189,9 @@ void samd_step_set_prewalk(int n_tokens);
  * through that token and the next `depth` ones, requesting the records and overflow slots a falling-back cursor walk ends
  * at.  -1 = off, 0 = only the root's slots, default 6. */
 void samd_step_set_ngram(int depth);
+/* tuning hook (variant 1): 1 = always the lean build (64 registers, two warps, 16 CTAs per SM), 0 = always the wide one
+ * (96 registers, three warps, 7 CTAs per SM), -1 (default) = lean when the batch exceeds one wave of the wide build. */
+void samd_step_set_lean(int mode);
 /* profiling hook (variant 1): when non-NULL, every samd_step launch writes, per request, trace_dev[r][0] = the number of
  * state records its builder read and trace_dev[r][1..] = their state indices in order (capacity `cap` words per
  * request) - the request's dependent-load chain, replayed as bare loads by samd_debug_replay_trace. */

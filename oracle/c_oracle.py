@@ -35,6 +35,10 @@ def lib():
         L.so_export.argtypes = [vp, i32p, i32p, i32p]
         L.so_run_steps.restype = C.c_int64
         L.so_run_steps.argtypes = [C.POINTER(vp), C.c_int64, i32p, i32p, i32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]
+        L.so_batch_advance.argtypes = [vp, i32p, i32p, C.c_int64, i32p, C.c_int64]
+        L.so_batch_lookup.argtypes = [vp, i32p, i32p, C.c_int64, C.c_int32, i32p, i32p, i32p]
+        L.so_min_endpos.restype = C.c_int32
+        L.so_min_endpos.argtypes = [vp, C.c_int32]
         _lib = L
     return _lib
 
@@ -87,6 +91,21 @@ class CSam:
         kind = lib().so_select_samd(self.h, static.h if static is not None else None, int(start), int(n), int(len_bias),
                                     int(len_threshold), _p(out), _p(info))
         return kind, out.tolist(), info.tolist()
+
+    def batch_advance(self, cursors, tokens, counts=None):
+        """cursors [n, 2] int32 (state, matched), advanced in place by tokens [n, stride] (counts [n] or all)."""
+        assert cursors.dtype == np.int32 and cursors.flags.c_contiguous
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        c = None if counts is None else np.ascontiguousarray(counts, dtype=np.int32)
+        lib().so_batch_advance(self.h, _p(cursors), _p(t), t.shape[1], None if c is None else _p(c), len(cursors))
+
+    def batch_lookup(self, cursors, start, n_predicts):
+        """-> (state [n], matched [n], draft [n, n_predicts]) of StaticSAM.lookup + gen_draft for every cursor."""
+        n = len(cursors)
+        st, ln = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        dr = np.zeros((n, n_predicts), dtype=np.int32)
+        lib().so_batch_lookup(self.h, _p(cursors), _p(np.ascontiguousarray(start, dtype=np.int32)), n, int(n_predicts), _p(st), _p(ln), _p(dr))
+        return st, ln, dr
 
     def info(self):
         o = np.zeros(8, dtype=np.int64)

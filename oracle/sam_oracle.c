@@ -255,3 +255,26 @@ int64_t so_run_steps(sam_t **sams, int64_t R, const int32_t *tokens, const int32
         }
     return sum;
 }
+
+/* Many independent query cursors over ONE read-only automaton (the static SAM's use, static_sam.py:102-125): cur[i] =
+ * {state, matched}.  so_batch_advance = StaticSAM.transfer_tokens for every cursor (counts NULL = stride tokens each);
+ * so_batch_lookup = StaticSAM.lookup + gen_draft (no to_anc) with each cursor's start token, cursors unchanged. */
+void so_batch_advance(const sam_t *s, int32_t *cur, const int32_t *tokens, int64_t stride, const int32_t *counts, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t k = counts ? counts[i] : stride;
+        for (int64_t j = 0; j < k; ++j) so_step(s, &cur[2 * i], &cur[2 * i + 1], tokens[i * stride + j]);
+    }
+}
+
+void so_batch_lookup(const sam_t *s, const int32_t *cur, const int32_t *start, int64_t n, int32_t n_predicts, int32_t *out_state,
+                     int32_t *out_len, int32_t *out_draft) {
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t st = cur[2 * i], ln = cur[2 * i + 1];
+        so_step(s, &st, &ln, start[i]);
+        out_state[i] = st;
+        out_len[i] = ln;
+        if (out_draft) so_draft_samd(s, st, start[i], n_predicts, 0, out_draft + i * n_predicts);
+    }
+}
+
+int32_t so_min_endpos(const sam_t *s, int32_t state) { return s->end[state]; }

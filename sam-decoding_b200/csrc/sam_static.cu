@@ -466,12 +466,13 @@ extern "C" int samd_static_set_l2_window(samd_static_t h, void *stream, int64_t 
     SAMD_CUDA(cudaGetDeviceProperties(&prop, h->device));
     size_t carve = std::min((size_t)bytes, (size_t)prop.persistingL2CacheMaxSize);
     SAMD_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
-    // state records are contiguous in creation (= document) order; the window covers their prefix
-    // (root + the states of the first documents).  hitRatio scales the window down to the carve-out.
-    size_t span = std::min((size_t)h->dev.n_states * SAMD_REC * sizeof(int32_t), (size_t)prop.accessPolicyMaxWindowSize);
+    // State records are contiguous in creation (= document) order.  The window is the PREFIX that fits the carve-out
+    // (root, and the states of the first documents - where the states of short, frequent contexts are created), all
+    // of it persisting; everything else streams.
+    size_t span = std::min(std::min(carve, (size_t)h->dev.n_states * SAMD_REC * sizeof(int32_t)), (size_t)prop.accessPolicyMaxWindowSize);
     attr.accessPolicyWindow.base_ptr = (void *)h->dev.recs;
     attr.accessPolicyWindow.num_bytes = span;
-    attr.accessPolicyWindow.hitRatio = span <= carve ? 1.0f : (float)((double)carve / (double)span);
+    attr.accessPolicyWindow.hitRatio = 1.0f;
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     SAMD_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));

@@ -58,7 +58,11 @@ extern "C" int samd_dyn_create(int n_requests, int max_tokens, samd_dyn_t *out) 
     SAMD_CUDA(cudaMalloc(&a.meta, b_meta));
     h->bytes = (int64_t)(b_recs + b_slots + b_text + b_meta);
     *out = h;
-    return samd_dyn_reset(h, nullptr, nullptr);
+    // the arenas are filled on the default stream; the caller's first launch may come on any other (non-blocking) stream
+    // - torch's side streams do not order with the legacy default stream - so creation finishes the fill before returning
+    if (int rc = samd_dyn_reset(h, nullptr, nullptr)) return rc;
+    SAMD_CUDA(cudaDeviceSynchronize());
+    return 0;
 }
 
 extern "C" int samd_dyn_destroy(samd_dyn_t h) {
@@ -828,7 +832,7 @@ __device__ __forceinline__ void sc_redirect_scout(const int32_t *recs, const uin
 }
 
 template <bool kProf>
-__global__ void __maxnreg__(96) sam_step_scalar_kernel(StepParams P) {
+__device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
     __shared__ int s_mailbox[4 * SCOUT_MAX_TOKENS + 2];
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31;
@@ -868,7 +872,7 @@ __global__ void __maxnreg__(96) sam_step_scalar_kernel(StepParams P) {
             return;
         }
         const int peek = P.start_tok ? P.start_tok[r] : -1;
-        if (threadIdx.x < 64) {
+        if (threadIdx.x < 64 && !(P.has_static && blockDim.x == 64)) {
             sc_scout_walk<false>(recs, slots, P.dyn.bmask, text, meta[META_CUR], tk, k, peek, P.n_predicts, (long long)meta[META_N],
                                  (long long)P.dyn.s_cap, (blockDim.x > 64 && !P.has_static) ? s_mailbox : nullptr, P.prewalk);
             __threadfence_block();
@@ -1054,17 +1058,30 @@ __global__ void __maxnreg__(96) sam_step_scalar_kernel(StepParams P) {
     }
 }
 
+// Two builds of the same body: the wide one (96 registers, three warps: 7 CTAs per SM, enough for 1024 requests in one
+// wave) and a lean one (64 registers, two warps: 16 CTAs per SM) for batches so large that residency matters more than
+// the third warp - 4096 static-SAM cursors (config c3) would otherwise run in four waves.
+template <bool kProf>
+__global__ void __maxnreg__(96) sam_step_scalar_kernel(StepParams P) {
+    sam_step_scalar_body<kProf>(P);
+}
+__global__ void __maxnreg__(64) sam_step_scalar_lean_kernel(StepParams P) {
+    sam_step_scalar_body<false>(P);
+}
+
 static long long *g_dbg_cycles = nullptr;
 static int g_scouts = 2;
 static int g_variant = 1;
 static int g_prewalk = 0;
 static int g_ngram = 6;
+static int g_lean = -1;
 static int32_t *g_trace = nullptr;
 static int g_trace_cap = 0;
 extern "C" void samd_step_set_scouts(int on) { g_scouts = on; }
 extern "C" void samd_step_set_variant(int v) { g_variant = v; }
 extern "C" void samd_step_set_prewalk(int n) { g_prewalk = n < 0 ? 0 : n; }
 extern "C" void samd_step_set_ngram(int depth) { g_ngram = depth; }
+extern "C" void samd_step_set_lean(int mode) { g_lean = mode; }
 extern "C" void samd_step_set_trace(int32_t *trace_dev, int cap) {
     g_trace = trace_dev;
     g_trace_cap = trace_dev ? cap : 0;
@@ -1112,8 +1129,17 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
     // costs more than it brings - 49.2 vs 43.2 us per step)
     if (g_variant == 1) {
         // builder + cursor scout + (static cursor scout | redirect scout); one walking thread per warp
-        const int threads = g_scouts ? ((P.has_static || (a->tokens_dev && g_scouts > 1)) ? 96 : 64) : 32;
+        int threads = g_scouts ? ((P.has_static || (a->tokens_dev && g_scouts > 1)) ? 96 : 64) : 32;
+        static int n_sm = 0;
+        if (!n_sm) {
+            int dev = 0;
+            SAMD_CUDA(cudaGetDevice(&dev));
+            SAMD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const bool lean = g_lean >= 0 ? g_lean != 0 : P.dyn.n_requests > 7 * n_sm;      // more requests than one wave of the wide build
+        if (lean && threads > 64) threads = 64;
         if (P.dbg_cycles) sam_step_scalar_kernel<true><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
+        else if (lean) sam_step_scalar_lean_kernel<<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
         else sam_step_scalar_kernel<false><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
         samd_count_launch();
         SAMD_CUDA(cudaGetLastError());
