@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--only-verify", action="store_true", help="profiling aid: run only the c4 verify loop")
     ap.add_argument("--only-step", action="store_true", help="profiling aid: run only the c2 device loop")
     ap.add_argument("--scouts", type=int, default=2, help="profiling aid: scout warps of the step kernel (0 none, 1 cursor scouts, 2 all)")
+    ap.add_argument("--overlap", type=int, default=None, help="tuning aid: 1 overlapped / 0 two-barrier flow of the verify kernel")
     ap.add_argument("--lean", type=int, default=None, help="tuning aid: 1 lean / 0 wide build of the step kernel (default: by batch size)")
     ap.add_argument("--ngram", type=int, default=None, help="tuning aid: depth of the short-context scouts (-1 off)")
     ap.add_argument("--prewalk", type=int, default=None, help="tuning aid: draft tokens the scouts walk ahead for the next step")
@@ -332,6 +333,8 @@ def run_ours(a):
         K.lib().samd_step_set_ngram(a.ngram)
     if a.lean is not None:
         K.lib().samd_step_set_lean(a.lean)
+    if a.overlap is not None:
+        K.lib().samd_verify_set_overlap(a.overlap)
     launches0 = E.launch_count()
     if a.only_verify:                         # profiling aid (ncu): just the c4 loop
         print(json.dumps({"verify": bench_verify(a, dev, 6458.1, iters=6, warm=2)}))

@@ -38,6 +38,7 @@ struct samd_verify_s {
     unsigned long long *topk_part;  // [topk_items][TOPK] per-chunk top-8 lists
     long long topk_items;
     int *kv_start;                  // [max_batch] cache_len before the bump
+    int *req_done, *act_flag;       // [max_batch] each (overlapped flow)
     int max_batch, max_nodes, device, n_sms;
 };
 
@@ -45,6 +46,9 @@ struct VerifyParams {
     samd_verify_args a;
     unsigned long long *node_key;
     int *active, *counters, *kv_start;
+    int *req_done;                   // [max_batch] items of the request that have reported (overlapped flow)
+    int *act_flag;                   // [max_batch] launch epoch once move record [slot] is complete (overlapped flow)
+    int overlap;                     // 1 = walks as requests complete, ticketed row moves, no grid barrier
     int max_nodes, max_batch;
     int chunk, chunks_per_row, n_items1, n_items2, vec_ok, stage_cap;
     unsigned long long *topk_part;   // [n_items1][TOPK] per-chunk lists (top-k launches)
@@ -335,7 +339,8 @@ __device__ __forceinline__ size_t item_offset(const VerifyParams &P, const Item 
 }
 
 // counters[] slots (all re-armed by the kernel itself, so a launch can be captured in a CUDA graph and replayed)
-enum { CN_EPOCH = 0, CN_EXIT, CN_ARRIVE_A, CN_FLAG_A, CN_ARRIVE_B, CN_FLAG_B, CN_ACTIVE, CN_ARRIVE_C, CN_FLAG_C, CN_QUEUES = 32 };
+enum { CN_EPOCH = 0, CN_EXIT, CN_ARRIVE_A, CN_FLAG_A, CN_ARRIVE_B, CN_FLAG_B, CN_ACTIVE, CN_ARRIVE_C, CN_FLAG_C, CN_TICKET, CN_WALKS,
+       CN_QUEUES = 32 };
 // Work queues: one counter would be hit by every warp for every item, and same-address atomics serialise at about
 // 3 ns each on B200 (measured: 62k items took 135 us whatever their size) - so the dynamic items are dealt round-robin
 // into N_QUEUES queues, each with its own counter on its own 128-byte line.
@@ -362,6 +367,154 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
     int *s_tok = s_am + T;
     const uint16_t *logits = reinterpret_cast<const uint16_t *>(A.logits_dev);
 
+    // The walk of one request (samd/utils.py:127-141 + update_state + the move record), by one warp.
+    auto walk_request = [&](int b) {
+        // keys, tree tokens and this lane's path row are fetched together (one memory round trip); the walk
+        // itself then runs out of shared memory and registers
+        const int n_rows = A.n_nodes_dev ? A.n_nodes_dev[b] : T;
+        const int32_t *tok = A.tree_tokens_dev + (size_t)b * T;
+        const int n_paths = A.retrieve_dev ? (A.n_paths_dev ? A.n_paths_dev[b] : A.n_paths) : 1;
+        const int depth = A.retrieve_dev ? A.depth : n_rows;
+        constexpr int WD = 8;                                   // path depth held in registers
+        const bool fast = A.retrieve_dev && depth <= WD && n_paths <= 32;
+        int rp[WD];
+#pragma unroll
+        for (int j = 0; j < WD; ++j) rp[j] = (fast && lane < n_paths && j < depth) ? ri_at(P, b, lane, j) : -1;
+        int start = 0;
+        if (lane == 0 && A.cache_len_dev) start = A.cache_len_dev[b];
+        for (int i = lane; i < T; i += 32) {
+            unsigned long long *kp = &P.node_key[(size_t)b * P.max_nodes + i];
+            const unsigned long long k = __ldcg(kp);
+            s_tok[i] = i < n_rows ? tok[i] : 0;
+            const int am = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+            s_am[i] = am;
+            *kp = 0;                                            // re-arm for the next launch
+            if (A.out_node_argmax_dev && i < n_rows) A.out_node_argmax_dev[(size_t)b * T + i] = am;
+        }
+        __syncwarp();
+        unsigned int bestpk = 0;
+        if (fast) {
+            if (lane < n_paths) {
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j + 1 < WD; ++j) {
+                    if (j + 1 < depth && acc == j) {
+                        const int rowi = rp[j] < 0 ? n_rows - 1 : rp[j];          // -1 wraps to the last row
+                        const int cand = rp[j + 1] < 0 ? 0 : s_tok[rp[j + 1]];    // -1 selects the appended 0
+                        if (cand == s_am[rowi]) acc++;
+                    }
+                }
+                bestpk = ((unsigned)acc << 16) | (unsigned)(0xFFFF - lane);
+            }
+        } else {
+            for (int p = lane; p < n_paths; p += 32) {
+                int acc = 0;
+                int prev = ri_at(P, b, p, 0);
+                for (int j = 0; j + 1 < depth; ++j) {
+                    const int nxt = ri_at(P, b, p, j + 1);
+                    const int rowi = prev < 0 ? n_rows - 1 : prev;
+                    const int cand = nxt < 0 ? 0 : s_tok[nxt];
+                    if (cand != s_am[rowi]) break;
+                    acc++;
+                    prev = nxt;
+                }
+                bestpk = max(bestpk, ((unsigned)acc << 16) | (unsigned)(0xFFFF - p));   // max accept, first path
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bestpk = max(bestpk, __shfl_xor_sync(SAMD_FULL, bestpk, o));
+        const int acc = (int)(bestpk >> 16);
+        const int best = acc == 0 ? 0 : (int)(0xFFFF - (bestpk & 0xFFFF));
+        const int out_stride = A.retrieve_dev ? A.depth : T;
+        int moved = 0, last = 0, ix0 = -1;                     // ix0: this lane's accepted index for j = lane
+        for (int j0 = 0; j0 < out_stride; j0 += 32) {
+            const int j = j0 + lane;
+            int tk = -1, ix = -1;
+            if (fast) {                                         // the best path's row is in that lane's registers
+#pragma unroll
+                for (int q = 0; q < WD; ++q) {
+                    const int v = __shfl_sync(SAMD_FULL, rp[q], best);
+                    if (lane == q) ix = v;
+                }
+                if (j > acc) ix = -1;
+            } else if (j < out_stride && j <= acc) {
+                ix = ri_at(P, b, best, j);
+            }
+            if (j < out_stride && j <= acc) {
+                tk = ix < 0 ? 0 : s_tok[ix];
+                moved += ix != j;
+            }
+            if (j < out_stride) {
+                if (A.out_tokens_dev) A.out_tokens_dev[(size_t)b * out_stride + j] = tk;
+                if (A.out_indices_dev) A.out_indices_dev[(size_t)b * out_stride + j] = ix;
+            }
+            if (j0 == 0) ix0 = ix;
+            if (acc >= j0 && acc < j0 + 32) last = __shfl_sync(SAMD_FULL, ix, acc - j0);
+        }
+        if (lane == 0) {
+            if (A.out_best_dev) A.out_best_dev[b] = best;
+            if (A.out_accept_len_dev) A.out_accept_len_dev[b] = acc + 1;
+            if (A.out_next_token_dev) A.out_next_token_dev[b] = s_am[last < 0 ? n_rows - 1 : last];
+            if (A.cache_len_dev) A.cache_len_dev[b] = start + acc + 1;
+            P.kv_start[b] = start;
+        }
+        // publish: requests that really move rows append their move record {request, accept_len, start, first
+        // KV_GROUP source rows} to the compact active list of phase 2
+        moved = __reduce_add_sync(SAMD_FULL, moved);
+        if (P.n_items2 > 0) {
+            int slot = 0;
+            if (lane == 0 && moved > 0) slot = atomicAdd(&P.counters[CN_ACTIVE], 1);
+            slot = __shfl_sync(SAMD_FULL, slot, 0);
+            start = __shfl_sync(SAMD_FULL, start, 0);
+            if (moved > 0) {
+                int *rec = P.active + (size_t)slot * KV_REC;
+                if (lane == 0) rec[0] = b, rec[1] = acc + 1, rec[2] = start;
+                if (lane < KV_GROUP) rec[3 + lane] = lane <= acc ? ix0 : lane;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                if (P.overlap) {
+                    // the record (and the outputs phase 2 reads) first, then its flag, then the count of finished walks
+                    if (moved > 0) *reinterpret_cast<volatile int *>(&P.act_flag[slot]) = epoch;
+                    __threadfence();
+                    atomicAdd(&P.counters[CN_WALKS], 1);
+                } else if (atomicAdd(&P.counters[CN_ARRIVE_B], 1) == A.batch - 1) {  // barrier B: every walk is published
+                    P.counters[CN_ARRIVE_B] = 0;
+                    __threadfence();
+                    *reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_B]) = epoch;
+                }
+            }
+        }
+        if (P.overlap && lane == 0) P.req_done[b] = 0;          // re-armed for the next launch
+        __syncwarp();
+        if (P.overlap == 2 && P.n_items2 > 0 && moved > 0) {
+            // The source rows of this request's moves are known NOW, long before the row moves run (after the last
+            // walk): request them into L2 - every 128-byte line of every (tensor, head, row) - so that phase 2 reads hit L2
+            // (cp.async.bulk.prefetch.L2 takes a warp-uniform address: 10 k of them per request would be issued one
+            // by one; the per-lane prefetch covers 32 rows per instruction) (the 42 MB of config c4 fit three times) instead of scattered DRAM rows.
+            const int pairs = A.n_kv * A.n_heads;
+            int sj[KV_GROUP];
+#pragma unroll
+            for (int j = 0; j < KV_GROUP; ++j) {
+                const int v = __shfl_sync(SAMD_FULL, ix0, j);
+                sj[j] = (j >= 1 && j <= acc && v != j && v >= 0) ? v : -1;
+            }
+            const int lines = (A.row_bytes + 127) >> 7;
+            for (int w = lane; w < pairs; w += 32) {
+                const int kv = w / A.n_heads, hd = w - kv * A.n_heads;
+                const char *hb = reinterpret_cast<const char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.kv_ptrs_dev) + kv)) +
+                                 (size_t)b * A.kv_batch_stride + (size_t)hd * A.kv_head_stride;
+#pragma unroll
+                for (int j = 1; j < KV_GROUP; ++j)
+                    if (sj[j] >= 0)
+                        for (int l = 0; l < lines; ++l)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(hb + (size_t)(start + sj[j]) * A.kv_pos_stride + ((size_t)l << 7)));
+            }
+        }
+    };
+
+    int arrived = 0;                                           // lane 0: items of cur.b reported so far (overlapped flow)
     // ------------------------------ phase 1: row argmax -----------------------------------
     // Items (row chunks) are handed out dynamically - the first one per warp is its own index, the rest come from
     // a counter: measured on B200, equal static shares finish between 27 and 50 us after launch (the memory system
@@ -494,18 +647,45 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
                 }
                 if (lane == 0) {
                     unsigned long long *kp = &P.node_key[(size_t)cur.b * P.max_nodes + cur.t];
-                    if (C == 1) *reinterpret_cast<volatile unsigned long long *>(kp) = pk;
-                    else atomicMax(kp, pk);
+                    if constexpr (!kTopK) {
+                        if (P.overlap) {
+                            // The maximum comes back (so it HAS been performed at L2), and only then is the request's
+                            // arrival counted - the add's operand depends on the returned value.  Whoever counts the
+                            // request's last item therefore finds every row maximum in L2 without any fence.
+                            const unsigned long long old = atomicMax(kp, pk);
+                            int dep;
+                            asm volatile("and.b32 %0, %1, 0;" : "=r"(dep) : "r"((int)old));
+                            arrived = atomicAdd(&P.req_done[cur.b], 1 + dep) + 1;
+                        } else if (C == 1) *reinterpret_cast<volatile unsigned long long *>(kp) = pk;
+                        else atomicMax(kp, pk);
+                    } else {
+                        if (C == 1) *reinterpret_cast<volatile unsigned long long *>(kp) = pk;
+                        else atomicMax(kp, pk);
+                    }
                 }
-            } else if constexpr (kTopK) {
-                if (lane < TOPK) P.topk_part[(size_t)cur.item * TOPK + lane] = 0;   // dead row: empty list
+            } else {
+                if constexpr (kTopK) {
+                    if (lane < TOPK) P.topk_part[(size_t)cur.item * TOPK + lane] = 0;   // dead row: empty list
+                } else if (P.overlap && lane == 0) {
+                    arrived = atomicAdd(&P.req_done[cur.b], 1) + 1;                     // dead row: it still counts
+                }
             }
             if (!fetched) fetch_next();
+            if constexpr (!kTopK) {
+                if (P.overlap) {
+                    // the warp that reports a request's last item walks it at once (the next item's first loads are
+                    // already in flight): its row moves can start while the rest of the logits still stream
+                    const int done_b = __shfl_sync(SAMD_FULL, arrived == T * C ? cur.b : -1, 0);
+                    arrived = 0;
+                    if (done_b >= 0) walk_request(done_b);
+                }
+            }
         }
     }
     if (dbg && lane == 0) dbg[1] = samd_globaltimer();
 
     // ------------------------------ barrier A: every row maximum is published -----------------
+    if (!P.overlap) {
     if (lane == 0) __threadfence();                            // this warp's keys, before the CTA arrives
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -534,121 +714,9 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         }
         __syncwarp();
     }
-    for (int b = gwarp; b < A.batch; b += n_warps) {
-        // keys, tree tokens and this lane's path row are fetched together (one memory round trip); the walk
-        // itself then runs out of shared memory and registers
-        const int n_rows = A.n_nodes_dev ? A.n_nodes_dev[b] : T;
-        const int32_t *tok = A.tree_tokens_dev + (size_t)b * T;
-        const int n_paths = A.retrieve_dev ? (A.n_paths_dev ? A.n_paths_dev[b] : A.n_paths) : 1;
-        const int depth = A.retrieve_dev ? A.depth : n_rows;
-        constexpr int WD = 8;                                   // path depth held in registers
-        const bool fast = A.retrieve_dev && depth <= WD && n_paths <= 32;
-        int rp[WD];
-#pragma unroll
-        for (int j = 0; j < WD; ++j) rp[j] = (fast && lane < n_paths && j < depth) ? ri_at(P, b, lane, j) : -1;
-        int start = 0;
-        if (lane == 0 && A.cache_len_dev) start = A.cache_len_dev[b];
-        for (int i = lane; i < T; i += 32) {
-            unsigned long long *kp = &P.node_key[(size_t)b * P.max_nodes + i];
-            const unsigned long long k = __ldcg(kp);
-            s_tok[i] = i < n_rows ? tok[i] : 0;
-            const int am = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
-            s_am[i] = am;
-            *kp = 0;                                            // re-arm for the next launch
-            if (A.out_node_argmax_dev && i < n_rows) A.out_node_argmax_dev[(size_t)b * T + i] = am;
-        }
-        __syncwarp();
-        unsigned int bestpk = 0;
-        if (fast) {
-            if (lane < n_paths) {
-                int acc = 0;
-#pragma unroll
-                for (int j = 0; j + 1 < WD; ++j) {
-                    if (j + 1 < depth && acc == j) {
-                        const int rowi = rp[j] < 0 ? n_rows - 1 : rp[j];          // -1 wraps to the last row
-                        const int cand = rp[j + 1] < 0 ? 0 : s_tok[rp[j + 1]];    // -1 selects the appended 0
-                        if (cand == s_am[rowi]) acc++;
-                    }
-                }
-                bestpk = ((unsigned)acc << 16) | (unsigned)(0xFFFF - lane);
-            }
-        } else {
-            for (int p = lane; p < n_paths; p += 32) {
-                int acc = 0;
-                int prev = ri_at(P, b, p, 0);
-                for (int j = 0; j + 1 < depth; ++j) {
-                    const int nxt = ri_at(P, b, p, j + 1);
-                    const int rowi = prev < 0 ? n_rows - 1 : prev;
-                    const int cand = nxt < 0 ? 0 : s_tok[nxt];
-                    if (cand != s_am[rowi]) break;
-                    acc++;
-                    prev = nxt;
-                }
-                bestpk = max(bestpk, ((unsigned)acc << 16) | (unsigned)(0xFFFF - p));   // max accept, first path
-            }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) bestpk = max(bestpk, __shfl_xor_sync(SAMD_FULL, bestpk, o));
-        const int acc = (int)(bestpk >> 16);
-        const int best = acc == 0 ? 0 : (int)(0xFFFF - (bestpk & 0xFFFF));
-        const int out_stride = A.retrieve_dev ? A.depth : T;
-        int moved = 0, last = 0, ix0 = -1;                     // ix0: this lane's accepted index for j = lane
-        for (int j0 = 0; j0 < out_stride; j0 += 32) {
-            const int j = j0 + lane;
-            int tk = -1, ix = -1;
-            if (fast) {                                         // the best path's row is in that lane's registers
-#pragma unroll
-                for (int q = 0; q < WD; ++q) {
-                    const int v = __shfl_sync(SAMD_FULL, rp[q], best);
-                    if (lane == q) ix = v;
-                }
-                if (j > acc) ix = -1;
-            } else if (j < out_stride && j <= acc) {
-                ix = ri_at(P, b, best, j);
-            }
-            if (j < out_stride && j <= acc) {
-                tk = ix < 0 ? 0 : s_tok[ix];
-                moved += ix != j;
-            }
-            if (j < out_stride) {
-                if (A.out_tokens_dev) A.out_tokens_dev[(size_t)b * out_stride + j] = tk;
-                if (A.out_indices_dev) A.out_indices_dev[(size_t)b * out_stride + j] = ix;
-            }
-            if (j0 == 0) ix0 = ix;
-            if (acc >= j0 && acc < j0 + 32) last = __shfl_sync(SAMD_FULL, ix, acc - j0);
-        }
-        if (lane == 0) {
-            if (A.out_best_dev) A.out_best_dev[b] = best;
-            if (A.out_accept_len_dev) A.out_accept_len_dev[b] = acc + 1;
-            if (A.out_next_token_dev) A.out_next_token_dev[b] = s_am[last < 0 ? n_rows - 1 : last];
-            if (A.cache_len_dev) A.cache_len_dev[b] = start + acc + 1;
-            P.kv_start[b] = start;
-        }
-        // publish: requests that really move rows append their move record {request, accept_len, start, first
-        // KV_GROUP source rows} to the compact active list of phase 2
-        moved = __reduce_add_sync(SAMD_FULL, moved);
-        if (P.n_items2 > 0) {
-            int slot = 0;
-            if (lane == 0 && moved > 0) slot = atomicAdd(&P.counters[CN_ACTIVE], 1);
-            slot = __shfl_sync(SAMD_FULL, slot, 0);
-            start = __shfl_sync(SAMD_FULL, start, 0);
-            if (moved > 0) {
-                int *rec = P.active + (size_t)slot * KV_REC;
-                if (lane == 0) rec[0] = b, rec[1] = acc + 1, rec[2] = start;
-                if (lane < KV_GROUP) rec[3 + lane] = lane <= acc ? ix0 : lane;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                if (atomicAdd(&P.counters[CN_ARRIVE_B], 1) == A.batch - 1) {  // barrier B: every walk is published
-                    P.counters[CN_ARRIVE_B] = 0;
-                    __threadfence();
-                    *reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_B]) = epoch;
-                }
-            }
-        }
-        __syncwarp();
-    }
+    }   // !P.overlap
+    if (!P.overlap)
+        for (int b = gwarp; b < A.batch; b += n_warps) walk_request(b);
 
     // ------------------------------ phase 1c: per-row top-8 (token_recycle.py:36-47) ----------
     // The chunks' lists are merged row by row (rows strided over every warp); the row that comes last in (request,
@@ -718,7 +786,70 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
     // The moved rows of the active requests are flattened into 16-byte units and strided over every lane of the
     // grid.  (Dedicating a quarter of the CTAs to row moves that overlap the logits stream was measured slower,
     // 111 vs 90 us on C4: the moves are bound by DRAM row activations and steal DRAM cycles from the stream.)
-    if (P.n_items2 > 0) {
+    if (P.n_items2 > 0 && P.overlap == 1) {
+        // Overlapped flow: a warp that finds no more logits to stream takes TICKETS - (move record, chunk of its 16-byte
+        // units) - and waits only for that record's flag, so the rows of the requests that completed first are moved
+        // while the later ones are still being streamed and walked.  A ticket beyond the last record ends the warp
+        // once every walk has reported.
+        const int cols = A.row_bytes >> 4;
+        const int per_tensor = A.n_heads * cols;
+        const int per_req = A.n_kv * per_tensor;
+        constexpr int UNITS = 256;                             // 16-byte units (x accepted rows) per ticket: 8 passes of a warp
+        const int n_ch = (per_req + UNITS - 1) / UNITS;
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&P.counters[CN_TICKET], 1);
+        while (true) {
+            t = __shfl_sync(SAMD_FULL, t, 0);
+            const int a_i = t / n_ch, ch = t - a_i * n_ch;
+            if (a_i >= A.batch) break;                          // beyond any possible record
+            int have = 0;
+            if (lane == 0) {
+                t = atomicAdd(&P.counters[CN_TICKET], 1);       // the next ticket is requested one ahead
+                unsigned ns = 200;
+                for (int spin = 0;; ++spin) {
+                    if (*reinterpret_cast<volatile int *>(&P.act_flag[a_i]) == epoch) {
+                        have = 1;
+                        break;
+                    }
+                    if ((spin & 3) == 3 && *reinterpret_cast<volatile int *>(&P.counters[CN_WALKS]) == A.batch) {
+                        have = *reinterpret_cast<volatile int *>(&P.act_flag[a_i]) == epoch;   // flags precede the count
+                        break;
+                    }
+                    __nanosleep(ns);                            // (thousands of warps may be waiting: back off)
+                    if (ns < 3200) ns *= 2;
+                }
+                __threadfence();
+            }
+            have = __shfl_sync(SAMD_FULL, have, 0);
+            if (!have) break;                                   // every walk has reported and there is no such record
+            const int *m = P.active + (size_t)a_i * KV_REC;
+            const int b = __ldcg(m), acc1 = __ldcg(m + 1), start = __ldcg(m + 2);
+            int src0[KV_GROUP];
+#pragma unroll
+            for (int q = 0; q < KV_GROUP; ++q) src0[q] = __ldcg(m + 3 + q);
+            const int u_end = min(per_req, (ch + 1) * UNITS);
+            for (int unit = ch * UNITS + lane; unit < u_end; unit += 32) {
+                const int kv = unit / per_tensor;
+                const int w = unit - kv * per_tensor;
+                const int hd = w / cols, col = w - hd * cols;
+                char *hb = reinterpret_cast<char *>(__ldg(reinterpret_cast<const unsigned long long *>(A.kv_ptrs_dev) + kv)) +
+                           (size_t)b * A.kv_batch_stride + (size_t)hd * A.kv_head_stride + ((size_t)col << 4);
+                for (int j0 = 0; j0 < acc1; j0 += KV_GROUP) {
+                    uint4 val[KV_GROUP];
+                    int src[KV_GROUP];
+#pragma unroll
+                    for (int q = 0; q < KV_GROUP; ++q)
+                        src[q] = j0 == 0 ? src0[q] : ((j0 + q < acc1) ? __ldcg(A.out_indices_dev + (size_t)b * A.depth + j0 + q) : j0 + q);
+#pragma unroll
+                    for (int q = 0; q < KV_GROUP; ++q)
+                        if (src[q] != j0 + q) val[q] = *reinterpret_cast<const uint4 *>(hb + (size_t)(start + src[q]) * A.kv_pos_stride);
+#pragma unroll
+                    for (int q = 0; q < KV_GROUP; ++q)
+                        if (src[q] != j0 + q) *reinterpret_cast<uint4 *>(hb + (size_t)(start + j0 + q) * A.kv_pos_stride) = val[q];
+                }
+            }
+        }
+    } else if (P.n_items2 > 0) {
         const int cols = A.row_bytes >> 4;                      // 16-byte columns per (head,row)
         const int per_tensor = A.n_heads * cols;
         const long long per_req = (long long)A.n_kv * per_tensor;
@@ -726,7 +857,8 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         int *s_meta = s_am_all + VW * 2 * T;
         __syncthreads();
         if (threadIdx.x == 0) {                                 // one poller per CTA, plain loads, backoff
-            while (*reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_B]) != epoch) __nanosleep(200);
+            if (P.overlap) while (*reinterpret_cast<volatile int *>(&P.counters[CN_WALKS]) != A.batch) __nanosleep(200);
+            else while (*reinterpret_cast<volatile int *>(&P.counters[CN_FLAG_B]) != epoch) __nanosleep(200);
             __threadfence();
         }
         __syncthreads();
@@ -809,6 +941,8 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         if (atomicAdd(&P.counters[CN_EXIT], 1) == n_ctas - 1) {
             P.counters[CN_EXIT] = 0;
             P.counters[CN_ACTIVE] = 0;
+            P.counters[CN_TICKET] = 0;
+            P.counters[CN_WALKS] = 0;
             for (int q = 0; q < N_QUEUES; ++q) P.counters[CN_QUEUES + q * QUEUE_STRIDE] = 0;
             __threadfence();
             *reinterpret_cast<volatile int *>(&P.counters[CN_EPOCH]) = epoch;
@@ -828,6 +962,10 @@ extern "C" int samd_verify_create(int max_batch, int max_nodes, samd_verify_t *o
     SAMD_CUDA(cudaMalloc(&h->active, (size_t)max_batch * KV_REC * sizeof(int)));
     SAMD_CUDA(cudaMalloc(&h->counters, CN_WORDS * sizeof(int)));
     SAMD_CUDA(cudaMalloc(&h->kv_start, (size_t)max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMalloc(&h->req_done, (size_t)max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMalloc(&h->act_flag, (size_t)max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMemset(h->req_done, 0, (size_t)max_batch * sizeof(int)));
+    SAMD_CUDA(cudaMemset(h->act_flag, 0, (size_t)max_batch * sizeof(int)));
     h->topk_items = std::max<long long>((long long)max_batch * max_nodes * 16, 32768);
     SAMD_CUDA(cudaMalloc(&h->topk_part, (size_t)h->topk_items * 8 * sizeof(unsigned long long)));
     SAMD_CUDA(cudaMemset(h->node_key, 0, (size_t)max_batch * max_nodes * sizeof(unsigned long long)));
@@ -845,6 +983,8 @@ extern "C" int samd_verify_destroy(samd_verify_t h) {
     cudaFree(h->active);
     cudaFree(h->counters);
     cudaFree(h->kv_start);
+    cudaFree(h->req_done);
+    cudaFree(h->act_flag);
     cudaFree(h->topk_part);
     delete h;
     return 0;
@@ -852,6 +992,8 @@ extern "C" int samd_verify_destroy(samd_verify_t h) {
 
 static int g_chunk_override = 0;
 static int g_min_chunk = 2048;
+static int g_overlap = 0;
+extern "C" void samd_verify_set_overlap(int on) { g_overlap = on; }
 static unsigned long long *g_dbg_times = nullptr;
 extern "C" void samd_verify_set_debug_times(uint64_t *times_dev) { g_dbg_times = (unsigned long long *)times_dev; }
 extern "C" void samd_verify_set_chunk(int elements) { g_chunk_override = elements; }
@@ -881,11 +1023,14 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     P.counters = h->counters;
     P.max_batch = h->max_batch;
     P.kv_start = h->kv_start;
+    P.req_done = h->req_done;
+    P.act_flag = h->act_flag;
     P.dbg_times = g_dbg_times;
     P.max_nodes = h->max_nodes;
     P.stage_cap = move ? std::min(a->batch, 512) : 0;
     const size_t smem = ((size_t)VW * 2 * a->n_nodes + (size_t)P.stage_cap * (3 + KV_GROUP)) * sizeof(int);
     const bool topk = a->out_topk_dev != nullptr;
+    P.overlap = topk ? 0 : g_overlap;
     SAMD_REQUIRE(!a->recycle_table_dev || (topk && a->recycle_owner_dev),
                  "samd_verify_compact: a recycle table needs out_topk_dev and recycle_owner_dev");
     SAMD_REQUIRE(!topk || a->vocab >= TOPK, "samd_verify_compact: top-8 needs a vocabulary of at least 8");

@@ -112,6 +112,7 @@ SYMBOLS = {
     "samd_verify_compact": (C.c_int, [vp, C.POINTER(VerifyArgs), vp]),
     "samd_recycle_gen_tree": (C.c_int, [vp, C.c_int32, vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "samd_verify_set_chunk": (None, [C.c_int]),
+    "samd_verify_set_overlap": (None, [C.c_int]),
     "samd_verify_set_debug_times": (None, [C.c_void_p]),
 }
 

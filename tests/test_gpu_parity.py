@@ -245,9 +245,20 @@ def test_verify_sequence_golden():
     assert (out["best"] == 0).all()
 
 
-def test_kv_compaction_golden():
-    """select_indices through the fused kernel: the fixture's 16 cases as one batch of 16 requests."""
+@pytest.mark.parametrize("overlap", [0, 1, 2])
+def test_kv_compaction_golden(overlap):
+    """select_indices through the fused kernel: the fixture's 16 cases as one batch of 16 requests.  All three flows of
+    the kernel: 0 = stream / barrier / walks / barrier / row moves (the default), 1 = walks as requests complete and
+    ticketed row moves, 2 = early walks + L2 prefetch of the source rows (the two measured alternatives)."""
     E, K = _engine_mod()
+    K.lib().samd_verify_set_overlap(overlap)
+    try:
+        _kv_compaction_golden(E, K)
+    finally:
+        K.lib().samd_verify_set_overlap(0)
+
+
+def _kv_compaction_golden(E, K):
     z = load("verify.npz")
     init = torch.from_numpy(z["kv/init_bits"]).view(torch.bfloat16)            # [2L, 1, H, ML, DH]
     cases = z["kv/cases"]
@@ -267,6 +278,12 @@ def test_kv_compaction_golden():
         got = torch.stack([t[c] for t in kv]).view(torch.int16).cpu().numpy()
         assert np.array_equal(got, after[c][:, 0]), c
         assert cache_len[c].item() == cases[c][1] + z["bf16/accept_len"][sel[c]]
+    assert np.array_equal(out["accept_len"].cpu().numpy(), z["bf16/accept_len"][sel])
+    # a second launch on the same scratch (self re-arming counters): nothing left to move, lengths bump again
+    before = [t.clone() for t in kv]
+    ver.verify(lg, tok, _dev_i32(z["retrieve"]), cache_len=None, move_kv=False)
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(before, kv))
 
 
 # --------------------------------------------------------------------------------------
