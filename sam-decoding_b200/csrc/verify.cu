@@ -1038,6 +1038,11 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     auto kern = a->dtype == SAMD_DTYPE_BF16   ? (topk ? verify_compact_kernel<SAMD_DTYPE_BF16, true> : verify_compact_kernel<SAMD_DTYPE_BF16, false>)
                 : a->dtype == SAMD_DTYPE_FP16 ? (topk ? verify_compact_kernel<SAMD_DTYPE_FP16, true> : verify_compact_kernel<SAMD_DTYPE_FP16, false>)
                                               : (topk ? verify_compact_kernel<SAMD_DTYPE_FP32, true> : verify_compact_kernel<SAMD_DTYPE_FP32, false>);
+    if (smem > 48 * 1024) {
+        // large path tables (eval_posterior verifies P*D rows as nodes): beyond 48 KB the kernel has to opt in
+        SAMD_REQUIRE(smem <= 200 * 1024, "samd_verify_compact: n_nodes too large for the per-warp node tables in shared memory");
+        SAMD_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     int per_sm = h->occ_per_sm[a->dtype + (topk ? 3 : 0)];
     if (per_sm <= 0 || smem > 8192) {                           // cached for the common (small) shared-memory sizes
         SAMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, VT, smem > 8192 ? smem : 8192));

@@ -75,7 +75,9 @@ class RaggedKVCache(Cache):
         self._bidx = torch.arange(batch, device=device)[:, None]
 
     def begin(self, n_new: int, kv_len: int):
-        self.rows = self.cache_len.long()[:, None] + torch.arange(n_new, device=self.kv.device)[None, :]
+        # (clamped: a finished request still rides along in the batch; its rows may be written past its end, never past
+        # the cache)
+        self.rows = (self.cache_len.long()[:, None] + torch.arange(n_new, device=self.kv.device)[None, :]).clamp_(max=self.max_len - 1)
         self.kv_len = kv_len
 
     def write(self, k, v, layer):
@@ -186,6 +188,13 @@ class BatchedSamdDecoder:
         assert len(prompts) == B
         lens = torch.tensor([len(p) for p in prompts], dtype=torch.int32, device=dev)
         n_max = int(lens.max())
+        # the reference stops a request before a step that could run past the cache (samd_model.py:251-254); here the
+        # prompt itself must leave room for one step, and a request that gets within one step of the end is finished
+        if n_max + T > self.cache.max_len:
+            raise K.SamdError(f"prompt of {n_max} tokens + one decode step of {T} does not fit max_cache_len={self.cache.max_len}")
+        if n_max + max_new_tokens + T > self.dyn.max_tokens:
+            raise K.SamdError(f"prompt + max_new_tokens + one step = {n_max + max_new_tokens + T} exceeds the automaton "
+                              f"capacity max_tokens={self.dyn.max_tokens}")
         ids = torch.zeros(B, n_max, dtype=torch.long, device=dev)
         for b, p in enumerate(prompts):
             ids[b, :len(p)] = torch.as_tensor(p, dtype=torch.long)
@@ -210,8 +219,10 @@ class BatchedSamdDecoder:
         steps, accept_hist, res = 0, [], None
         # ---- decode ---------------------------------------------------------------------------
         while True:
+            # a request whose next step could run past the cache is finished (samd_model.py:251-254)
+            done = done | (self.cache.cache_len + T > self.cache.max_len)
             self.eng.step(acc_tokens, acc_count, start)                            # update(accepted) + lookup(start): one launch
-            kv_len = int(self.cache.cache_len.max()) + T
+            kv_len = min(int(self.cache.cache_len.max()) + T, self.cache.max_len)
             self.cache.begin(T, kv_len)
             saved_len = self.cache.cache_len.clone()
             if self.tree is None:

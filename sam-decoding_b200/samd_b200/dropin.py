@@ -34,6 +34,8 @@ def _as_i32_row(tokens, device) -> torch.Tensor:
     """[1, k] int32 CUDA tensor from a python list / numpy array / torch tensor."""
     if isinstance(tokens, torch.Tensor):
         t = tokens.reshape(1, -1)
+        if t.numel() and not t.dtype.is_floating_point and (bool((t < 0).any()) or bool((t >= 2 ** 31 - 1).any())):
+            raise ValueError("token ids must be in [0, 2^31 - 2] (the flat automaton reserves -1 for free edges)")
         return t.to(device=device, dtype=torch.int32).contiguous()
     a = np.asarray(tokens, dtype=np.int64).reshape(1, -1)
     if a.size and (a.min() < 0 or a.max() >= 2 ** 31 - 1):

@@ -83,6 +83,17 @@ class DynSamBatch:
             K.check(K.lib().samd_dyn_meta(self._h, m.ctypes.data_as(K.c_i32p)), "samd_dyn_meta")
         return m
 
+    def check(self):
+        """Raise when a request was handed a token it could not take (synchronises): a full arena (grow with grown())
+        or a negative token id.  The step kernel only raises per-request flags - it never stops a launch - so callers
+        that size `max_tokens` from prompt + max_new_tokens call this once at the end; DraftEngine.step documents it."""
+        st = self.stats()
+        if st["overflowed"]:
+            raise K.SamdError(f"{st['overflowed']} request(s) ran out of arena capacity (max_tokens={self.max_tokens}): "
+                              "tokens were not appended; grow the batch (DynSamBatch.grown) or size it for prompt + new tokens")
+        if st["bad_tokens"]:
+            raise K.SamdError(f"{st['bad_tokens']} request(s) were handed a negative token id (-1 marks a free edge slot)")
+
     def grown(self, new_max_tokens: int) -> "DynSamBatch":
         """A new batch with a larger capacity holding the same automata (samd_dyn_grow)."""
         new = DynSamBatch.__new__(DynSamBatch)
@@ -253,7 +264,9 @@ class DraftEngine:
     def step(self, tokens: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
              start_tok: Optional[torch.Tensor] = None, out_buf: Optional[torch.Tensor] = None):
         """update(tokens[:, :counts]) then lookup(start_tok); either half may be omitted.  `out_buf` (same
-        layout as self.out_buf, device or pinned host memory) redirects every output."""
+        layout as self.out_buf, device or pinned host memory) redirects every output.
+        Token ids must be non-negative (-1 is the layout's free-slot marker) and a request's history must fit
+        `dyn.max_tokens`: a violation never stops the launch, it raises the request's flag - `dyn.check()` reports it."""
         a = self._args
         a.dyn = self.dyn.handle
         a.stat = self.static.handle if self.static is not None else None
