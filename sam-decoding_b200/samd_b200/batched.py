@@ -182,8 +182,59 @@ class BatchedSamdDecoder:
                                move_kv=True, n_nodes=self._n_nodes[kind].contiguous(), n_paths=self._n_paths[kind].contiguous(),
                                out=res, recycle=self.table)
 
+    # ---- one decode step, entirely on the device (no host read anywhere: it is what gets captured in a CUDA graph) ----
+    def _step_body(self, kv_len: int, max_new_tokens: int):
+        st, T = self._st, self.T
+        cache = self.cache
+        # a request whose step could run past the cache is finished (samd_model.py:251-254)
+        st["done"].logical_or_(cache.cache_len + T > cache.max_len)
+        self.eng.step(st["acc_tokens"], st["acc_count"], st["start"])              # update(accepted) + lookup(start): one launch
+        cache.begin(T, kv_len)
+        saved_len = cache.cache_len.clone()
+        if self.tree is None:
+            draft = self.eng.draft
+            draft[:, 0] = st["start"]                                              # short matches verify the start token only
+            pos = cache.cache_len.long()[:, None] + self._ar[None, :]
+            logits = self.lm(input_ids=draft.long(), position_ids=pos, past_key_values=cache,
+                             attention_mask=self._mask(T, kv_len, cache.cache_len)).logits
+            res = self.ver.verify(logits.contiguous(), draft, None, cache_len=cache.cache_len, out=st["res"])
+        else:
+            res = self._tree_step(st["start"], kv_len, st["res"])
+        st["res"] = res
+        done = st["done"]
+        n_acc = torch.where(done, torch.zeros_like(res["accept_len"]), res["accept_len"])
+        ar = self._ar[:res["tokens"].shape[1]]
+        if self.eos is not None:                                                   # truncate at the first EOS (samd_model.py:257-263)
+            is_eos = (res["tokens"] == self.eos) & (ar[None, :] < n_acc[:, None])
+            first = torch.where(is_eos.any(1), is_eos.int().argmax(1).int() + 1, n_acc)
+            done.logical_or_(is_eos.any(1))
+            n_acc = torch.minimum(n_acc, first)
+        room = (max_new_tokens - st["out_len"]).clamp(min=0)
+        n_emit = torch.minimum(n_acc, room)
+        out = st["out"]
+        cols = st["out_len"].long()[:, None] + ar[None, :]
+        keep = ar[None, :] < n_emit[:, None]
+        out.scatter_(1, torch.where(keep, cols, torch.full_like(cols, out.shape[1] - 1)),
+                     torch.where(keep, res["tokens"], torch.zeros_like(res["tokens"])))
+        st["out_len"].add_(n_emit)
+        done.logical_or_(st["out_len"] >= max_new_tokens)
+        cache.cache_len.copy_(saved_len + n_acc)                                   # finished requests stop advancing
+        st["acc_tokens"].copy_(res["tokens"])
+        st["acc_count"].copy_(n_acc)
+        st["start"].copy_(res["next_token"])
+        st["hist"].index_copy_(0, st["step"], n_acc[None, :])
+        st["step"].add_(1)
+        # what the host reads every `check_every` steps: [all finished?, longest cache]
+        st["flag"][0] = done.all().to(torch.int32)
+        st["flag"][1] = cache.cache_len.max()
+
     @torch.inference_mode()
-    def generate(self, prompts: Sequence[Sequence[int]], max_new_tokens: int):
+    def generate(self, prompts: Sequence[Sequence[int]], max_new_tokens: int, graph: bool = True, check_every: int = 4):
+        """Lossless batched speculative decoding.  The decode step has no host synchronisation in it: it is captured
+        once per key-length bucket (64 positions) as a CUDA graph and replayed; the host reads a two-word flag (all
+        finished / longest cache) once every `check_every` steps - 1 / check_every host syncs per step - and sizes
+        the next steps' key length from that bound.  A finished batch may therefore run up to check_every - 1 idle
+        steps (every request done: nothing is emitted).  graph=False runs the same body eagerly."""
         B, T, dev = self.B, self.T, self.device
         assert len(prompts) == B
         lens = torch.tensor([len(p) for p in prompts], dtype=torch.int32, device=dev)
@@ -210,51 +261,92 @@ class BatchedSamdDecoder:
         if self.tree is not None:                                                  # TokenRecycle.update over the prompt rows
             valid = torch.arange(n_max, device=dev)[None, :] < lens[:, None]
             self.table.update(ids[valid].to(torch.int32), logits[valid])
-        start = logits[torch.arange(B, device=dev), lens.long() - 1].argmax(-1).to(torch.int32)
-        out = torch.zeros(B, max_new_tokens + T, dtype=torch.int32, device=dev)
-        out_len = torch.zeros(B, dtype=torch.int32, device=dev)
-        done = torch.zeros(B, dtype=torch.bool, device=dev)
-        acc_tokens = torch.zeros(B, T, dtype=torch.int32, device=dev)
-        acc_count = torch.zeros(B, dtype=torch.int32, device=dev)
-        steps, accept_hist, res = 0, [], None
+            if not self.ver_bound:
+                self.ver.bind_kv([self.cache.kv[i] for i in range(self.cache.kv.shape[0])])
+                self.ver_bound = True
+        max_steps = max_new_tokens + check_every + 1
+        width = T if self.tree is None else self._ret.shape[2]
+        first_tok = logits[torch.arange(B, device=dev), lens.long() - 1].argmax(-1).to(torch.int32)
+        key = (max_new_tokens, max_steps, width)
+        if getattr(self, "_st_key", None) != key:
+            # the step's state lives in tensors that persist across generate() calls: the captured graphs refer to them
+            mk = lambda *sh: torch.zeros(*sh, dtype=torch.int32, device=dev)
+            self._st = dict(start=mk(B), acc_tokens=mk(B, width), acc_count=mk(B), out=mk(B, max_new_tokens + T), out_len=mk(B),
+                            done=torch.zeros(B, dtype=torch.bool, device=dev), hist=mk(max_steps, B),
+                            step=torch.zeros(1, dtype=torch.long, device=dev), flag=mk(2), res=None)
+            self._st_key, self._graphs = key, {}
+        else:
+            for k in ("acc_tokens", "acc_count", "out", "out_len", "done", "hist", "step", "flag"):
+                self._st[k].zero_()
+        self._st["start"].copy_(first_tok)
+        flag_host = torch.zeros(2, dtype=torch.int32).pin_memory()
         # ---- decode ---------------------------------------------------------------------------
-        while True:
-            # a request whose next step could run past the cache is finished (samd_model.py:251-254)
-            done = done | (self.cache.cache_len + T > self.cache.max_len)
-            self.eng.step(acc_tokens, acc_count, start)                            # update(accepted) + lookup(start): one launch
-            kv_len = min(int(self.cache.cache_len.max()) + T, self.cache.max_len)
-            self.cache.begin(T, kv_len)
-            saved_len = self.cache.cache_len.clone()
-            if self.tree is None:
-                draft = self.eng.draft
-                draft[:, 0] = start                                                # short matches verify the start token only
-                pos = self.cache.cache_len.long()[:, None] + self._ar[None, :]
-                logits = self.lm(input_ids=draft.long(), position_ids=pos, past_key_values=self.cache,
-                                 attention_mask=self._mask(T, kv_len, self.cache.cache_len)).logits
-                res = self.ver.verify(logits.contiguous(), draft, None, cache_len=self.cache.cache_len, out=res)
-            else:
-                res = self._tree_step(start, kv_len, res)
-            n_acc = torch.where(done, torch.zeros_like(res["accept_len"]), res["accept_len"])
-            ar = self._ar[:res["tokens"].shape[1]]
-            if self.eos is not None:                                               # truncate at the first EOS (samd_model.py:257-263)
-                is_eos = (res["tokens"] == self.eos) & (ar[None, :] < n_acc[:, None])
-                first = torch.where(is_eos.any(1), is_eos.int().argmax(1).int() + 1, n_acc)
-                done = done | is_eos.any(1)
-                n_acc = torch.minimum(n_acc, first)
-            room = (max_new_tokens - out_len).clamp(min=0)
-            n_emit = torch.minimum(n_acc, room)
-            cols = out_len.long()[:, None] + ar[None, :]
-            keep = ar[None, :] < n_emit[:, None]
-            out.scatter_(1, torch.where(keep, cols, torch.full_like(cols, max_new_tokens + T - 1)),
-                         torch.where(keep, res["tokens"], torch.zeros_like(res["tokens"])))
-            out_len = out_len + n_emit
-            done = done | (out_len >= max_new_tokens)
-            self.cache.cache_len.copy_(saved_len + n_acc)                           # finished requests stop advancing
-            acc_tokens, acc_count, start = res["tokens"], n_acc, res["next_token"]
+        max_accept = width                     # the most one step can add to a request's cache
+        kv_hi, since, steps, syncs = n_max, 0, 0, 0
+        graphs = self._graphs
+        self.last_graphed = False
+        while steps < max_steps - 1:
+            kv_len = min((kv_hi + since * max_accept + T + 63) // 64 * 64, self.cache.max_len)
+            if graph:
+                g = graphs.get(kv_len)
+                if g is None:
+                    # warm-up run on a side stream (allocations, lazy initialisation), state restored, then the capture
+                    snap = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self._st.items() if k != "res"}
+                    snap_len = self.cache.cache_len.clone()
+                    snap_dyn = E.DynSamBatch(B, self.dyn.max_tokens, dev)
+                    snap_dyn.copy_from(self.dyn)
+                    snap_cur = self.eng.static_cursor.clone() if self.eng.static_cursor is not None else None
+                    snap_tab = (self.table.table.clone(), self.table.owner.clone()) if self.tree is not None else None
+                    side = torch.cuda.Stream(dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        self._step_body(kv_len, max_new_tokens)
+                    torch.cuda.current_stream(dev).wait_stream(side)
+
+                    def restore():
+                        for k, v in snap.items():
+                            if torch.is_tensor(v):
+                                self._st[k].copy_(v)
+                        self.cache.cache_len.copy_(snap_len)
+                        self.dyn.copy_from(snap_dyn)
+                        if snap_cur is not None:
+                            self.eng.static_cursor.copy_(snap_cur)
+                        if snap_tab is not None:
+                            self.table.table.copy_(snap_tab[0])
+                            self.table.owner.copy_(snap_tab[1])
+
+                    restore()
+                    torch.cuda.synchronize(dev)
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._step_body(kv_len, max_new_tokens)
+                        graphs[kv_len] = g
+                        self.last_graphed = True
+                    except Exception:                      # an LM whose forward cannot be captured: same body, eagerly
+                        graph = False
+                        torch.cuda.synchronize(dev)
+                    restore()                              # (capture does not run the work; the warm-up did)
+                    snap_dyn.close()
+                if graph:
+                    graphs[kv_len].replay()
+                    self.last_graphed = True
+            if not graph:
+                self._step_body(kv_len, max_new_tokens)
             steps += 1
-            accept_hist.append(n_acc)
-            if bool(done.all()):                                                   # the step's one host sync
-                break
-        lens_out = out_len.tolist()
-        rows = out.tolist()
-        return [rows[b][:lens_out[b]] for b in range(B)], dict(steps=steps, accept_lengths=torch.stack(accept_hist, 1).tolist())
+            since += 1
+            if since == check_every:
+                flag_host.copy_(self._st["flag"], non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()                       # the host sync: once per check_every steps
+                syncs += 1
+                if int(flag_host[0]):
+                    break
+                kv_hi, since = int(flag_host[1]), 0
+        st = self._st
+        lens_out = st["out_len"].tolist()
+        rows = st["out"].tolist()
+        hist = st["hist"][:steps].t().tolist()
+        n_live = max((max((i + 1 for i, a in enumerate(h) if a), default=0) for h in hist), default=0)
+        return ([rows[b][:lens_out[b]] for b in range(B)],
+                dict(steps=n_live, steps_run=steps, host_syncs=syncs, graphed=self.last_graphed, graphs=len(graphs),
+                     accept_lengths=[h[:n_live] for h in hist]))

@@ -238,6 +238,11 @@ def test_batched_decoder_is_lossless_on_a_tiny_llama():
     got, stats = dec.generate(prompts, n_new)
     assert got == want
     assert stats["steps"] < n_new                                  # drafts were accepted
+    # the decode step is captured as a CUDA graph per key-length bucket and the host reads one flag every 4 steps
+    assert stats["graphed"] and stats["graphs"] >= 1
+    assert stats["host_syncs"] <= stats["steps_run"] // 4 + 1 and stats["steps_run"] - stats["steps"] < 4
+    got_e, stats_e = dec.generate(prompts, n_new, graph=False)      # the same body, eagerly: same stream of tokens
+    assert got_e == want and stats_e["accept_lengths"] == stats["accept_lengths"] and not stats_e["graphed"]
     eos = want[1][10]                                              # pick a token request 1 really emits
     dec2 = BatchedSamdDecoder(lm, 4, 512, n_predicts=8, len_bias=5, len_threshold=3, eos_token_id=eos, dtype=torch.float32)
     got2, _ = dec2.generate(prompts, n_new)
