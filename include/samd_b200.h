@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SAMD_ABI_VERSION 2
+#define SAMD_ABI_VERSION 3
 
 /* draft flavours (which reference package's rules apply) */
 #define SAMD_FLAVOUR_SAMD      0   /* samd/draft.py:52-63, fixed n_predicts, zero padding      */
@@ -107,6 +107,8 @@ int samd_static_build(const int32_t *docs_flat_host, const int64_t *doc_offsets_
 int samd_static_build_host(const int32_t *docs_flat_host, const int64_t *doc_offsets_host, int64_t n_docs, int32_t eos,
                            int with_counts, samd_static_t *out);
 int samd_static_upload(samd_static_t h);
+/* Free the host mirrors of an uploaded automaton (they only serve export / save); queries keep working. */
+int samd_static_drop_host(samd_static_t h);
 int samd_static_destroy(samd_static_t h);
 /* info[8] = {n_states, n_edges, n_tokens, n_slots, device_bytes, with_counts, n_clones, 0} */
 int samd_static_info(samd_static_t h, int64_t *info_host);
@@ -297,6 +299,42 @@ typedef struct samd_verify_args {
 } samd_verify_args;
 
 int samd_verify_compact(samd_verify_t h, const samd_verify_args *args, void *stream);
+/* ----------------------------------------------------------------------------------------
+ * Stochastic (typical-acceptance) verification: the sampling branch of eval_posterior (samd/utils.py:142-184) and the
+ * draw of the token that follows (gen_candidates, samd/utils.py:85-88, torch.multinomial(sample_p, 1)), for a batch.
+ * Level by level, each distinct candidate token x among the paths that share the accepted prefix is tested once, in
+ * path order, with one uniform draw r:  accept iff r <= p(x) / (1 - mass rejected so far at this level), where
+ * p = softmax(logits_processor(row)) and logits_processor = temperature, then top-p, then top-k (samd/utils.py:44-58).
+ * The next token is drawn from the level's residual distribution when its last level rejected something (and the path
+ * is not complete), else from the plain softmax of the last accepted node's row (samd/utils.py:173-179).
+ * RNG CONTRACT: Philox4x32-10; uniform number k of request b is
+ *     u = (philox(counter = {lo32(c), hi32(c), 0, 0}, key = {lo32(seed_b), hi32(seed_b)})[0] >> 8) * 2^-24,  c = offset_b + k
+ * one draw per tested candidate, then one for the next token (inverse CDF in token-id order); offsets_dev[b] is advanced
+ * by the draws used, so consecutive calls continue one stream per request.  Python's random.random() of the reference
+ * cannot be reproduced bit for bit: decisions are exact against the oracle given the same stream
+ * (tests/test_gpu_sampling.py) and the acceptance-length / next-token statistics match the reference's own function.
+ * -------------------------------------------------------------------------------------- */
+typedef struct samd_sample_args {
+    const void    *logits_dev;        /* [B][T][V], dtype below */
+    int32_t        dtype;             /* SAMD_DTYPE_* */
+    int32_t        batch, n_nodes, vocab;
+    int64_t        batch_stride, row_stride;       /* in elements */
+    const int32_t *tree_tokens_dev;   /* [B][n_nodes] */
+    const int32_t *retrieve_dev;      /* [P][D] shared, or [B][P][D] when retrieve_batch_stride != 0; NULL = one identity path */
+    int32_t        n_paths, depth;
+    int64_t        retrieve_batch_stride;
+    const int32_t *n_paths_dev;       /* [B] live paths per request, or NULL */
+    float          temperature;       /* >= 1e-5 */
+    float          top_p;             /* active when 1e-8 <= top_p < 1 */
+    int32_t        top_k;             /* active when > 0 */
+    const uint64_t *seeds_dev;        /* [B] */
+    uint64_t      *offsets_dev;       /* [B] in/out */
+    int32_t *out_best_dev, *out_accept_len_dev, *out_next_token_dev;   /* [B]; accept_len = accepted + 1 */
+    int32_t *out_tokens_dev, *out_indices_dev;      /* [B][depth] (identity path: [B][n_nodes]); -1 past accept_len */
+    float   *out_sample_p_dev;        /* [B][V] the next token's distribution (the reference's returned sample_p), or NULL */
+} samd_sample_args;
+int samd_verify_sample(const samd_sample_args *args, void *stream);
+
 /* TokenRecycle.gen_draft (token_recycle.py:49-59) for a batch: tokens[b][0] = start_tok[b]; every other node takes
  * table[token of its parent][its rank among the parent's children], or 0 when the parent's token has no entry.
  * parent / rank: [n_nodes] device arrays describing the static tree (node 0 = root, parents before children);

@@ -526,3 +526,93 @@ def brute_peek(history: Sequence[int], tok: int) -> Tuple[int, int]:
             if h[end - L:end] == pat:
                 return L, end
     return 0, 0
+
+
+# --------------------------------------------------------------------------------------
+# Stochastic (typical-acceptance) verification, samd/utils.py:142-184 + the draw of the next token (:85-88)
+# --------------------------------------------------------------------------------------
+def philox_uniform(seed: int, counter: int) -> float:
+    """The product's RNG contract (include/samd_b200.h): Philox4x32-10, counter = {lo32(c), hi32(c), 0, 0},
+    key = {lo32(seed), hi32(seed)}; u = (word 0 >> 8) * 2^-24."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c = [counter & MASK, (counter >> 32) & MASK, 0, 0]
+    k0, k1 = seed & MASK, (seed >> 32) & MASK
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c[3] ^ k1) & MASK, p0 & MASK]
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return float(np.float32(c[0] >> 8) * np.float32(1.0 / 16777216.0))
+
+
+def processed_probs(row: np.ndarray, temperature: float, top_p: float, top_k: int) -> np.ndarray:
+    """softmax(logits_processor(row)) with the processor list of SamdGenerationConfig.prepare_logits_processor
+    (samd/utils.py:44-58): TemperatureLogitsWarper, then TopPLogitsWarper, then TopKLogitsWarper (transformers)."""
+    s = row.astype(np.float64)
+    if temperature >= 1e-5 and temperature != 1.0:
+        s = s / temperature
+    if 1e-8 <= top_p < 1.0:
+        order = np.argsort(s, kind="stable")                       # ascending
+        e = np.exp(s[order] - s.max())
+        cum = np.cumsum(e / e.sum())
+        remove = cum <= (1.0 - top_p)
+        remove[-1] = False                                          # min_tokens_to_keep = 1
+        s = s.copy()
+        s[order[remove]] = -np.inf
+    if top_k > 0:
+        k = min(top_k, s.size)
+        kth = np.sort(s)[-k]
+        s = np.where(s < kth, -np.inf, s)
+    e = np.exp(s - s.max())
+    return e / e.sum()
+
+
+def verify_typical(logits: np.ndarray, tree_tokens: np.ndarray, retrieve: np.ndarray, temperature: float, top_p: float,
+                   top_k: int, uniform):
+    """eval_posterior's sampling branch for ONE request.  logits [T, V], tree_tokens [T], retrieve [P, D] (-1 padded);
+    `uniform()` supplies the draws in order (the reference calls random.random(); the product its Philox stream).
+    Returns dict(best, accept_len, next_token, tokens, indices, sample_p, margins) - `margins` lists |r - p| of every
+    decision so that a comparison with float32 arithmetic can skip the razor-edge ones."""
+    T, V = logits.shape
+    ext = np.concatenate([np.asarray(tree_tokens, dtype=np.int64), [0]])
+    cand = ext[retrieve]                                            # -1 picks the appended 0
+    rows = np.where(retrieve < 0, T - 1, retrieve)                  # -1 wraps to the last row
+    P, D = cand.shape
+    accept, best, adjust = 1, 0, False
+    gtp, margins = None, []
+    for i in range(1, D):
+        if i != accept:
+            break
+        adjust = False
+        is_eq = (cand[:, :accept] == cand[best, :accept]).all(axis=1)
+        fi = int(np.nonzero(is_eq)[0][0])
+        gtp = processed_probs(logits[rows[fi, i - 1]], temperature, top_p, top_k)
+        seen = []
+        for j in range(P):
+            if not is_eq[j]:
+                continue
+            x = int(cand[j, i])
+            if x in seen or x == -1:
+                continue
+            seen.append(x)
+            r = uniform()
+            margins.append(abs(r - gtp[x]))
+            if r <= gtp[x]:
+                accept += 1
+                best = j
+                break
+            gtp = gtp.copy()
+            gtp[x] = 0.0
+            gtp = gtp / gtp.sum()
+            adjust = True
+    if adjust and accept != D:
+        sample_p = gtp
+    else:
+        row = logits[rows[best, accept - 1]].astype(np.float64)
+        e = np.exp(row - row.max())
+        sample_p = e / e.sum()
+    u = uniform()
+    cdf = np.cumsum(sample_p)
+    nxt = int(min(np.searchsorted(cdf, u * cdf[-1], side="right"), V - 1))
+    margins.append(float(np.min(np.abs(cdf / cdf[-1] - u))))
+    return dict(best=best, accept_len=accept, next_token=nxt, tokens=cand[best, :accept].tolist(),
+                indices=retrieve[best, :accept].tolist(), sample_p=sample_p, margins=margins)

@@ -22,6 +22,7 @@ struct HostSam {
     uint32_t bmask = 0;
     int64_t n_states = 1, n = 0, n_edges = 0, n_clones = 0, n_ovf = 0;
     int last = 0;
+    bool growable = false;
     std::vector<uint8_t> is_clone;
 
     int32_t *rec(int64_t v) const { return recs + (size_t)v * SAMD_REC; }
@@ -56,6 +57,41 @@ struct HostSam {
         if (!ovf_find((uint32_t)state, (uint32_t)tok, slot)) return nullptr;
         return reinterpret_cast<int32_t *>(&slots[slot].z);
     }
+    std::vector<int32_t> ovf_states;                      // states that own an overflow list (for grow())
+    // The overflow table doubles when half full (host builder only: the device arenas are sized up front).  Sizing it
+    // for the worst case - 4 slots per token - costs 8.6 GB of touched memory for a 125 M-token shard of which a few
+    // hundred MB are ever used: only hubs and the root overflow.  Per-state list order is preserved.
+    void grow() {
+        const uint64_t ncap = h_cap * 2;
+        uint4 *nsl = (uint4 *)malloc(ncap * sizeof(uint4));
+        if (!nsl) return;                                  // keep filling the old table; the hard check below still holds
+        memset(nsl, 0xFF, ncap * sizeof(uint4));
+        const uint32_t nmask = (uint32_t)(ncap / SAMD_BUCKET - 1);
+        std::vector<uint32_t> map((size_t)h_cap, SAMD_NIL);
+        for (uint64_t i = 0; i < h_cap; ++i) {
+            if (slots[i].x == SAMD_EMPTY) continue;
+            uint32_t bk = samd_hash(slots[i].x, slots[i].y) & nmask, pos = 0;
+            for (bool placed = false; !placed; bk = (bk + 1) & nmask)
+                for (int l = 0; l < SAMD_BUCKET && !placed; ++l)
+                    if (nsl[(size_t)bk * SAMD_BUCKET + l].x == SAMD_EMPTY) {
+                        pos = bk * SAMD_BUCKET + l;
+                        placed = true;
+                    }
+            nsl[pos] = slots[i];
+            map[(size_t)i] = pos;
+        }
+        for (uint64_t i = 0; i < h_cap; ++i)
+            if (map[(size_t)i] != SAMD_NIL && slots[i].w != SAMD_NIL) nsl[map[(size_t)i]].w = map[slots[i].w];
+        for (int32_t v : ovf_states) {
+            int32_t *r = rec(v);
+            r[R_OHEAD] = (int32_t)map[(uint32_t)r[R_OHEAD]];
+            r[R_OTAIL] = (int32_t)map[(uint32_t)r[R_OTAIL]];
+        }
+        free(slots);
+        slots = nsl;
+        h_cap = ncap;
+        bmask = nmask;
+    }
     void add_edge(int state, int tok, int target) {
         int32_t *r = rec(state);
         n_edges++;
@@ -65,6 +101,8 @@ struct HostSam {
                 r[R_TGT + i] = target;
                 return;
             }
+        if (growable && 2 * ((uint64_t)n_ovf + 1) > h_cap) grow();
+        if ((uint32_t)r[R_OHEAD] == SAMD_NIL) ovf_states.push_back(state);
         uint32_t slot;
         ovf_find((uint32_t)state, (uint32_t)tok, slot);
         slots[slot] = make_uint4((uint32_t)state, (uint32_t)tok, (uint32_t)target, SAMD_NIL);
@@ -263,8 +301,10 @@ extern "C" int samd_static_build_host(const int32_t *docs, const int64_t *offs, 
     // overflow edges are rare (only states with > 5 out-edges): start at n/2 slots... but never re-hash
     // mid-build, so size for the worst case the corpus allows: edges <= 3n, all of them could overflow
     // only in adversarial inputs; n slots (load <= ~0.5 in practice) with a hard check below.
-    int rc = alloc_host(b, 2 * (uint64_t)total + 2, (uint64_t)total, samd_table_slots((uint64_t)total));
+    // the overflow table starts small and doubles when half full (HostSam::grow): only hubs and the root overflow
+    int rc = alloc_host(b, 2 * (uint64_t)total + 2, (uint64_t)total, std::min<uint64_t>(samd_table_slots((uint64_t)total), 1u << 16));
     if (rc) return rc;
+    b.growable = true;
     b.is_clone.reserve(b.s_cap);
     b.is_clone.push_back(0);
     for (int64_t d = 0; d < n_docs; ++d) {
@@ -275,6 +315,23 @@ extern "C" int samd_static_build_host(const int32_t *docs, const int64_t *offs, 
         if (docs[offs[d + 1] - 1] != eos) b.append(eos);
     }
     *out = finish(b, nullptr, with_counts != 0);
+    return 0;
+}
+
+// Free the host mirrors of an uploaded automaton (they only serve export / save): a 125 M-token shard keeps 15 GB of them.
+extern "C" int samd_static_drop_host(samd_static_t h) {
+    SAMD_REQUIRE(h, "samd_static_drop_host: null handle");
+    SAMD_REQUIRE(h->dev.recs, "samd_static_drop_host: upload the automaton first");
+    free(h->h_recs);
+    free(h->h_slots);
+    free(h->h_text);
+    free(h->h_occ);
+    free(h->h_topk);
+    h->h_recs = nullptr;
+    h->h_slots = nullptr;
+    h->h_text = nullptr;
+    h->h_occ = nullptr;
+    h->h_topk = nullptr;
     return 0;
 }
 

@@ -86,7 +86,8 @@ class SamdModel(nn.Module):
         logits = outputs.logits
         self.draft.update(tokens=input_ids.squeeze(0), tree_tokens=input_ids.squeeze(0), tree_logits=logits.squeeze(0))
         self.cache.set_length()
-        return logits[:, -1]
+        # samd/samd_model.py:124-128: the logits row when greedy, its softmax when sampling
+        return logits[:, -1] if self.gen_config.greedy else torch.softmax(logits[:, -1].float(), dim=-1)
 
     def decode(self, sample_p: torch.Tensor, length: int):
         """samd/samd_model.py:131-182 with the verify / commit tail fused."""
@@ -112,6 +113,8 @@ class SamdModel(nn.Module):
             self._verifier = E.Verifier(1, 256, self.device)
             self._verifier.bind_kv(self.cache.kv_tensors())
         toks = tree_tokens.to(torch.int32).contiguous()
+        if not self.gen_config.greedy:
+            return self._update_state_sampling(toks, tree_logits, is_seq)
         # Token Recycle: the table update (TokenRecycle.update) rides on the verify launch's pass over the logits
         recycle = getattr(getattr(self.draft, "tree_model", None), "table", None)
         out = self._verifier.verify(tree_logits, toks, None if is_seq else self._retrieve_i32, cache_len=self.cache.cache_len,
@@ -127,6 +130,29 @@ class SamdModel(nn.Module):
         self._draft_update(out["tokens"][0, :k], tree_tokens.squeeze(0), None if recycle is not None else tree_logits.squeeze(0))
         self.cache.cache_length += k
         return sample_p, new_tokens
+
+    def _update_state_sampling(self, toks: torch.Tensor, tree_logits: torch.Tensor, is_seq: bool):
+        """The sampling branch (samd/utils.py:142-184): samd_verify_sample (typical acceptance + the residual / plain
+        distribution of the next token), then the row moves of select_indices as their own launch."""
+        from samd_b200 import _cabi as K
+        from .utils import _sampling_state
+        g = self.gen_config
+        st = _sampling_state(self.device, g.seed)
+        out = self._verifier.verify_sample(tree_logits, toks, None if is_seq else self._retrieve_i32, g.temperature, g.top_p,
+                                           g.top_k, st["seed"], st["offset"], want_sample_p=True)
+        v = self._verifier
+        m = v._kv_meta
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_kv_compact(v._kv_ptrs.data_ptr(), m["n_kv"], m["n_heads"], m["row_bytes"], m["batch_stride"],
+                                            m["head_stride"], m["pos_stride"], None if is_seq else out["indices"].data_ptr(),
+                                            out["indices"].shape[1], out["accept_len"].data_ptr(), self.cache.cache_len.data_ptr(),
+                                            1, K.stream_ptr()), "samd_kv_compact")
+        packed = torch.cat([out["accept_len"], out["tokens"][0]]).tolist()
+        k = packed[0]
+        new_tokens = packed[1:1 + k]
+        self._draft_update(out["tokens"][0, :k], toks.squeeze(0), tree_logits.squeeze(0))
+        self.cache.cache_length += k
+        return out["sample_p"], new_tokens
 
     def _draft_update(self, tokens, tree_tokens, tree_logits):
         self.draft.update(tokens=tokens, tree_tokens=tree_tokens, tree_logits=tree_logits)

@@ -1,8 +1,9 @@
 """gen_candidates / eval_posterior / SamdGenerationConfig (reference: samd/utils.py:19-184).
 
-Greedy decoding only: the start token, the draft lookup and the posterior evaluation run on the
-device (one `samd_step` launch and one `samd_verify_compact` launch); the stochastic
-typical-acceptance branch (samd/utils.py:142-184) is outside the scope of this framework.
+The start token, the draft lookup and the posterior evaluation run on the device: greedy = one `samd_step`
+launch and one `samd_verify_compact` launch; greedy=False = the typical-acceptance branch (samd/utils.py:142-184)
+as one `samd_verify_sample` launch with a Philox stream per request (include/samd_b200.h states the contract:
+Python's random.random() of the reference cannot be reproduced, the statistics are).
 """
 from dataclasses import dataclass, field
 from typing import Callable, Optional
@@ -35,18 +36,19 @@ class SamdGenerationConfig:
     top_p: float = field(default=0.0)
     top_k: int = field(default=0)
     logits_processor: object = field(default=None)
+    seed: int = field(default=0)              # (not in the reference) seed of the device Philox stream when greedy=False
 
     def __post_init__(self):
         if not self.greedy:
-            raise NotImplementedError("only greedy decoding is supported (the sampling branch of the reference, "
-                                      "samd/utils.py:142-184, is out of scope)")
+            assert self.temperature >= 1e-5   # samd/utils.py:41
 
 
 @profile_decorator("gen_candidates")
 def gen_candidates(sample_p: torch.Tensor, tree_retrieve_indices: torch.Tensor, draft: DraftModel,
                    samd_config: SamdConfig, gen_config: SamdGenerationConfig, device: torch.device):
     """samd/utils.py:67-104.  `sample_p` [1, V] -> Candidates(type, tokens [1, n], candidate_tokens, buffers)."""
-    start = torch.argmax(sample_p, dim=-1)                       # stays on the device
+    # samd/utils.py:85-88: greedy -> argmax of the logits row; sampling -> one draw from the distribution
+    start = torch.argmax(sample_p, dim=-1) if gen_config.greedy else torch.multinomial(sample_p, 1).view(-1)
     eng = draft.lookup_device(start)
     kind = int(eng.out_type.item())
     if kind != K.DRAFT_TREE_MODEL:
@@ -61,6 +63,17 @@ def gen_candidates(sample_p: torch.Tensor, tree_retrieve_indices: torch.Tensor, 
 
 
 _verifiers = {}
+_sampling = {}
+
+
+def _sampling_state(device, seed: int):
+    """The process-wide Philox stream of eval_posterior's sampling branch: (seed, offset) as device tensors."""
+    key = (str(device), int(seed))
+    st = _sampling.get(key)
+    if st is None:
+        st = _sampling[key] = dict(seed=torch.tensor([int(seed)], dtype=torch.int64, device=device),
+                                   offset=torch.zeros(1, dtype=torch.int64, device=device))
+    return st
 
 
 def _verifier(device, batch, nodes) -> E.Verifier:
@@ -78,9 +91,15 @@ def eval_posterior(logits: torch.Tensor, candidates: torch.Tensor, config: SamdG
     """samd/utils.py:108-141 (greedy).  `logits` [P, D, V] are the already gathered candidate logits,
     `candidates` [P, D].  Returns (best_candidate, accept_length (accepted + 1), logits[best, accepted]
     as [1, V]).  Runs as one fused launch: the P*D rows are verified with an identity path table."""
-    if not config.greedy:
-        raise NotImplementedError("only greedy decoding is supported")
     P, D, V = logits.shape
+    if not config.greedy:
+        # samd/utils.py:142-184: one launch, the P*D gathered rows as nodes with an identity path table
+        st = _sampling_state(logits.device, config.seed)
+        out = _verifier(logits.device, 1, P * D).verify_sample(
+            logits.reshape(1, P * D, V), candidates.reshape(1, P * D).to(torch.int32).contiguous(),
+            torch.arange(P * D, dtype=torch.int32, device=logits.device).view(P, D), config.temperature, config.top_p,
+            config.top_k, st["seed"], st["offset"], want_sample_p=True)
+        return out["best"][0].to(torch.long), out["accept_len"][0].to(torch.long), out["sample_p"]
     lg = logits.reshape(1, P * D, V)
     toks = candidates.reshape(1, P * D).to(torch.int32).contiguous()
     ident = torch.arange(P * D, dtype=torch.int32, device=logits.device).view(P, D)

@@ -51,6 +51,17 @@ class VerifyArgs(C.Structure):
     ]
 
 
+class SampleArgs(C.Structure):
+    _fields_ = [
+        ("logits_dev", vp), ("dtype", C.c_int32), ("batch", C.c_int32), ("n_nodes", C.c_int32), ("vocab", C.c_int32),
+        ("batch_stride", C.c_int64), ("row_stride", C.c_int64), ("tree_tokens_dev", vp), ("retrieve_dev", vp),
+        ("n_paths", C.c_int32), ("depth", C.c_int32), ("retrieve_batch_stride", C.c_int64), ("n_paths_dev", vp),
+        ("temperature", C.c_float), ("top_p", C.c_float), ("top_k", C.c_int32), ("seeds_dev", vp), ("offsets_dev", vp),
+        ("out_best_dev", vp), ("out_accept_len_dev", vp), ("out_next_token_dev", vp), ("out_tokens_dev", vp),
+        ("out_indices_dev", vp), ("out_sample_p_dev", vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/samd_b200.h declares
 SYMBOLS = {
     "samd_abi_version": (C.c_int, []),
@@ -75,6 +86,7 @@ SYMBOLS = {
     "samd_static_build": (C.c_int, [c_i32p, c_i64p, C.c_int64, C.c_int32, C.c_int, C.POINTER(vp)]),
     "samd_static_build_host": (C.c_int, [c_i32p, c_i64p, C.c_int64, C.c_int32, C.c_int, C.POINTER(vp)]),
     "samd_static_upload": (C.c_int, [vp]),
+    "samd_static_drop_host": (C.c_int, [vp]),
     "samd_static_destroy": (C.c_int, [vp]),
     "samd_static_info": (C.c_int, [vp, c_i64p]),
     "samd_static_export": (C.c_int, [vp, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]),
@@ -110,6 +122,7 @@ SYMBOLS = {
     "samd_verify_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
     "samd_verify_destroy": (C.c_int, [vp]),
     "samd_verify_compact": (C.c_int, [vp, C.POINTER(VerifyArgs), vp]),
+    "samd_verify_sample": (C.c_int, [C.POINTER(SampleArgs), vp]),
     "samd_recycle_gen_tree": (C.c_int, [vp, C.c_int32, vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "samd_verify_set_chunk": (None, [C.c_int]),
     "samd_verify_set_overlap": (None, [C.c_int]),
@@ -136,7 +149,7 @@ def lib():
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
-        if _lib.samd_abi_version() != 2:
+        if _lib.samd_abi_version() != 3:
             raise SamdError("libsamd_b200.so ABI version mismatch")
     return _lib
 

@@ -180,6 +180,11 @@ class StaticSamDevice:
             K.check(K.lib().samd_static_upload(self._h), "samd_static_upload")
         return self
 
+    def drop_host(self):
+        """Free the host mirrors (export / save stop working, queries do not): 15 GB for a 125 M-token shard."""
+        K.check(K.lib().samd_static_drop_host(self._h), "samd_static_drop_host")
+        return self
+
     @staticmethod
     def load(path: str, device: Optional[torch.device] = None, host_only: bool = False) -> "StaticSamDevice":
         h = K.vp()
@@ -465,6 +470,49 @@ class Verifier:
         # remember the argument block for the fast path (keyed on the caller-provided `out`, if any)
         self._last_key = key[:10] + (out["tokens"].data_ptr(),) + key[11:]
         self._last_out = out
+        return out
+
+    def verify_sample(self, logits: torch.Tensor, tree_tokens: torch.Tensor, retrieve: Optional[torch.Tensor],
+                      temperature: float, top_p: float, top_k: int, seeds: torch.Tensor, offsets: torch.Tensor,
+                      n_paths: Optional[torch.Tensor] = None, want_sample_p: bool = False) -> dict:
+        """Typical-acceptance verification + the draw of the next token (samd/utils.py:142-184, :85-88) for a batch:
+        one launch, one CTA per request.  `seeds` / `offsets`: int64 CUDA tensors [B] - the Philox stream of every request
+        (include/samd_b200.h states the contract); `offsets` is advanced in place by the draws used."""
+        assert logits.is_cuda and logits.dim() == 3 and logits.stride(2) == 1
+        B, T, V = logits.shape
+        dt = {torch.bfloat16: K.DTYPE_BF16, torch.float16: K.DTYPE_FP16, torch.float32: K.DTYPE_FP32}.get(logits.dtype)
+        if dt is None:
+            raise K.SamdError(f"unsupported logits dtype {logits.dtype} (bf16 / fp16 / fp32)")
+        _i32(tree_tokens)
+        assert tree_tokens.shape == (B, T) and seeds.dtype == torch.int64 and offsets.dtype == torch.int64
+        assert seeds.is_cuda and offsets.is_cuda and seeds.numel() == B and offsets.numel() == B
+        a = K.SampleArgs()
+        a.logits_dev, a.dtype, a.batch, a.n_nodes, a.vocab = logits.data_ptr(), dt, B, T, V
+        a.batch_stride, a.row_stride = logits.stride(0), logits.stride(1)
+        a.tree_tokens_dev = tree_tokens.data_ptr()
+        if retrieve is not None:
+            _i32(retrieve)
+            if retrieve.dim() == 2:
+                a.n_paths, a.depth, a.retrieve_batch_stride = retrieve.shape[0], retrieve.shape[1], 0
+            else:
+                a.n_paths, a.depth, a.retrieve_batch_stride = retrieve.shape[1], retrieve.shape[2], retrieve.stride(0)
+            a.retrieve_dev, width = retrieve.data_ptr(), a.depth
+        else:
+            a.retrieve_dev, a.n_paths, a.depth, a.retrieve_batch_stride, width = None, 1, T, 0, T
+        a.n_paths_dev = K.ptr(_i32(n_paths)) if n_paths is not None else None
+        a.temperature, a.top_p, a.top_k = float(temperature), float(top_p), int(top_k)
+        a.seeds_dev, a.offsets_dev = seeds.data_ptr(), offsets.data_ptr()
+        mk = lambda *s: torch.empty(*s, dtype=torch.int32, device=logits.device)
+        out = dict(best=mk(B), accept_len=mk(B), next_token=mk(B), tokens=mk(B, width), indices=mk(B, width))
+        a.out_best_dev, a.out_accept_len_dev, a.out_next_token_dev = out["best"].data_ptr(), out["accept_len"].data_ptr(), out["next_token"].data_ptr()
+        a.out_tokens_dev, a.out_indices_dev = out["tokens"].data_ptr(), out["indices"].data_ptr()
+        if want_sample_p:
+            out["sample_p"] = torch.empty(B, V, dtype=torch.float32, device=logits.device)
+            a.out_sample_p_dev = out["sample_p"].data_ptr()
+        else:
+            a.out_sample_p_dev = None
+        with torch.cuda.device(self.device):
+            K.check(K.lib().samd_verify_sample(C.byref(a), K.stream_ptr()), "samd_verify_sample")
         return out
 
     def close(self):

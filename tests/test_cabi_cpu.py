@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} is declared in include/samd_b200.h but not exported"
     assert set(K.SYMBOLS) <= set(declared) | {"samd_verify_set_chunk"}
     assert set(declared) <= set(K.SYMBOLS), sorted(set(declared) - set(K.SYMBOLS))
-    assert lib.samd_abi_version() == 2
+    assert lib.samd_abi_version() == 3
 
 
 def test_no_cpu_fallback():

@@ -224,6 +224,37 @@ def test_generate_is_lossless_on_a_tiny_llama(pkg):
     assert out.decode_tokens == sum(out.accepet_length_per_step)
 
 
+def test_generate_with_sampling_on_a_tiny_llama():
+    """SamdGenerationConfig(greedy=False) - the reference's typical-acceptance branch (samd/utils.py:142-184) through
+    samd_verify_sample, end to end: the loop runs to the requested length with consistent bookkeeping and is a pure
+    function of (torch seed, Philox seed / offset).  (Like the reference, only the ACCEPTANCE test uses the temperature /
+    top-p / top-k processor; the first token and the non-residual next tokens are drawn from the plain softmax -
+    samd/samd_model.py:127, samd/utils.py:176-179 - so a low temperature does not reproduce greedy decoding.)"""
+    import samd as mod
+    from samd import utils as U
+    from samd_b200 import synth
+    lm = _tiny_llama(torch.float32)
+    prompt = torch.as_tensor(synth.copy_mix(160, 96, 77, p_copy=0.7)[None]).cuda()
+    n_new = 64
+    cfg = mod.SamdConfig(n_predicts=8, len_threshold=3, len_bias=1)
+    runs = []
+    for _ in range(2):
+        # (a fresh draft model per run: like the reference's, the Token-Recycle table survives DraftModel.reset())
+        draft = mod.DraftModel(cfg, lm=lm, dtype=torch.float32, device="cuda")
+        model = mod.SamdModel(cfg, lm, draft, eos_token_id=-1, dtype=torch.float32, device="cuda")
+        torch.manual_seed(0)
+        U._sampling.clear()                                              # a fresh Philox stream (offset 0)
+        out = model.generate(prompt, generation_config=mod.SamdGenerationConfig(max_new_tokens=n_new, max_cache_len=512,
+                                                                                greedy=False, temperature=0.8, top_p=0.95,
+                                                                                top_k=20, seed=4))
+        ids = out.output_ids[0]
+        assert len(ids) == prompt.shape[1] + n_new and ids[:prompt.shape[1]] == prompt[0].tolist()
+        assert out.decode_tokens == sum(out.accepet_length_per_step) and all(a >= 1 for a in out.accepet_length_per_step)
+        assert all(0 <= t < 96 for t in ids)
+        runs.append(ids)
+    assert runs[0] == runs[1]
+
+
 def test_batched_decoder_is_lossless_on_a_tiny_llama():
     """B = 4 requests with ragged prompts decoded in lockstep (one samd_step launch,
     one LM forward, one samd_verify_compact launch per step, per-request KV offsets) must reproduce plain

@@ -269,3 +269,25 @@ def test_row_topk_refinement_on_ties():
     idx = O.row_topk(y, 8)
     vals = np.take_along_axis(y.numpy(), idx, axis=1)
     assert np.array_equal(vals, y.topk(8).values.numpy())
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3])
+def test_typical_acceptance_oracle_matches_reference(ci):
+    """samd/utils.py:142-184: the reference's eval_posterior (greedy=False) was run with random.random() replaced by a
+    recorded stream (oracle/gen_sampling_golden.py); the oracle's restatement, fed the same stream, must take the same
+    decisions and return the same next-token distribution - and consume the same number of draws."""
+    z = load("sampling.npz")
+    temp, top_p, top_k = z["configs"][ci]
+    det, sps = z[f"c{ci}/det"], z[f"c{ci}/det_sample_p"]
+    for (k0, n_draws, best, acc), sp in zip(det.tolist(), sps):
+        k = [0]
+
+        def draw():
+            u = O.philox_uniform(5000 + ci, k0 + k[0])
+            k[0] += 1
+            return u
+
+        got = O.verify_typical(z["logits"], z["tree_tokens"], z["retrieve"].astype(np.int64), float(temp), float(top_p), int(top_k), draw)
+        assert (got["best"], got["accept_len"]) == (best, acc)
+        assert k[0] - 1 == n_draws                       # (+1: the oracle also draws the next token)
+        assert np.allclose(got["sample_p"], sp, rtol=1e-4, atol=1e-7)
