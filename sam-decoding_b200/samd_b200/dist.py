@@ -99,6 +99,22 @@ class ShardedStaticSam:
         self.n_queries = n_queries
         self._xchg = None
 
+    @classmethod
+    def from_parts(cls, sam, offset: int, corpus: torch.Tensor, rank: int, world: int, n_queries: int) -> "ShardedStaticSam":
+        """A shard whose automaton was built by this rank from ITS documents only (no rank ever holds the whole corpus
+        on the host): `sam` = the uploaded StaticSamDevice of the shard, `offset` = corpus tokens in front of it,
+        `corpus` = the replicated 1-based token array on this rank's device (corpus[0] = -1)."""
+        self = cls.__new__(cls)
+        self.rank, self.world, self.plan = rank, world, None
+        self.offset, self.sam, self.device = int(offset), sam, sam.device
+        self.n_corpus = int(corpus.numel() - 1)
+        self.corpus = corpus
+        self.cursor = sam.new_cursors(n_queries)
+        self.keys = torch.zeros(n_queries, dtype=torch.int64, device=self.device)
+        self.n_queries = n_queries
+        self._xchg = None
+        return self
+
     def connect_peers(self, group=None) -> bool:
         """Set up the NVLink peer exchange (one process per GPU of one node): every rank allocates its exchange
         buffer, the CUDA IPC handles are all-gathered through torch.distributed, and every rank maps its peers'
