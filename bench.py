@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--l2-mb", type=int, default=0, help="with --only-static: also time with this many MB of state records pinned in L2")
     ap.add_argument("--only-verify", action="store_true", help="profiling aid: run only the c4 verify loop")
     ap.add_argument("--only-step", action="store_true", help="profiling aid: run only the c2 device loop")
+    ap.add_argument("--only-tree", action="store_true", help="run only the sam_only static tree drafter measurement")
     ap.add_argument("--scouts", type=int, default=2, help="profiling aid: scout warps of the step kernel (0 none, 1 cursor scouts, 2 all)")
     ap.add_argument("--overlap", type=int, default=None, help="tuning aid: 1 overlapped / 0 two-barrier flow of the verify kernel")
     ap.add_argument("--lean", type=int, default=None, help="tuning aid: 1 lean / 0 wide build of the step kernel (default: by batch size)")
@@ -342,6 +343,9 @@ def run_ours(a):
     if a.only_static:
         print(json.dumps({"static": bench_static(a, dev, n_corpus=a.static_tokens, check=a.check_static, l2_mb=a.l2_mb)}))
         return
+    if a.only_tree:
+        print(json.dumps({"sam_only_tree": bench_tree_drafter(a, dev)}))
+        return
     if a.only_step:
         a.no_extras = a.no_cpu = True
     R, N, S, W = a.requests, a.prompt, a.steps, a.warmup
@@ -522,6 +526,10 @@ def run_ours(a):
             out["c1"] = bench_c1(a, dev)
         except Exception as e:
             out["c1"] = {"error": repr(e)}
+        try:
+            out["sam_only_tree"] = bench_tree_drafter(a, dev)
+        except Exception as e:
+            out["sam_only_tree"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not a.no_cpu:
         # the CPU baseline beside it (rank 0, N = 1 only): the reference's own classes when baseline/_ref is staged, on a
         # bounded sample of the same workload; the Python port and the C restatement of the oracle follow for context
@@ -582,6 +590,9 @@ def run_ours(a):
     v = out.get("c1")
     if isinstance(v, dict) and "gpu_us_per_step" in v:
         others["c1"] = {k: v[k] for k in v if k != "workload"}
+    v = out.get("sam_only_tree")
+    if isinstance(v, dict) and "trees_per_s" in v:
+        others["sam_only_static_tree"] = {k: v[k] for k in v if k != "workload"}
     v = out.get("sharded_static")
     if isinstance(v, dict) and "queries_per_s" in v:
         others["c5_sharded_static"] = {"queries_per_s": v["queries_per_s"], "p2p": v.get("p2p"), "nccl": v.get("nccl"),
@@ -841,11 +852,26 @@ def bench_c1(a, dev, prompt=4096, steps=256):
     t0 = time.perf_counter()
     co.extend(stream[:prompt])
     c_build = time.perf_counter() - t0
+    # the same loop through the DROP-IN classes (samd_sam_only.DraftModel.update / lookup: one launch each, the lookup's
+    # result read back with one device-to-host copy - what a caller of the reference's API sees, syncs included)
+    import samd_sam_only as SO
+    dm = SO.DraftModel(SO.SamdConfig(max_predicts=40, alpha=4.0, K=8, len_bias=5), device=str(dev))
+    dm.reset()
+    dm.update(torch.as_tensor(stream[:prompt]).to(dev))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        dm.update(toks[i][0])
+        dm.lookup(int(stream[ends[i]]))
+    dropin_us = (time.perf_counter() - t0) / steps * 1e6
     return {"workload": f"c1: one request, {prompt}-token prompt, {steps} steps of 1-8 appended tokens + lookup + draft "
                         f"(samd_sam_only flavour, max_predicts 40, alpha 4)",
             "gpu_build_tokens_per_s": prompt / (build_ms * 1e-3), "gpu_us_per_step": gpu_us,
             "cpu_python_port_build_tokens_per_s": prompt / py_build, "cpu_python_port_us_per_step": py_us,
-            "cpu_c_port_build_tokens_per_s": prompt / c_build, "cores": 1}
+            "cpu_c_port_build_tokens_per_s": prompt / c_build, "cores": 1,
+            "dropin_api_us_per_step": dropin_us, "dropin_api_steps_per_s": 1e6 / dropin_us,
+            "dropin_note": "samd_sam_only.DraftModel.update + lookup per step through the reference's class API "
+                           "(two launches and one device-to-host read per step)"}
 
 
 def bench_static(a, dev, n_corpus=2_000_000, n_q=4096, steps=64, warm=8, check=False, l2_mb=None):
@@ -938,6 +964,51 @@ def bench_static(a, dev, n_corpus=2_000_000, n_q=4096, steps=64, warm=8, check=F
         out["l2_window"] = {"mb_requested": int(l2_mb), "us_per_step": ms_w / steps * 1e3, "queries_per_s": n_q * steps / (ms_w * 1e-3),
                             "us_per_step_without": ms / steps * 1e3, "results_identical": checksum_w == checksum}
     return out
+
+
+def bench_tree_drafter(a, dev, n_corpus=5_000_000, n_q=4096, steps=32, warm=4):
+    """samd_sam_only's static tree drafter (samd_sam_only/sam/static_sam.py:182-215: best-first search over occurrence
+    counts with CPython-heapq order, then the mask / position / retrieve buffers): 4096 cursors over a count-annotated
+    static automaton, every query drafts a tree of up to 40 nodes per step.  Trees per second."""
+    import torch
+    from samd_b200 import _cabi as K, engine as E, synth
+    docs = synth.make_corpus(n_corpus, VOCAB, 3100, singletons=True)
+    st = E.StaticSamDevice.build(docs, synth.EOS, with_counts=True, device=dev)
+    q = synth.corpus_queries(docs, n_q, 8 * (steps + warm) + 1, VOCAB, 3101).astype(np.int32)
+    rng = np.random.default_rng(3102)
+    counts = rng.integers(1, 9, size=(steps + warm, n_q)).astype(np.int32)
+    ends = np.cumsum(counts, axis=0)
+    begins = ends - counts
+    cols = np.arange(8)[None, None, :]
+    rows = np.arange(n_q)[None, :, None]
+    tokens = np.where(cols < counts[:, :, None], q[rows, np.minimum(begins[:, :, None] + cols, q.shape[1] - 1)], 0).astype(np.int32)
+    start = q[np.arange(n_q)[None, :], ends].astype(np.int32)
+    dyn = E.DynSamBatch(n_q, 8 * (steps + warm) * 2 + 64, dev)
+    eng = E.DraftEngine(dyn, st, K.FLAVOUR_SAM_ONLY, n_predicts=40, len_bias=-(1 << 20), alpha=4.0)   # the static tree always wins
+    d_tok, d_cnt, d_st = (torch.as_tensor(x).to(dev) for x in (tokens, counts, start))
+
+    def step(s):
+        eng.step(d_tok[s], d_cnt[s], d_st[s])
+        eng.tree_draft(d_st[s], K_top=8)
+
+    for s in range(warm):
+        step(s)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i, s in enumerate(range(warm, warm + steps)):
+        ev[i][0].record()
+        eng.step(d_tok[s], d_cnt[s], d_st[s])
+        ev[i][1].record()
+        eng.tree_draft(d_st[s], K_top=8)
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    us_step = float(np.median([x.elapsed_time(y) for x, y, _ in ev])) * 1e3
+    us_tree = float(np.median([y.elapsed_time(z) for _, y, z in ev])) * 1e3
+    n_tree = int((eng.out_type == K.DRAFT_STATIC_TREE).sum().item())
+    return {"workload": f"samd_sam_only static tree drafter: {st.n_tokens}-token corpus with counts ({st.n_states} states), {n_q} queries/step, "
+                        f"max_predicts 40, alpha 4, K 8",
+            "us_per_step_tree_kernel": us_tree, "trees_per_s": n_tree / (us_tree * 1e-6), "trees_per_step": n_tree,
+            "mean_tree_nodes": float(eng.tree_n.float().mean()), "us_per_step_lookup_kernel": us_step}
 
 
 def bench_sharded_static(a, dev, rank, world, tokens_per_shard=2_000_000, n_q=4096, steps=64, warm=8):

@@ -86,12 +86,14 @@ class SamdModel(nn.Module):
         logits = outputs.logits
         self.draft.update(tokens=input_ids.squeeze(0), tree_tokens=input_ids.squeeze(0), tree_logits=logits.squeeze(0))
         self.cache.set_length()
+        self._next_token = None
         # samd/samd_model.py:124-128: the logits row when greedy, its softmax when sampling
         return logits[:, -1] if self.gen_config.greedy else torch.softmax(logits[:, -1].float(), dim=-1)
 
     def decode(self, sample_p: torch.Tensor, length: int):
         """samd/samd_model.py:131-182 with the verify / commit tail fused."""
-        cands = gen_candidates(sample_p, self.base_tree_retrieve_indices, self.draft, self.samd_config, self.gen_config, self.device)
+        cands = gen_candidates(sample_p, self.base_tree_retrieve_indices, self.draft, self.samd_config, self.gen_config, self.device,
+                               start_token=self._next_token)
         self.update_buffers(cands.buffers_kwargs)
         is_seq = cands.type == CandidateType.sequence
         input_ids = cands.tokens
@@ -129,6 +131,7 @@ class SamdModel(nn.Module):
         new_tokens = packed[1:1 + k]
         self._draft_update(out["tokens"][0, :k], tree_tokens.squeeze(0), None if recycle is not None else tree_logits.squeeze(0))
         self.cache.cache_length += k
+        self._next_token = out["next_token"]            # = argmax(sample_p): the next step's start token, already on the device
         return sample_p, new_tokens
 
     def _update_state_sampling(self, toks: torch.Tensor, tree_logits: torch.Tensor, is_seq: bool):

@@ -45,10 +45,17 @@ class SamdGenerationConfig:
 
 @profile_decorator("gen_candidates")
 def gen_candidates(sample_p: torch.Tensor, tree_retrieve_indices: torch.Tensor, draft: DraftModel,
-                   samd_config: SamdConfig, gen_config: SamdGenerationConfig, device: torch.device):
-    """samd/utils.py:67-104.  `sample_p` [1, V] -> Candidates(type, tokens [1, n], candidate_tokens, buffers)."""
+                   samd_config: SamdConfig, gen_config: SamdGenerationConfig, device: torch.device,
+                   start_token: Optional[torch.Tensor] = None):
+    """samd/utils.py:67-104.  `sample_p` [1, V] -> Candidates(type, tokens [1, n], candidate_tokens, buffers).
+    `start_token` (not in the reference): the start token as a 1-element device tensor when the caller already has it -
+    the fused verify launch returns the argmax of the row it hands back as sample_p, so the greedy loop skips this pass
+    over the vocabulary."""
     # samd/utils.py:85-88: greedy -> argmax of the logits row; sampling -> one draw from the distribution
-    start = torch.argmax(sample_p, dim=-1) if gen_config.greedy else torch.multinomial(sample_p, 1).view(-1)
+    if start_token is not None and gen_config.greedy:
+        start = start_token.view(-1)
+    else:
+        start = torch.argmax(sample_p, dim=-1) if gen_config.greedy else torch.multinomial(sample_p, 1).view(-1)
     eng = draft.lookup_device(start)
     kind = int(eng.out_type.item())
     if kind != K.DRAFT_TREE_MODEL:
