@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--l2-mb", type=int, default=0, help="with --only-static: also time with this many MB of state records pinned in L2")
     ap.add_argument("--only-verify", action="store_true", help="profiling aid: run only the c4 verify loop")
     ap.add_argument("--only-step", action="store_true", help="profiling aid: run only the c2 device loop")
+    ap.add_argument("--only-c1", action="store_true", help="run only the c1 (one request) measurement")
     ap.add_argument("--only-tree", action="store_true", help="run only the sam_only static tree drafter measurement")
     ap.add_argument("--scouts", type=int, default=2, help="profiling aid: scout warps of the step kernel (0 none, 1 cursor scouts, 2 all)")
     ap.add_argument("--overlap", type=int, default=None, help="tuning aid: 1 overlapped / 0 two-barrier flow of the verify kernel")
@@ -345,6 +346,9 @@ def run_ours(a):
         return
     if a.only_tree:
         print(json.dumps({"sam_only_tree": bench_tree_drafter(a, dev)}))
+        return
+    if a.only_c1:
+        print(json.dumps({"c1": bench_c1(a, dev)}))
         return
     if a.only_step:
         a.no_extras = a.no_cpu = True
@@ -859,11 +863,15 @@ def bench_c1(a, dev, prompt=4096, steps=256):
     dm.reset()
     dm.update(torch.as_tensor(stream[:prompt]).to(dev))
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(steps):
+    n_warm = 16                               # first calls allocate the pinned I/O buffers and build the argument blocks
+    for i in range(n_warm):
         dm.update(toks[i][0])
         dm.lookup(int(stream[ends[i]]))
-    dropin_us = (time.perf_counter() - t0) / steps * 1e6
+    t0 = time.perf_counter()
+    for i in range(n_warm, steps):
+        dm.update(toks[i][0])
+        dm.lookup(int(stream[ends[i]]))
+    dropin_us = (time.perf_counter() - t0) / (steps - n_warm) * 1e6
     return {"workload": f"c1: one request, {prompt}-token prompt, {steps} steps of 1-8 appended tokens + lookup + draft "
                         f"(samd_sam_only flavour, max_predicts 40, alpha 4)",
             "gpu_build_tokens_per_s": prompt / (build_ms * 1e-3), "gpu_us_per_step": gpu_us,

@@ -72,11 +72,9 @@ class DraftModel(torch.nn.Module):
 
     def lookup(self, start_token: int):
         e = self._bind()
-        e.start.fill_(int(start_token))
-        e.step(None, None, e.start)
-        packed = torch.cat([e.out_type, e.draft.reshape(-1)]).tolist()         # one device->host copy
-        if packed[0] != K.DRAFT_TREE_MODEL:
-            return (CandidateType.sequence, packed[1:], {})
+        out_np = e.host_lookup(start_token)       # one launch, mapped pinned host I/O, one stream synchronise
+        if int(out_np[0]) != K.DRAFT_TREE_MODEL:
+            return (CandidateType.sequence, out_np[6:6 + e.n_predicts].tolist(), {})
         return (CandidateType.tree,) + tuple(self.tree_model.gen_draft(int(start_token)))
 
     def update(self, tokens: Optional[torch.Tensor] = None, last_hidden_states: Optional[torch.Tensor] = None,
@@ -86,8 +84,10 @@ class DraftModel(torch.nn.Module):
         if k:
             self.sam_dyn._ensure(k)
             e = self._bind()
-            row = tokens.reshape(1, -1).to(device=e.dyn.device, dtype=torch.int32).contiguous()
-            e.step(row, None, None)                                             # dyn.add_tokens + static.transfer_tokens
+            row = tokens.reshape(1, -1)
+            if row.dtype != torch.int32 or row.device != e.dyn.device or not row.is_contiguous():
+                row = row.to(device=e.dyn.device, dtype=torch.int32).contiguous()
+            e.quick_update(row)                                                 # dyn.add_tokens + static.transfer_tokens
             self.sam_dyn._n_tokens += k
         self.tree_model.update(tokens=tokens, last_hidden_states=last_hidden_states, tree_tokens=tree_tokens,
                                tree_logits=tree_logits)

@@ -295,6 +295,61 @@ class DraftEngine:
         with torch.cuda.device(self.dyn.device):
             K.check(K.lib().samd_step(C.byref(a), K.stream_ptr()), "samd_step")
 
+    # ---- batch-1 host-facing calls (the drop-in DraftModel.update / lookup): argument blocks built once --------------
+    def _fill_common(self, a):
+        a.dyn = self.dyn.handle
+        a.stat = self.static.handle if self.static is not None else None
+        a.static_cursor_dev = K.ptr(self.static_cursor)
+        a.flavour, a.n_predicts, a.len_bias, a.len_threshold, a.alpha = \
+            self.flavour, self.n_predicts, self.len_bias, self.len_threshold, self.alpha
+
+    def _make_current(self):
+        """The arenas' device must be the current one for the launch; switching costs ~100 us, checking costs nothing."""
+        idx = self.dyn.device.index
+        if idx is not None and torch.cuda.current_device() != idx:
+            torch.cuda.set_device(idx)
+
+    def quick_update(self, tokens: torch.Tensor):
+        """update(tokens [1, k] int32 on the device) with a pre-built argument block: a Python call costs the ctypes
+        launch and nothing else (no tensor checks, no device context switch when the device is already current)."""
+        a = self.__dict__.get("_qu_args")
+        if a is None:
+            a = self._qu_args = K.StepArgs()
+            a.counts_dev = a.start_tok_dev = None
+            a.out_type_dev = a.out_match_dyn_dev = a.out_match_static_dev = a.out_index_dyn_dev = None
+            a.out_index_static_dev = a.out_draft_dev = a.out_draft_len_dev = None
+            a.draft_stride = 0
+        self._fill_common(a)
+        a.tokens_dev, a.token_stride = tokens.data_ptr(), tokens.shape[-1]
+        self._make_current()
+        K.check(K.lib().samd_step(C.byref(a), torch.cuda.current_stream().cuda_stream), "samd_step")
+
+    def host_lookup(self, start_token: int) -> np.ndarray:
+        """lookup(start_token) for ONE request with the start token read from, and every output written to, mapped
+        pinned host memory by the one launch; returns the output block as a numpy view (layout of `out_buf`) after one
+        stream synchronise.  No fill / cat / copy kernels, no per-call tensor checks."""
+        h = self.__dict__.get("_hl")
+        if h is None:
+            assert self.dyn.n_requests == 1
+            start = torch.zeros(1, dtype=torch.int32).pin_memory()
+            out = torch.zeros(self.out_buf.numel(), dtype=torch.int32).pin_memory()
+            a = K.StepArgs()
+            a.tokens_dev, a.token_stride, a.counts_dev = None, 0, None
+            a.start_tok_dev = start.data_ptr()
+            base = out.data_ptr()
+            a.out_type_dev, a.out_match_dyn_dev, a.out_match_static_dev = base, base + 4, base + 8
+            a.out_index_dyn_dev, a.out_index_static_dev, a.out_draft_len_dev = base + 12, base + 16, base + 20
+            a.out_draft_dev, a.draft_stride = base + 24, self.n_predicts
+            h = self._hl = (a, start, out, start.numpy(), out.numpy())
+        a, start, out, start_np, out_np = h
+        self._fill_common(a)
+        start_np[0] = int(start_token)
+        self._make_current()
+        st = torch.cuda.current_stream()
+        K.check(K.lib().samd_step(C.byref(a), st.cuda_stream), "samd_step")
+        st.synchronize()
+        return out_np
+
     # ---- host-buffer path: one H2D copy in, one launch, one D2H copy out ---------------------------
     def host_buffers(self, max_tokens_per_step: int = 8):
         """Pinned host staging buffers for step_host(): `inp` = [counts (B) | start (B) | tokens (B x k)],

@@ -87,6 +87,15 @@ class DraftModel(torch.nn.Module):
     @profile_decorator("DraftModel.lookup")
     def lookup(self, start_token: int):
         e = self._bind()
+        if e.static is None or not e.static.with_counts:
+            # host-facing fast path (no static tree to draft): DraftEngine.host_lookup - one launch that reads the start
+            # token from and writes every output to mapped pinned host memory, one stream synchronise
+            out_np = e.host_lookup(start_token)
+            n = int(out_np[5])                                   # layout of DraftEngine.out_buf at one request
+            pos = e.__dict__.get("_seq_pos")
+            if pos is None:
+                pos = e._seq_pos = torch.arange(0, e.n_predicts, dtype=torch.long, device=e.dyn.device).unsqueeze(0)
+            return (CandidateType.sequence, out_np[6:6 + n].tolist(), {"seq_position_ids": pos[:, :n]})
         e.start.fill_(int(start_token))
         kind, toks, buffers = self.results(self.lookup_device(e.start))
         return (kind, toks.tolist(), buffers)
@@ -98,8 +107,10 @@ class DraftModel(torch.nn.Module):
             return
         self.sam_dyn._ensure(k)
         e = self._bind()
-        row = tokens.reshape(1, -1).to(device=e.dyn.device, dtype=torch.int32).contiguous()
-        e.step(row, None, None)
+        row = tokens.reshape(1, -1)
+        if row.dtype != torch.int32 or row.device != e.dyn.device or not row.is_contiguous():
+            row = row.to(device=e.dyn.device, dtype=torch.int32).contiguous()
+        e.quick_update(row)
         self.sam_dyn._n_tokens += k
 
     @profile_decorator("DraftModel.prefill_update")

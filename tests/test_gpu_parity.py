@@ -896,3 +896,31 @@ def test_peer_exchange_single_rank_matches_key_path():
         for s in range(steps):
             assert torch.equal(outs[s][0], want[s][0]) and torch.equal(outs[s][1], want[s][1]), (rep, s)
     assert b.peers_ok()
+
+
+def test_static_l2_window_does_not_change_results():
+    """samd_static_set_l2_window pins the record prefix in L2 through an access-policy window (a residency hint; measured
+    on the 50 M-token automaton: no gain): lookups and drafts with and without it must be identical."""
+    E, K = _engine_mod()
+    from samd_b200 import synth
+    docs = synth.make_corpus(300000, 32000, 71, singletons=True)
+    st = E.StaticSamDevice.build(docs, synth.EOS)
+    nq = 256
+    q = synth.corpus_queries(docs, nq, 40, 32000, 72).astype(np.int32)
+
+    def run():
+        dyn = E.DynSamBatch(nq, 128)
+        eng = E.DraftEngine(dyn, st, K.FLAVOUR_SAMD, n_predicts=16, len_bias=0, len_threshold=0)
+        outs = []
+        for s in range(4):
+            eng.step(_dev_i32(q[:, 8 * s:8 * s + 8]), None, _dev_i32(q[:, 8 * s + 8]))
+            outs.append(eng.out_buf.clone())
+        torch.cuda.synchronize()
+        return torch.stack(outs)
+
+    base = run()
+    st.set_l2_window(32 << 20)
+    pinned = run()
+    st.set_l2_window(0)
+    again = run()
+    assert torch.equal(base, pinned) and torch.equal(base, again)
