@@ -899,8 +899,13 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
         b.d.recs = recs;
         b.d.slots = slots;
         b.d.text = text;
-        b.d.bmask = P.dyn.bmask;
-        b.d.max_tokens = P.dyn.max_tokens;
+        {
+            unsigned bm = P.dyn.bmask;                        // (likewise: not re-read from the constant bank at every use)
+            int mt = P.dyn.max_tokens;
+            asm volatile("" : "+r"(bm), "+r"(mt));
+            b.d.bmask = bm;
+            b.d.max_tokens = mt;
+        }
         b.x_state = -1;
         b.tr.trace = (kProf && P.trace) ? P.trace + (size_t)r * P.trace_cap + 1 : nullptr;
         b.tr.cap = P.trace_cap - 1;
@@ -938,7 +943,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
                     break;
                 }
                 if (P.has_static) sc_prefetch_rec(P.st.recs, s_idx);
-                if (b.g.n >= P.dyn.max_tokens) {
+                if (b.g.n >= b.d.max_tokens) {
                     // arena full: the token cannot be appended (the flag tells the caller to grow); the cursors still
                     // follow the text so that the lookups keep returning what the automaton knows
                     flags |= 1;
