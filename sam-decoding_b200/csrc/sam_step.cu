@@ -768,11 +768,12 @@ __device__ __forceinline__ void sc_scout_walk(const int32_t *recs, const uint4 *
             sc_prefetch(slots + (size_t)(samd_hash((uint32_t)idx, (uint32_t)tok) & bmask) * SAMD_BUCKET);
         }
         if (!kStatic && mailbox && i < k) {                  // every token gets an entry (stop 0 = nothing to look up)
-            mailbox[4 * i + 0] = up_state;
-            mailbox[4 * i + 1] = tok;
-            mailbox[4 * i + 2] = up_target;
+            // (atomics: a hand-off between two warps of the CTA that the race checker can follow)
+            atomicExch((int *)&mailbox[4 * i + 0], up_state);
+            atomicExch((int *)&mailbox[4 * i + 1], tok);
+            atomicExch((int *)&mailbox[4 * i + 2], up_target);
             __threadfence_block();
-            mailbox[4 * SCOUT_MAX_TOKENS] = i + 1;
+            atomicExch((int *)&mailbox[4 * SCOUT_MAX_TOKENS], i + 1);
         }
     }
     if (peek < 0) return;
@@ -814,14 +815,14 @@ __device__ __forceinline__ void sc_redirect_scout(const int32_t *recs, const uin
     if (k > SCOUT_MAX_TOKENS) return;
     for (int i = 0; i < k; ++i) {
         while (true) {
-            if (mailbox[4 * SCOUT_MAX_TOKENS] > i) break;
-            if (mailbox[4 * SCOUT_MAX_TOKENS + 1]) return;                     // the cursor scout is done and never got this far
+            if (atomicAdd((int *)&mailbox[4 * SCOUT_MAX_TOKENS], 0) > i) break;
+            if (atomicAdd((int *)&mailbox[4 * SCOUT_MAX_TOKENS + 1], 0)) return;   // the cursor scout is done and never got this far
             __nanosleep(40);
         }
         __threadfence_block();
-        int pp = mailbox[4 * i + 0];
-        const int tok = mailbox[4 * i + 1];
-        const int target = mailbox[4 * i + 2];
+        int pp = atomicAdd((int *)&mailbox[4 * i + 0], 0);
+        const int tok = atomicAdd((int *)&mailbox[4 * i + 1], 0);
+        const int target = atomicAdd((int *)&mailbox[4 * i + 2], 0);
         for (int up = 0; up < 6 && pp > 0 && !sc_bad(pp, cap); ++up) {
             const Rec Y = rec_load<false>(recs, pp);
             const Probe pr = rec_probe<false>(Y, slots, bmask, pp, tok, 16);
@@ -876,7 +877,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
             sc_scout_walk<false>(recs, slots, P.dyn.bmask, text, meta[META_CUR], tk, k, peek, P.n_predicts, (long long)meta[META_N],
                                  (long long)P.dyn.s_cap, (blockDim.x > 64 && !P.has_static) ? s_mailbox : nullptr, P.prewalk);
             __threadfence_block();
-            *(volatile int *)&s_mailbox[4 * SCOUT_MAX_TOKENS + 1] = 1;   // whatever path the scout left by: no more hand-offs
+            atomicExch(&s_mailbox[4 * SCOUT_MAX_TOKENS + 1], 1);         // whatever path the scout left by: no more hand-offs
         } else if (P.has_static) {
             sc_scout_walk<true>(P.st.recs, P.st.slots, P.st.bmask, P.st.text, P.static_cursor[2 * r], tk, k, peek, P.n_predicts,
                                 (long long)P.st.n_tokens, (long long)P.st.n_states, nullptr, P.prewalk);
