@@ -342,10 +342,12 @@ int samd_verify_sample(const samd_sample_args *args, void *stream);
 int samd_recycle_gen_tree(const int32_t *table_dev, int32_t vocab, const int32_t *parent_dev, const int32_t *rank_dev,
                           int32_t n_nodes, const int32_t *start_tok_dev, const int32_t *type_dev, int32_t only_type,
                           int32_t batch, int32_t *out_tokens_dev, void *stream);
-/* tuning hook: 1 (default) = overlapped flow of samd_verify_compact - a request is walked by the warp that reports its
+/* tuning hook: 1 = overlapped flow of samd_verify_compact - a request is walked by the warp that reports its
  * last logits chunk and its KV rows are moved by warps that have run out of logits, while the rest still streams; no
- * grid-wide barrier.  0 = the two-barrier flow (stream, barrier, walks, barrier, row moves).  Launches that also
- * compute the top-8 lists always use the barrier flow. */
+ * grid-wide barrier.  2 = walks as requests complete + L2 prefetch of their source rows, row moves after the last walk;
+ * 3 = the same without the prefetch.  0 (default) = the two-barrier flow (stream, barrier, walks, barrier, row moves):
+ * measured on c4, 79.6 us against 94.7 / 152 / 82.3 for modes 1 / 2 / 3.  Launches that also compute the
+ * top-8 lists always use the barrier flow. */
 void samd_verify_set_overlap(int on);
 /* tuning hook: logits elements per phase-1 work item (0 = default) */
 void samd_verify_set_chunk(int elements);

@@ -245,11 +245,12 @@ def test_verify_sequence_golden():
     assert (out["best"] == 0).all()
 
 
-@pytest.mark.parametrize("overlap", [0, 1, 2])
+@pytest.mark.parametrize("overlap", [0, 1, 2, 3])
 def test_kv_compaction_golden(overlap):
     """select_indices through the fused kernel: the fixture's 16 cases as one batch of 16 requests.  All three flows of
     the kernel: 0 = stream / barrier / walks / barrier / row moves (the default), 1 = walks as requests complete and
-    ticketed row moves, 2 = early walks + L2 prefetch of the source rows (the two measured alternatives)."""
+    ticketed row moves, 2 = early walks + L2 prefetch of the source rows, 3 = early walks only (the measured alternatives,
+    DESIGN.md)."""
     E, K = _engine_mod()
     K.lib().samd_verify_set_overlap(overlap)
     try:
