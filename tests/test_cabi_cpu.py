@@ -116,3 +116,27 @@ def test_header_is_plain_c(tmp_path):
                     "-lsamd_b200", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == len(names) and int(out[1]) == K.lib().samd_abi_version()
+
+
+def test_host_builder_overflow_table_growth():
+    """The host builder's overflow table starts at 64 k slots and doubles when half full (sam_static.cu HostSam::grow):
+    70 000 single-token documents give the root 70 000 out-edges, i.e. two doublings, with hub states in between; states,
+    links, lengths, min_endpos and every state's edges in insertion order must still equal the oracle's."""
+    import samd_oracle as O
+    from samd_b200 import engine as E
+    rng = np.random.default_rng(9)
+    docs = [rng.integers(3, 50, size=int(rng.integers(5, 40))).tolist() for _ in range(300)]
+    docs += [[t] for t in range(70000)]
+    docs += [rng.integers(3, 70000, size=30).tolist() for _ in range(200)]
+    st = E.StaticSamDevice.build(docs, 2, with_counts=True, host_only=True)
+    ref = O.build_static(docs, 2, count_occurrences=True)
+    ex = st.export()
+    assert st.n_states == ref.n_states and st.n_edges == ref.n_edges
+    assert np.array_equal(ex["link"], np.array(ref.link)) and np.array_equal(ex["length"], np.array(ref.length))
+    assert np.array_equal(ex["min_endpos"], np.array(ref.first_end)) and np.array_equal(ex["cnt_endpos"], np.array(ref.occ))
+    assert st.n_slots >= 2 * 65536                       # the table really grew
+    edges = np.zeros((st.n_edges, 3), dtype=np.int32)
+    from samd_b200 import _cabi as K
+    K.check(K.lib().samd_static_export_edges(st.handle, edges.ctypes.data_as(K.c_i32p), None))
+    want = [(v, t, g) for v in range(ref.n_states) for t, g in ref.trans[v].items()]
+    assert [tuple(e) for e in edges.tolist()] == want
