@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--only-c1", action="store_true", help="run only the c1 (one request) measurement")
     ap.add_argument("--only-tree", action="store_true", help="run only the sam_only static tree drafter measurement")
     ap.add_argument("--scouts", type=int, default=2, help="profiling aid: scout warps of the step kernel (0 none, 1 cursor scouts, 2 all)")
+    ap.add_argument("--tma", type=int, default=None, help="tuning aid: 1 bulk-copy staged / 0 register staged logits stream of the verify kernel")
+    ap.add_argument("--even-items", type=int, default=None, help="tuning aid: 1 even / 0 all-warps phase-1 item split of the verify kernel")
     ap.add_argument("--overlap", type=int, default=None, help="tuning aid: 1 overlapped / 0 two-barrier flow of the verify kernel")
     ap.add_argument("--lean", type=int, default=None, help="tuning aid: 1 lean / 0 wide build of the step kernel (default: by batch size)")
     ap.add_argument("--ngram", type=int, default=None, help="tuning aid: depth of the short-context scouts (-1 off)")
@@ -337,6 +339,10 @@ def run_ours(a):
         K.lib().samd_step_set_lean(a.lean)
     if a.overlap is not None:
         K.lib().samd_verify_set_overlap(a.overlap)
+    if a.even_items is not None:
+        K.lib().samd_verify_set_even_items(a.even_items)
+    if a.tma is not None:
+        K.lib().samd_verify_set_tma(a.tma)
     launches0 = E.launch_count()
     if a.only_verify:                         # profiling aid (ncu): just the c4 loop
         print(json.dumps({"verify": bench_verify(a, dev, 6458.1, iters=6, warm=2)}))

@@ -349,6 +349,14 @@ int samd_recycle_gen_tree(const int32_t *table_dev, int32_t vocab, const int32_t
  * measured on c4, 79.6 us against 94.7 / 152 / 82.3 for modes 1 / 2 / 3.  Launches that also compute the
  * top-8 lists always use the barrier flow. */
 void samd_verify_set_overlap(int on);
+/* tuning hook: 1 (default) = only as many warps stream logits as divide the work items evenly (the rest of the grid joins
+ * for the row moves); 0 = every resident warp takes items (round 1). */
+void samd_verify_set_even_items(int on);
+/* tuning hook: 1 = 16-bit logits are streamed through shared memory by the bulk-copy engine (cp.async.bulk + mbarrier
+ * ring, 8 KB in flight per warp; UBLKCP / SYNCS in SASS); 0 (default) = register-staged 128-bit loads.  Measured on c4:
+ * 56.9 vs 50.0 us verify-only (the ring's shared memory costs a quarter of the resident warps and the stream was already at
+ * 6.1-7 TB/s), so the register path stays the default. */
+void samd_verify_set_tma(int on);
 /* tuning hook: logits elements per phase-1 work item (0 = default) */
 void samd_verify_set_chunk(int elements);
 /* profiling hook: [grid warps][3] uint64 globaltimer ns per warp of the next launches - start, end of the logits

@@ -51,6 +51,9 @@ struct VerifyParams {
     int overlap;                     // 1 = walks as requests complete, ticketed row moves, no grid barrier
     int max_nodes, max_batch;
     int chunk, chunks_per_row, n_items1, n_items2, vec_ok, stage_cap;
+    int p1_warps;                    // warps that take part in phase 1 (<= the grid's warps)
+    int tma;                         // 1 = phase 1 stages the logits through shared memory with the bulk-copy engine
+    int ring_off;                    // byte offset of the staging rings in dynamic shared memory (128-byte aligned)
     unsigned long long *topk_part;   // [n_items1][TOPK] per-chunk lists (top-k launches)
     unsigned long long *dbg_times;   // optional [grid warps][3] globaltimer ns: start, end of streaming, exit (profiling hook)
 };
@@ -142,6 +145,34 @@ __device__ __forceinline__ void fold_vec(const uint4 &x, uint32_t elem, uint32_t
             }
         }
     }
+}
+
+// ---- bulk-copy engine (TMA) staging: global -> shared with an mbarrier per stage ---------------------------------
+#define TMA_STAGES 4           // groups (2 KB each) in flight per warp
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 template <int G>
@@ -528,9 +559,108 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
         const uint32_t ninf = kDtype == SAMD_DTYPE_BF16 ? 0xFF80FF80u : 0xFC00FC00u;
         const bool vec16 = k16 && P.vec_ok;
         uint4 xa[G], xb[G];
-        Item cur = decode_item(P, gwarp), nx;
+        // only the first p1 warps stream logits (the launch sizes p1 so that the items divide evenly among them, see
+        // samd_verify_compact); the others go straight to the barrier and join the row moves
+        const int p1 = P.p1_warps;
+        Item cur = decode_item(P, gwarp < p1 ? gwarp : P.n_items1), nx;
         int queue = gwarp % N_QUEUES;                           // lane 0's view is the one that counts
         bool stolen = false;
+        if constexpr (!kTopK && k16) {
+            if (P.tma) {
+                // ---- bulk-copy staged stream.  A group = 32 x G consecutive 16-byte vectors (2 KB) of the item; lane 0 asks
+                // the copy engine for it - one instruction, completion on the stage's mbarrier - TMA_STAGES groups ahead of
+                // the fold, across item boundaries; the warp reads a landed group out of shared memory (conflict-free
+                // 128-bit loads) into the registers fold_group works on.  What is in flight no longer lives in registers:
+                // 8 KB per warp instead of 2-4, which is what the stream was short of (it ran at the rate of its slowest
+                // warps' round trips, not at the DRAM's).
+                constexpr int GV = 32 * G;
+                uint4 *ring = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(s_am_all) + P.ring_off) + (size_t)warp * TMA_STAGES * GV;
+                unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+                                               reinterpret_cast<unsigned char *>(s_am_all) + P.ring_off + (size_t)VW * TMA_STAGES * GV * 16) + warp * TMA_STAGES;
+                if (lane == 0)
+                    for (int st = 0; st < TMA_STAGES; ++st) mbar_init(&bars[st], 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                Item pit = cur;                                 // the item the producer is issuing from
+                int pv = 0, pstage = 0, cstage = 0, inflight = 0;
+                uint32_t phases = 0;
+                auto claim_next = [&]() {                       // blocking claim of the next item (lane 0's atomics)
+                    int nxt = 0;
+                    if (lane == 0) {
+                        nxt = p1 + atomicAdd(&P.counters[CN_QUEUES + queue * QUEUE_STRIDE], 1) * N_QUEUES + queue;
+                        if (nxt >= P.n_items1 && !stolen) {
+                            stolen = true;
+                            queue = (queue + N_QUEUES / 2) % N_QUEUES;
+                            nxt = p1 + atomicAdd(&P.counters[CN_QUEUES + queue * QUEUE_STRIDE], 1) * N_QUEUES + queue;
+                        }
+                    }
+                    return decode_item(P, __shfl_sync(SAMD_FULL, nxt, 0));
+                };
+                auto produce = [&]() {                          // issue the next group, if there is one
+                    if (pit.item >= P.n_items1) return;
+                    const int nvec = pit.len >> 3;
+                    const int nv = min(GV, nvec - pv);
+                    if (lane == 0) {
+                        mbar_expect_tx(&bars[pstage], (uint32_t)nv * 16u);
+                        bulk_g2s(ring + (size_t)pstage * GV, reinterpret_cast<const uint4 *>(logits + item_offset(P, pit)) + pv,
+                                 (uint32_t)nv * 16u, &bars[pstage]);
+                    }
+                    pv += GV;
+                    pstage = (pstage + 1) % TMA_STAGES;
+                    ++inflight;
+                    if (pv >= nvec) {                           // the item is fully requested: on to the next one
+                        nx = claim_next();
+                        pit = nx;
+                        pv = 0;
+                    }
+                };
+                for (int st = 0; st < TMA_STAGES; ++st) produce();
+                while (cur.item < P.n_items1) {
+                    const int e0 = cur.e0, len = cur.len;
+                    const int nvec = len >> 3;
+                    const Item mine = cur;
+                    uint32_t best_key = 0, best_idx = 0;
+                    for (int v0 = 0; v0 < nvec; v0 += GV) {
+                        mbar_wait(&bars[cstage], (phases >> cstage) & 1u);
+                        phases ^= 1u << cstage;
+                        const uint4 *sg = ring + (size_t)cstage * GV;
+#pragma unroll
+                        for (int u = 0; u < G; ++u) {
+                            const int vi = v0 + u * 32 + lane;
+                            xa[u] = vi < nvec ? sg[u * 32 + lane] : make_uint4(ninf, ninf, ninf, ninf);
+                        }
+                        cstage = (cstage + 1) % TMA_STAGES;
+                        --inflight;
+                        // fold first: its warp-wide reduction consumes every lane's vectors, so all reads of the stage are
+                        // complete before lane 0 hands the stage back to the copy engine
+                        fold_group<kDtype, G>(xa, v0, nvec, lane, e0, best_key, best_idx);
+                        __syncwarp();
+                        produce();
+                    }
+                    const uint16_t *row = logits + item_offset(P, mine);
+                    const int tail = nvec << 3;
+                    if (len - tail > 0) {                       // < 8 trailing elements, all later than the vectors
+                        const uint32_t ke = lane < len - tail ? orderable16<kDtype>(row[tail + lane]) : 0u;
+                        const uint32_t wk = __reduce_max_sync(SAMD_FULL, ke);
+                        if (wk > best_key) {
+                            best_key = wk;
+                            best_idx = (uint32_t)(e0 + tail + __ffs(__ballot_sync(SAMD_FULL, ke == wk)) - 1);
+                        }
+                    }
+                    if (lane == 0) {
+                        const unsigned long long pk =
+                            best_key ? (((unsigned long long)best_key << 32) | (unsigned long long)(0xFFFFFFFFu - best_idx)) : 0ull;
+                        unsigned long long *kp = &P.node_key[(size_t)mine.b * P.max_nodes + mine.t];
+                        if (C == 1) *reinterpret_cast<volatile unsigned long long *>(kp) = pk;
+                        else atomicMax(kp, pk);
+                    }
+                    // the producer finished this item at least one group ago (an item has more groups than the ring has
+                    // stages), so `nx` is the item that follows it
+                    cur = nx;
+                }
+                cur = decode_item(P, P.n_items1);               // nothing left for the register-staged loop below
+            }
+        }
         if (vec16 && cur.act)
             load_group<G>(xa, reinterpret_cast<const uint4 *>(logits + item_offset(P, cur)), 0, cur.len >> 3, lane, ninf);
         for (; cur.item < P.n_items1; cur = nx) {
@@ -541,11 +671,11 @@ __global__ void __launch_bounds__(VT, 4) verify_compact_kernel(VerifyParams P) {
             auto fetch_next = [&]() {
                 int nxt = 0;
                 if (lane == 0) {
-                    nxt = n_warps + claim * N_QUEUES + queue;
+                    nxt = p1 + claim * N_QUEUES + queue;
                     if (nxt >= P.n_items1 && !stolen) {         // home queue drained: one try at the opposite queue
                         stolen = true;
                         queue = (queue + N_QUEUES / 2) % N_QUEUES;
-                        nxt = n_warps + atomicAdd(&P.counters[CN_QUEUES + queue * QUEUE_STRIDE], 1) * N_QUEUES + queue;
+                        nxt = p1 + atomicAdd(&P.counters[CN_QUEUES + queue * QUEUE_STRIDE], 1) * N_QUEUES + queue;
                     }
                 }
                 nx = decode_item(P, __shfl_sync(SAMD_FULL, nxt, 0));
@@ -993,6 +1123,10 @@ extern "C" int samd_verify_destroy(samd_verify_t h) {
 static int g_chunk_override = 0;
 static int g_min_chunk = 2048;
 static int g_overlap = 0;
+static int g_even_items = 1;
+static int g_tma = 0;
+extern "C" void samd_verify_set_tma(int on) { g_tma = on; }
+extern "C" void samd_verify_set_even_items(int on) { g_even_items = on; }
 extern "C" void samd_verify_set_overlap(int on) { g_overlap = on; }
 static unsigned long long *g_dbg_times = nullptr;
 extern "C" void samd_verify_set_debug_times(uint64_t *times_dev) { g_dbg_times = (unsigned long long *)times_dev; }
@@ -1028,9 +1162,11 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     P.dbg_times = g_dbg_times;
     P.max_nodes = h->max_nodes;
     P.stage_cap = move ? std::min(a->batch, 512) : 0;
-    const size_t smem = ((size_t)VW * 2 * a->n_nodes + (size_t)P.stage_cap * (3 + KV_GROUP)) * sizeof(int);
+    size_t smem = ((size_t)VW * 2 * a->n_nodes + (size_t)P.stage_cap * (3 + KV_GROUP)) * sizeof(int);
     const bool topk = a->out_topk_dev != nullptr;
     P.overlap = topk ? 0 : g_overlap;
+    P.tma = 0;
+    P.ring_off = 0;
     SAMD_REQUIRE(!a->recycle_table_dev || (topk && a->recycle_owner_dev),
                  "samd_verify_compact: a recycle table needs out_topk_dev and recycle_owner_dev");
     SAMD_REQUIRE(!topk || a->vocab >= TOPK, "samd_verify_compact: top-8 needs a vocabulary of at least 8");
@@ -1038,6 +1174,15 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     auto kern = a->dtype == SAMD_DTYPE_BF16   ? (topk ? verify_compact_kernel<SAMD_DTYPE_BF16, true> : verify_compact_kernel<SAMD_DTYPE_BF16, false>)
                 : a->dtype == SAMD_DTYPE_FP16 ? (topk ? verify_compact_kernel<SAMD_DTYPE_FP16, true> : verify_compact_kernel<SAMD_DTYPE_FP16, false>)
                                               : (topk ? verify_compact_kernel<SAMD_DTYPE_FP32, true> : verify_compact_kernel<SAMD_DTYPE_FP32, false>);
+    // Bulk-copy staging of the logits stream (16-bit logits, no top-8, no dead rows, barrier flow, aligned rows, a
+    // vocabulary large enough for items of several groups): every warp gets a ring of TMA_STAGES 2 KB stages + mbarriers
+    P.vec_ok = ((uintptr_t)a->logits_dev % 16 == 0) && (a->batch_stride % 8 == 0) && (a->row_stride % 8 == 0);
+    const bool tma_ok = g_tma && !topk && a->dtype != SAMD_DTYPE_FP32 && P.vec_ok && !P.overlap && !a->n_nodes_dev && a->vocab >= 16384;
+    if (tma_ok) {
+        P.ring_off = (int)((smem + 127) & ~(size_t)127);
+        smem = (size_t)P.ring_off + (size_t)VW * TMA_STAGES * (32 * (UNROLL / 2)) * 16 + (size_t)VW * TMA_STAGES * 8;
+        P.tma = 1;
+    }
     if (smem > 48 * 1024) {
         // large path tables (eval_posterior verifies P*D rows as nodes): beyond 48 KB the kernel has to opt in
         SAMD_REQUIRE(smem <= 200 * 1024, "samd_verify_compact: n_nodes too large for the per-warp node tables in shared memory");
@@ -1064,7 +1209,8 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     P.n_items1 = (int)rows * P.chunks_per_row;
     SAMD_REQUIRE(!topk || P.n_items1 <= h->topk_items, "samd_verify_compact: top-8 scratch too small for this shape");
     P.n_items2 = move ? a->batch * a->n_kv : 0;
-    P.vec_ok = ((uintptr_t)a->logits_dev % 16 == 0) && (a->batch_stride % 8 == 0) && (a->row_stride % 8 == 0);
+    // the staged stream runs TMA_STAGES groups ahead, across ONE item boundary: every item must hold more groups than that
+    if (P.tma && a->vocab - (P.chunks_per_row - 1) * chunk < (TMA_STAGES + 1) * 32 * (UNROLL / 2) * 8) P.tma = 0;
     // One warp per item up to the resident grid.  With row moves, a small batch keeps a small grid too (every CTA
     // takes part in the barriers, whose cost grows with their number: 20.6 -> 19.1 us per launch at batch 1) as long as
     // each moved request still finds about 32 CTAs' worth of lanes for its 16-byte units.
@@ -1072,6 +1218,16 @@ extern "C" int samd_verify_compact(samd_verify_t h, const samd_verify_args *a, v
     long long grid = std::min<long long>(full, ((long long)P.n_items1 + VW - 1) / VW);
     if (move) grid = std::max<long long>(grid, std::min<long long>(full, (long long)a->batch * 32));
     grid = std::max<long long>(grid, 1);
+    // Phase-1 warps.  Every warp streams at about the same rate, so the phase ends when the warps with the most items end:
+    // 7808 items over 4736 resident warps means 3072 warps stream two items while 1664 idle through the second half
+    // (measured: first items end at 20-24 us, second ones at 37-44).  With p1 = ceil(items / ceil(items / warps)) every
+    // streaming warp gets the same number of items (c4: 3904 warps x 2, c5: 4462 x 7) and the rest of the grid waits at
+    // the barrier for the row moves.
+    {
+        const long long w = grid * VW;
+        const long long per = std::max<long long>(1, (P.n_items1 + w - 1) / w);
+        P.p1_warps = g_even_items ? (int)std::min<long long>(w, (P.n_items1 + per - 1) / per) : (int)w;
+    }
     // Cooperative launch: the kernel's barriers need every CTA resident at once, and only a cooperative launch makes
     // the driver guarantee it - two overlapping launches (two handles on two streams) would otherwise each hold part
     // of the machine and wait for the rest forever.

@@ -126,6 +126,8 @@ SYMBOLS = {
     "samd_recycle_gen_tree": (C.c_int, [vp, C.c_int32, vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "samd_verify_set_chunk": (None, [C.c_int]),
     "samd_verify_set_overlap": (None, [C.c_int]),
+    "samd_verify_set_even_items": (None, [C.c_int]),
+    "samd_verify_set_tma": (None, [C.c_int]),
     "samd_verify_set_debug_times": (None, [C.c_void_p]),
 }
 

@@ -373,10 +373,20 @@ def test_dyn_batch_vs_oracle_8k():
         assert np.array_equal(ex["min_endpos"], np.array(oracles[r].first_end))
 
 
-def test_verify_full_size_properties():
+@pytest.mark.parametrize("tma", [0, 1])
+def test_verify_full_size_properties(tma):
     """Config-4 shape (B=64, T=61, V=32000, bf16): node argmax equals torch.argmax, outputs equal
-    the oracle walk, and the compacted KV rows equal an index_select reference."""
+    the oracle walk, and the compacted KV rows equal an index_select reference.  tma = 1: the logits stream staged
+    through shared memory by the bulk-copy engine (cp.async.bulk + mbarrier ring; a measured alternative, default off)."""
     E, K = _engine_mod()
+    K.lib().samd_verify_set_tma(tma)
+    try:
+        _verify_full_size(E, K)
+    finally:
+        K.lib().samd_verify_set_tma(0)
+
+
+def _verify_full_size(E, K):
     from samd_b200 import synth
     B, T, V = 64, 61, 32000
     ri_np = synth.tree_retrieve_indices(synth.token_recycle_tree())
