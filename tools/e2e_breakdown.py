@@ -1,0 +1,84 @@
+"""Where the host-to-host time of a c2 step goes (profiling aid; run from the repo root): the zero-copy step as the bench
+runs it, its device-side duration, and the launch + synchronise floor of an empty graph on this box."""
+import sys, time
+sys.path.insert(0, "sam-decoding_b200"); sys.path.insert(0, ".")
+import numpy as np
+import torch
+import bench
+from samd_b200 import _cabi as K, engine as E
+dev = torch.device("cuda")
+R, N, S, W = 1024, 8192, 128, 16
+streams, counts, tokens, start = bench.make_workload(R, N, S + W, 2000)
+dyn = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
+snap = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
+eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=bench.N_PREDICTS, len_bias=bench.LEN_BIAS, len_threshold=bench.LEN_THRESHOLD)
+eng.step(torch.as_tensor(streams[:, :N]).to(dev), None, None)
+d_tok, d_cnt, d_st = (torch.as_tensor(x).to(dev) for x in (tokens, counts, start))
+for s in range(W):
+    eng.step(d_tok[s], d_cnt[s], d_st[s])
+torch.cuda.synchronize()
+snap.copy_from(dyn)
+inp, res = eng.host_buffers(8)
+h_in = torch.empty(W + S, inp.numel(), dtype=torch.int32).pin_memory()
+h_in[:, :R] = torch.as_tensor(counts)
+h_in[:, R:2 * R] = torch.as_tensor(start)
+h_in[:, 2 * R:] = torch.as_tensor(tokens).reshape(W + S, R * 8)
+staged = [h_in[s] for s in range(W + S)]
+eng.step_host(inp, res)
+dyn.copy_from(snap); torch.cuda.synchronize()
+# (1) as the bench: stage, launch, wait
+t0 = time.perf_counter()
+for s in range(W, W + S):
+    inp.copy_(staged[s]); eng.step_host(inp, res)
+t_e2e = (time.perf_counter() - t0) / S * 1e6
+# (2) device-side duration of the same zero-copy launches (events, no host wait in between)
+dyn.copy_from(snap); torch.cuda.synchronize()
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(S)]
+for i, s in enumerate(range(W, W + S)):
+    inp.copy_(staged[s]); ev[i][0].record(); eng.step_host(inp, res, sync=False); ev[i][1].record(); torch.cuda.synchronize()
+t_dev_zc = float(np.median([a.elapsed_time(b) for a, b in ev])) * 1e3
+# (3) device-resident inputs / outputs, same launches one at a time
+dyn.copy_from(snap); torch.cuda.synchronize()
+for i, s in enumerate(range(W, W + S)):
+    ev[i][0].record(); eng.step(d_tok[s], d_cnt[s], d_st[s]); ev[i][1].record(); torch.cuda.synchronize()
+t_dev = float(np.median([a.elapsed_time(b) for a, b in ev])) * 1e3
+# (4) launch + synchronise floor: an empty graph
+x = torch.zeros(1, device=dev)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    x.add_(1)
+t0 = time.perf_counter()
+for _ in range(S):
+    g.replay(); torch.cuda.current_stream().synchronize()
+t_floor = (time.perf_counter() - t0) / S * 1e6
+t0 = time.perf_counter()
+for s in range(W, W + S):
+    inp.copy_(staged[s])
+t_stage = (time.perf_counter() - t0) / S * 1e6
+print(f"host to host {t_e2e:.1f} us/step = caller's staging copy {t_stage:.1f} + launch/sync floor of an empty graph {t_floor:.1f} + "
+      f"kernel with mapped host I/O {t_dev_zc:.1f} (events; {t_dev:.1f} with device-resident I/O, launched one at a time)")
+# (5) the same with the GPU kept out of its idle state by a one-warp spinner on another stream (diagnostic only)
+import ctypes as C
+spin_src = r'''
+extern "C" __global__ void spin(volatile int *stop) { while (!*stop) { __nanosleep(200); } }
+'''
+try:
+    from torch.utils.cpp_extension import load_inline
+    raise RuntimeError("skip the extension build on the box")
+except Exception:
+    pass
+stop = torch.zeros(1, dtype=torch.int32, device=dev)
+side = torch.cuda.Stream(dev)
+big = torch.zeros(1 << 20, device=dev)
+def busy(n):
+    with torch.cuda.stream(side):
+        for _ in range(n):
+            big.add_(1)          # a train of small kernels on another stream keeps the SMs clocked while we measure
+dyn.copy_from(snap); torch.cuda.synchronize()
+tt = []
+for i, s in enumerate(range(W, W + S)):
+    busy(40)
+    inp.copy_(staged[s]); ev[i][0].record(); eng.step_host(inp, res, sync=False); ev[i][1].record(); torch.cuda.current_stream().synchronize()
+    tt.append(ev[i][0].elapsed_time(ev[i][1]) * 1e3)
+torch.cuda.synchronize()
+print(f"with a train of small kernels running on another stream: kernel with mapped host I/O {np.median(tt):.1f} us")
