@@ -173,11 +173,11 @@ typedef struct samd_step_args {
 
 int samd_step(const samd_step_args *args, void *stream);
 /* profiling hook: when non-NULL, every samd_step launch that performs a lookup writes each request's SM
- * cycle counts to cycles_dev[12][n_requests].  Variant 0: whole request, cursor transfers, appends, lookup + draft, then
+ * cycle counts to cycles_dev[16][n_requests].  Variant 0: whole request, cursor transfers, appends, lookup + draft, then
  * inside the appends: chain look-ups, edge inserts, (unused), target record, clone overflow copy, clone redirect walk.
  * Variant 1: whole request, cycles waiting for record loads, update phase, lookup phase, number of record loads that took
  * < 120 / < 500 / < 1100 / more cycles, overflow-probe cycles and count, then %globaltimer (ns) at the builder's start and
- * end (rows 10, 11). */
+ * end (rows 10, 11), cycles in the cursor walks, in the clones' redirect walks and before the first token (rows 12-14). */
 void samd_step_set_debug_cycles(int64_t *cycles_dev);
 /* tuning hook: scout (prefetcher) warps of samd_step - 0 none, 1 the cursor scouts, 2 (default) also the redirect scout */
 void samd_step_set_scouts(int on);

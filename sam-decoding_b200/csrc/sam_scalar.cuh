@@ -216,7 +216,8 @@ SAMD_HD void sc_consume(int a, int b) {
     (void)a; (void)b;
 #endif
 }
-enum { SC_PF_LOAD_CYC = 0, SC_PF_L1 = 1, SC_PF_L2 = 2, SC_PF_DRAM = 3, SC_PF_SLOW = 4, SC_PF_OVF_CYC = 5, SC_PF_OVF_N = 6, SC_PF_N = 8 };
+enum { SC_PF_LOAD_CYC = 0, SC_PF_L1 = 1, SC_PF_L2 = 2, SC_PF_DRAM = 3, SC_PF_SLOW = 4, SC_PF_OVF_CYC = 5, SC_PF_OVF_N = 6, SC_PF_WALK_CYC = 7,
+       SC_PF_REDIR_CYC = 8, SC_PF_N = 10 };
 
 template <bool kProf>
 struct ScBuilderT {
@@ -296,6 +297,8 @@ struct ScBuilderT {
     // cursor IS link(last) - or, right after a split, the pre-clone state one stop in front of it.  So the two walks
     // are ONE: a stop that lacks the edge gets it on the spot, from the record the probe already holds.
     SAMD_HD void extend_one(int tok) {
+        long long t_walk0 = 0;
+        if constexpr (kProf) t_walk0 = sc_clock();
         int x = g.cur, len = g.cur_len;
         if (x_state != x) X = load(x);
         else SC_STAT(SC_ST_CARRIED);
@@ -332,6 +335,7 @@ struct ScBuilderT {
             x = nx;
             first = false;
         }
+        if constexpr (kProf) pf[SC_PF_WALK_CYC] += sc_clock() - t_walk0;      // the cursor's walk (with the fused inserts)
         g.hops += n_chain;
         if (n_chain > g.max_chain) g.max_chain = n_chain;
         const int new_cur = on_edge ? pr.target : 0;
@@ -422,6 +426,8 @@ struct ScBuilderT {
                     g.n_edges++;
                     e = se.w;
                 }
+                long long t_red0 = 0;
+                if constexpr (kProf) t_red0 = sc_clock();
                 // redirect p's suffix chain from q to the clone
                 int rp = p, rl = p_link;
                 Probe cp = pp;
@@ -436,6 +442,7 @@ struct ScBuilderT {
                     if (cp.k >= 0) cp.k = rec_inline_index(R, tok);
                     rl = R.w[R_LINK];
                 }
+                if constexpr (kProf) pf[SC_PF_REDIR_CYC] += sc_clock() - t_red0;
                 d.recs[(size_t)q * SAMD_REC + R_LINK] = clone;
                 X.w[R_LINK] = clone;
                 sc_prefetch_rec(d.recs, clone);             // a record that was only written is not in L1 (stores do not allocate)

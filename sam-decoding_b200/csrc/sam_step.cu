@@ -933,6 +933,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
             b.g.hops = m2.x; lookup_probes = m2.y; b.g.last_link = m2.z; b.g.ll_twin = m2.w;
             b.g.ll_len = m3.x; b.g.ll_link = m3.y; b.g.max_chain = m3.z;
         }
+        const long long t_tokens = kProf ? clock64() : 0;
         // ---- phase 1: DraftModel.update (draft.py:65-79) ----
         if (P.tokens) {
             int flags = 0;
@@ -1038,6 +1039,9 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
                 P.dbg_cycles[10 * n + r] = (long long)g_begin;       // ns, comparable across SMs: the step's span
                 P.dbg_cycles[11 * n + r] = (long long)g1;
+                P.dbg_cycles[12 * n + r] = b.pf[SC_PF_WALK_CYC];     // cursor walks (incl. fused inserts), clone redirect walks,
+                P.dbg_cycles[13 * n + r] = b.pf[SC_PF_REDIR_CYC];    // cycles before the first token starts
+                P.dbg_cycles[14 * n + r] = t_tokens - t_begin;
             }
         }
     }

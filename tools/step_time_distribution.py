@@ -8,7 +8,7 @@ dyn=E.DynSamBatch(1024, 8192+8*40+16, dev)
 eng=E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=16, len_bias=5, len_threshold=5)
 eng.step(torch.as_tensor(streams[:, :8192]).to(dev), None, None)
 dt,dc,ds=(torch.as_tensor(x).to(dev) for x in (tokens,counts,start))
-cyc=torch.zeros(10,1024,dtype=torch.int64,device=dev)
+cyc=torch.zeros(16,1024,dtype=torch.int64,device=dev)
 K.lib().samd_step_set_debug_cycles(cyc.data_ptr())
 allc=[]; feats=[]; phases=[]
 import ctypes as C
