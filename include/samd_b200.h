@@ -172,6 +172,13 @@ typedef struct samd_step_args {
 } samd_step_args;
 
 int samd_step(const samd_step_args *args, void *stream);
+/* Staging copy for the host-buffer path, as a kernel launch: dst[0:n_bytes] = src[0:n_bytes] with 16-byte coalesced
+ * accesses.  Either side may be mapped pinned host memory (cudaHostAlloc / torch pin_memory) or device memory; both
+ * pointers 16-byte aligned, n_bytes a multiple of 4.  A caller whose tokens / counts / start tokens live in pinned host
+ * memory stages them with ONE such launch in front of samd_step (the reference has no counterpart: its DraftModel.update
+ * takes Python lists, samd/draft.py:52-58); cheaper than a copy-engine node in the same graph and than letting every
+ * request's CTA read its own few words across PCIe. */
+int samd_stage_copy(void *dst, const void *src, int64_t n_bytes, void *stream);
 /* profiling hook: when non-NULL, every samd_step launch that performs a lookup writes each request's SM
  * cycle counts to cycles_dev[16][n_requests].  Variant 0: whole request, cursor transfers, appends, lookup + draft, then
  * inside the appends: chain look-ups, edge inserts, (unused), target record, clone overflow copy, clone redirect walk.

@@ -197,7 +197,7 @@ struct ScCounters {            // profiling build: per-request trace of the reco
 #define SC_STAT(x) ((void)0)
 #endif
 enum { SC_ST_ALIGNED = 0, SC_ST_TWIN = 1, SC_ST_GENERIC = 2, SC_ST_LONGCHAIN = 3, SC_ST_OVF_INSERT = 4, SC_ST_OVF_CLONE = 5,
-       SC_ST_CARRIED = 6, SC_ST_N = 8 };
+       SC_ST_CARRIED = 6, SC_ST_REDIR = 7, SC_ST_N = 8 };
 
 // cycle counter + a consumer of a load's result, for the profiling build (the clock is read after the data arrived)
 SAMD_HD long long sc_clock() {
@@ -439,6 +439,7 @@ struct ScBuilderT {
                     const Rec R = load(rp);
                     cp = probe(R, rp, tok);
                     if (!(cp.found && cp.target == q)) break;
+                    SC_STAT(SC_ST_REDIR);
                     if (cp.k >= 0) cp.k = rec_inline_index(R, tok);
                     rl = R.w[R_LINK];
                 }

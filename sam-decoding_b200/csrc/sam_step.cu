@@ -1098,6 +1098,34 @@ extern "C" void samd_step_set_trace(int32_t *trace_dev, int cap) {
 }
 extern "C" void samd_step_set_debug_cycles(int64_t *cycles_dev) { g_dbg_cycles = (long long *)cycles_dev; }
 
+// The host-buffer path's staging copy as a KERNEL: 16-byte coalesced loads turn into a few hundred full-size PCIe read
+// requests when `src` is mapped pinned host memory, where the step kernel's own per-request reads (a 4-byte count, a
+// 32-byte token row and a start token per CTA, repeated by its scouts) are thousands of small non-posted reads.  A
+// copy-engine memcpy node in the same graph costs ~10 us more per step than this launch.
+__global__ void __launch_bounds__(256) stage_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, long long n16,
+                                                         int32_t *__restrict__ dst_w, const int32_t *__restrict__ src_w, int n_tail) {
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = i0; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+    if (i0 < n_tail) dst_w[i0] = src_w[i0];
+}
+
+extern "C" int samd_stage_copy(void *dst, const void *src, int64_t n_bytes, void *stream) {
+    SAMD_REQUIRE(dst && src && n_bytes >= 0, "samd_stage_copy: bad arguments");
+    SAMD_REQUIRE(((uintptr_t)dst & 15) == 0 && ((uintptr_t)src & 15) == 0 && (n_bytes & 3) == 0,
+                 "samd_stage_copy: pointers must be 16-byte aligned and the size a multiple of 4");
+    if (n_bytes == 0) return 0;
+    const long long n16 = n_bytes >> 4;
+    const int n_tail = (int)((n_bytes & 15) >> 2);
+    long long blocks = (n16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 592) blocks = 592;
+    stage_copy_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((uint4 *)dst, (const uint4 *)src, n16, (int32_t *)dst + 4 * n16,
+                                                                    (const int32_t *)src + 4 * n16, n_tail);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int samd_step(const samd_step_args *a, void *stream) {
     SAMD_REQUIRE(a && a->dyn, "samd_step: dyn handle required");
     SAMD_REQUIRE((a->stat == nullptr) == (a->static_cursor_dev == nullptr),

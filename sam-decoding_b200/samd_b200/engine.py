@@ -361,15 +361,22 @@ class DraftEngine:
         self._io = (dev_in, k)
         return inp, out
 
-    def step_host(self, inp: torch.Tensor, out: torch.Tensor, sync: bool = True, zero_copy: bool = True):
-        """DraftModel.update + lookup with HOST inputs / outputs (pinned buffers from host_buffers()).
-        Default (zero_copy): the kernel reads `inp` and writes `out` directly over PCIe (pinned memory is mapped
-        into the device address space) - no copy-engine operations at all.  zero_copy=False stages through device
-        buffers: one H2D copy, the kernel, one D2H copy.  Either way the work is captured once per (inp, out) pair
-        and replayed as one graph launch.  Measured on B200 at 1024 requests, host to host: 45.9 us per step
-        zero-copy, 53.4 zero-copy in + copy out, 65.6 with both copies.  By default waits until `out` is complete."""
+    HOST_MODE = "stage_in"      # measured best on B200 at 1024 requests (35.8 us host to host; zero_copy 39.8, stage_both 38.6, copy_engine 49.7)
+
+    def step_host(self, inp: torch.Tensor, out: torch.Tensor, sync: bool = True, zero_copy: bool = True, mode: Optional[str] = None):
+        """DraftModel.update + lookup with HOST inputs / outputs (pinned buffers from host_buffers()).  `mode`:
+        "zero_copy"   the step kernel reads `inp` and writes `out` directly over PCIe (pinned memory is mapped into the
+                      device address space) - one launch, no copies;
+        "stage_in"    one staging-copy KERNEL (samd_stage_copy: 16-byte coalesced reads of `inp` into a device block),
+                      then the step kernel on device inputs, writing `out` directly;
+        "stage_both"  the same, and the outputs go to the device block first and leave through a second copy kernel;
+        "copy_engine" H2D memcpy, the kernel, D2H memcpy (zero_copy=False selects this).
+        Either way the work is captured once per (inp, out) pair and replayed as one graph launch.  By default waits
+        until `out` is complete.  Measured host to host at 1024 requests: see DESIGN.md section 5."""
+        if mode is None:
+            mode = self.HOST_MODE if zero_copy else "copy_engine"
         # same buffers and settings as the last call: replay at once (the check below costs a few microseconds)
-        quick = (self.n_predicts, self.len_bias, self.len_threshold, self.alpha, zero_copy)
+        quick = (self.n_predicts, self.len_bias, self.len_threshold, self.alpha, mode)
         last = self.__dict__.get("_host_quick")
         if last is not None and inp is last[0] and out is last[1] and quick == last[2]:
             self._host_graph.replay()
@@ -378,20 +385,32 @@ class DraftEngine:
             return
         if not (inp.is_pinned() and out.is_pinned()):
             raise K.SamdError("step_host needs pinned host buffers (DraftEngine.host_buffers())")
+        if mode not in ("zero_copy", "stage_in", "stage_both", "copy_engine"):
+            raise K.SamdError(f"step_host: unknown mode {mode!r}")
         dev_in, k = self._io
         B = self.dyn.n_requests
         key = (inp.data_ptr(), out.data_ptr(), self.dyn.handle.value, self.flavour, self.n_predicts, self.len_bias,
-               self.len_threshold, self.alpha, bool(zero_copy))
+               self.len_threshold, self.alpha, mode)
         if getattr(self, "_host_graph_key", None) != key:
+            def stage(dst, src):
+                K.check(K.lib().samd_stage_copy(dst.data_ptr(), src.data_ptr(), dst.numel() * 4, K.stream_ptr()), "samd_stage_copy")
+
             def work():
-                if zero_copy:
+                if mode == "zero_copy":
                     self.step(inp[2 * B:].view(B, k), inp[:B], inp[B:2 * B], out_buf=out)
-                else:
+                elif mode == "copy_engine":
                     dev_in.copy_(inp, non_blocking=True)
                     self.step(dev_in[2 * B:].view(B, k), dev_in[:B], dev_in[B:2 * B])
                     out.copy_(self.out_buf, non_blocking=True)
+                else:
+                    stage(dev_in, inp)
+                    if mode == "stage_in":
+                        self.step(dev_in[2 * B:].view(B, k), dev_in[:B], dev_in[B:2 * B], out_buf=out)
+                    else:
+                        self.step(dev_in[2 * B:].view(B, k), dev_in[:B], dev_in[B:2 * B])
+                        stage(out, self.out_buf)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.device(self.dyn.device), torch.cuda.graph(g):
                 work()
             self._host_graph, self._host_graph_key = g, key
         self._host_quick = (inp, out, quick)

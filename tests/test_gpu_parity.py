@@ -620,10 +620,10 @@ def test_verify_random_shapes(B, T, V, P, D, dt):
 
 
 # --------------------------------------------------------------------------------------
-@pytest.mark.parametrize("zero_copy", [True, False])
-def test_step_host_matches_device_step(zero_copy):
-    """The host-buffer entry (DraftEngine.step_host: pinned buffers, graph-replayed, zero-copy or staged through
-    device copies) produces exactly what the device-buffer step produces, step after step."""
+@pytest.mark.parametrize("mode", ["zero_copy", "stage_in", "stage_both", "copy_engine"])
+def test_step_host_matches_device_step(mode):
+    """The host-buffer entry (DraftEngine.step_host: pinned buffers, graph-replayed; zero-copy, staged by copy kernels or
+    by the copy engine) produces exactly what the device-buffer step produces, step after step."""
     E, K = _engine_mod()
     from samd_b200 import synth
     B, N, steps = 48, 512, 12
@@ -651,7 +651,7 @@ def test_step_host_matches_device_step(zero_copy):
         inp[:B] = torch.as_tensor(cnt)
         inp[B:2 * B] = torch.as_tensor(start)
         inp[2 * B:] = torch.as_tensor(tok).reshape(-1)
-        host_eng.step_host(inp, res, zero_copy=zero_copy)
+        host_eng.step_host(inp, res, mode=mode)
         want = dev_eng.out_buf.cpu().numpy()
         got = res.numpy()
         # type, match lengths, state indices, draft length: exact; draft tokens: up to draft_len

@@ -7,7 +7,7 @@ import torch
 import bench
 from samd_b200 import _cabi as K, engine as E
 dev = torch.device("cuda")
-R, N, S, W = 1024, 8192, 128, 16
+R, N, S, W = 1024, 8192, (int(sys.argv[2]) if len(sys.argv) > 2 else 128), 16
 streams, counts, tokens, start = bench.make_workload(R, N, S + W, 2000)
 dyn = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
 snap = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
@@ -31,6 +31,22 @@ t0 = time.perf_counter()
 for s in range(W, W + S):
     inp.copy_(staged[s]); eng.step_host(inp, res)
 t_e2e = (time.perf_counter() - t0) / S * 1e6
+for mode in ("zero_copy", "stage_in", "stage_both", "copy_engine"):
+    best, reps = 1e9, []
+    for rep in range(3):
+        dyn.copy_from(snap); torch.cuda.synchronize()
+        for s in range(W):
+            inp.copy_(staged[s]); eng.step_host(inp, res, mode=mode)
+        dyn.copy_from(snap); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(W, W + S):
+            inp.copy_(staged[s]); eng.step_host(inp, res, mode=mode)
+        reps.append((time.perf_counter() - t0) / S * 1e6)
+        best = min(best, reps[-1])
+    print(f"host to host, mode {mode}: {best:.1f} us/step (best of 3 x {S} steps: {' '.join('%.1f' % x for x in reps)}), draft checksum {int(res[6 * R:].sum())}")
+if "modes" in sys.argv[1:]:
+    sys.exit(0)
+eng.step_host(inp, res, mode="zero_copy")
 # (2) device-side duration of the same zero-copy launches (events, no host wait in between)
 dyn.copy_from(snap); torch.cuda.synchronize()
 ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(S)]
