@@ -184,7 +184,7 @@ int samd_stage_copy(void *dst, const void *src, int64_t n_bytes, void *stream);
  * inside the appends: chain look-ups, edge inserts, (unused), target record, clone overflow copy, clone redirect walk.
  * Variant 1: whole request, cycles waiting for record loads, update phase, lookup phase, number of record loads that took
  * < 120 / < 500 / < 1100 / more cycles, overflow-probe cycles and count, then %globaltimer (ns) at the builder's start and
- * end (rows 10, 11), cycles in the cursor walks, in the clones' redirect walks and before the first token (rows 12-14). */
+ * end (rows 10, 11), cycles in the cursor walks, in the clones' redirect walks and before the first token (rows 12-14), records read by the redirect walks (row 15). */
 void samd_step_set_debug_cycles(int64_t *cycles_dev);
 /* tuning hook: scout (prefetcher) warps of samd_step - 0 none, 1 the cursor scouts, 2 (default) also the redirect scout */
 void samd_step_set_scouts(int on);

@@ -217,7 +217,7 @@ SAMD_HD void sc_consume(int a, int b) {
 #endif
 }
 enum { SC_PF_LOAD_CYC = 0, SC_PF_L1 = 1, SC_PF_L2 = 2, SC_PF_DRAM = 3, SC_PF_SLOW = 4, SC_PF_OVF_CYC = 5, SC_PF_OVF_N = 6, SC_PF_WALK_CYC = 7,
-       SC_PF_REDIR_CYC = 8, SC_PF_N = 10 };
+       SC_PF_REDIR_CYC = 8, SC_PF_REDIR_N = 9, SC_PF_N = 10 };
 
 template <bool kProf>
 struct ScBuilderT {
@@ -437,6 +437,7 @@ struct ScBuilderT {
                     rp = rl;
                     if (rp == -1) break;
                     const Rec R = load(rp);
+                    if constexpr (kProf) pf[SC_PF_REDIR_N] += 1;
                     cp = probe(R, rp, tok);
                     if (!(cp.found && cp.target == q)) break;
                     SC_STAT(SC_ST_REDIR);

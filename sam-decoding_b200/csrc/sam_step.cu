@@ -1042,6 +1042,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
                 P.dbg_cycles[12 * n + r] = b.pf[SC_PF_WALK_CYC];     // cursor walks (incl. fused inserts), clone redirect walks,
                 P.dbg_cycles[13 * n + r] = b.pf[SC_PF_REDIR_CYC];    // cycles before the first token starts
                 P.dbg_cycles[14 * n + r] = t_tokens - t_begin;
+                P.dbg_cycles[15 * n + r] = b.pf[SC_PF_REDIR_N];      // records read by the redirect walks
             }
         }
     }

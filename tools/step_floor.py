@@ -109,7 +109,7 @@ def breakdown(a, name, sel=None):
     print(f"  {name}: total {tot / clk:5.2f} us = update {up / clk:5.2f} + lookup/draft {lk / clk:5.2f}; waiting for record loads {ld / clk:5.2f} us "
           f"({sum(c):.1f} loads: {c[0]:.1f} <120 cyc, {c[1]:.1f} <500, {c[2]:.1f} <1100, {c[3]:.1f} slower; mean {ld / max(sum(c), 1e-9):.0f} cyc); "
           f"overflow probes {f(a[:, 8]) / clk:5.2f} us ({f(a[:, 9]):.1f}); before the first token {f(a[:, 14]) / clk:5.2f}, cursor walks "
-          f"{f(a[:, 12]) / clk:5.2f}, redirect walks {f(a[:, 13]) / clk:5.2f}, rest of the appends {(up - f(a[:, 14]) - f(a[:, 12]) - f(a[:, 13])) / clk:5.2f} us")
+          f"{f(a[:, 12]) / clk:5.2f}, redirect walks {f(a[:, 13]) / clk:5.2f} ({f(a[:, 15]):.1f} records read), rest of the appends {(up - f(a[:, 14]) - f(a[:, 12]) - f(a[:, 13])) / clk:5.2f} us")
 
 
 slow = per1 > np.percentile(per1, 99.5)
