@@ -378,6 +378,12 @@ int samd_kv_compact(void *const *kv_ptrs_dev, int32_t n_kv, int32_t n_heads, int
 /* profiling aid: n_warps warps each chase `hops` dependent pointers through n_records 64-byte records
  * (record word 0 = next index); measures dependent-load latency at the step kernel's concurrency */
 int samd_debug_pointer_chase(const void *recs_dev, int64_t n_records, int n_warps, int hops, int32_t *sink_dev, void *stream);
+/* profiling aid: the ceiling of scattered row moves - n_granules copies of granule_bytes (a multiple of 16) each,
+ * base + src_off[g] -> base + dst_off[g] (byte offsets, 16-byte aligned), four independent 16-byte units in flight per
+ * lane over n_blocks x 256 threads; what samd_verify_compact's KV compaction (one 256-byte granule per tensor, head
+ * and accepted row) can reach at best.  tools/row_move_ceiling.py */
+int samd_debug_granule_copy(void *base_dev, const int64_t *src_off_dev, const int64_t *dst_off_dev, int64_t n_granules,
+                            int32_t granule_bytes, int32_t n_blocks, void *stream);
 /* profiling aid: the floor of samd_step's dependent-load chain.  One thread per request of `h` reads the records listed
  * in trace_dev (layout of samd_step_set_trace) one after the other, every address depending on the previous load's
  * value; with_scout != 0 adds a second thread per request that runs ahead through the same list with independent

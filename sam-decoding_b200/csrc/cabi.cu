@@ -51,3 +51,43 @@ extern "C" int samd_debug_pointer_chase(const void *recs_dev, int64_t n_records,
     SAMD_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Microbenchmark (profiling aid): the ceiling of scattered row moves.  n_granules copies of granule_bytes each,
+// base + src_off[g] -> base + dst_off[g], flattened into 16-byte units over the whole grid, four independent units in
+// flight per lane - nothing else in the kernel.  tools/row_move_ceiling.py sweeps the granule size at a fixed number
+// of bytes: what c4's KV compaction (256-byte granules, one per (tensor, head, row)) can reach at best.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) granule_copy_kernel(char *base, const long long *__restrict__ src_off,
+                                                           const long long *__restrict__ dst_off, long long n_granules, int cols) {
+    const long long total = n_granules * cols;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; u + 3 * stride < total; u += 4 * stride) {
+        uint4 v[4];
+        long long d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long w = u + i * stride, g = w / cols, c = w - g * cols;
+            v[i] = *reinterpret_cast<const uint4 *>(base + src_off[g] + (c << 4));
+            d[i] = dst_off[g] + (c << 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4 *>(base + d[i]) = v[i];
+    }
+    for (; u < total; u += stride) {
+        const long long g = u / cols, c = u - g * cols;
+        *reinterpret_cast<uint4 *>(base + dst_off[g] + (c << 4)) = *reinterpret_cast<const uint4 *>(base + src_off[g] + (c << 4));
+    }
+}
+
+extern "C" int samd_debug_granule_copy(void *base_dev, const int64_t *src_off_dev, const int64_t *dst_off_dev, int64_t n_granules,
+                                       int32_t granule_bytes, int32_t n_blocks, void *stream) {
+    SAMD_REQUIRE(base_dev && src_off_dev && dst_off_dev && n_granules > 0 && granule_bytes >= 16 && granule_bytes % 16 == 0 && n_blocks > 0,
+                 "samd_debug_granule_copy: bad arguments");
+    granule_copy_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>((char *)base_dev, (const long long *)src_off_dev,
+                                                                   (const long long *)dst_off_dev, (long long)n_granules, granule_bytes >> 4);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -117,6 +117,7 @@ SAMD_HD bool ovf_find(const uint4 *slots, uint32_t bmask, uint32_t state, uint32
                       int max_slots = 0) {
     const uint32_t smask = (bmask + 1u) * SAMD_BUCKET - 1u;
     uint32_t i = (samd_hash(state, tok) & bmask) * SAMD_BUCKET;
+#pragma unroll 1
     for (int n = 0; max_slots == 0 || n < max_slots; ++n) {
         const uint4 s = slot_load<kRO>(slots, i);
         if (s.x == state && s.y == tok) {
