@@ -556,6 +556,10 @@ def run_ours(a):
         except Exception as e:
             out["c2_concurrent"] = {"error": repr(e)}
         try:
+            out["c2_sam_only"] = bench_c2_sam_only(a, dev, (streams, counts, tokens, start))
+        except Exception as e:
+            out["c2_sam_only"] = {"error": repr(e)}
+        try:
             out["c1"] = bench_c1(a, dev)
         except Exception as e:
             out["c1"] = {"error": repr(e)}
@@ -623,6 +627,9 @@ def run_ours(a):
     v = out.get("c1")
     if isinstance(v, dict) and "gpu_us_per_step" in v:
         others["c1"] = {k: v[k] for k in v if k != "workload"}
+    v = out.get("c2_sam_only")
+    if isinstance(v, dict) and "queries_per_s" in v:
+        others["c2_sam_only"] = {k: v[k] for k in v if k != "workload"}
     v = out.get("sam_only_tree")
     if isinstance(v, dict) and "trees_per_s" in v:
         others["sam_only_static_tree"] = {k: v[k] for k in v if k != "workload"}
@@ -756,6 +763,40 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5, vocab=None, heads=32, kv_le
             "token_recycle": {"us_per_step_with_top8_table_update": float(np.median(t_rec)) * 1e3,
                               "us_torch_topk_separate_pass": us_torch_topk,
                               "note": "top-8 of all B*T rows + table[token] update fused into the verify launch"}}
+
+
+def bench_c2_sam_only(a, dev, workload):
+    """c2 in the samd_sam_only flavour (max_predicts = 40, alpha = 4): same streams and steps as the headline,
+    the draft is the unpadded continuation of up to 40 tokens (samd_sam_only/sam/dyn_sam.py gen_draft)."""
+    import torch
+    from samd_b200 import _cabi as K, engine as E
+    streams, counts, tokens, start = workload
+    R, N, S, W = a.requests, a.prompt, a.steps, a.warmup
+    d_tokens, d_counts, d_start = (torch.as_tensor(x).to(dev) for x in (tokens, counts, start))
+    dyn = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
+    eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAM_ONLY, n_predicts=40, len_bias=LEN_BIAS, len_threshold=LEN_THRESHOLD, alpha=4.0)
+    eng.step(torch.as_tensor(streams[:, :N]).to(dev), None, None)
+    for s in range(W):
+        eng.step(d_tokens[s], d_counts[s], d_start[s])
+    torch.cuda.synchronize()
+    snap = E.DynSamBatch(R, dyn.max_tokens, dev)
+    snap.copy_from(dyn)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for s in range(W, W + S):
+            eng.step(d_tokens[s], d_counts[s], d_start[s])
+    g.replay()
+    dyn.copy_from(snap)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"workload": f"c2, samd_sam_only flavour: {R} requests x {N}-token prompts, max_predicts 40, alpha 4",
+            "queries_per_s": R * S / (ms * 1e-3), "us_per_step": ms / S * 1e3,
+            "mean_draft_len": float(eng.draft_len.float().mean().item())}
 
 
 def bench_c2_concurrent(a, dev, workload, n_streams=4):

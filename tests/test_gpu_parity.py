@@ -935,3 +935,21 @@ def test_static_l2_window_does_not_change_results():
     st.set_l2_window(0)
     again = run()
     assert torch.equal(base, pinned) and torch.equal(base, again)
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_words", [1, 3, 4, 5, 4096, 10240, 10243, 1 << 20])
+def test_stage_copy_kernel(n_words):
+    """samd_stage_copy (the host-buffer path's staging kernel): pinned host -> device and device -> pinned host, sizes
+    with and without a 16-byte tail; unaligned pointers and sizes that are not a multiple of 4 are refused."""
+    E, K = _engine_mod()
+    src = torch.arange(n_words, dtype=torch.int32).mul_(2654435761 % 65521).pin_memory()
+    dst = torch.zeros(n_words + 8, dtype=torch.int32, device="cuda")
+    K.check(K.lib().samd_stage_copy(dst.data_ptr(), src.data_ptr(), n_words * 4, K.stream_ptr()))
+    back = torch.zeros(n_words, dtype=torch.int32).pin_memory()
+    K.check(K.lib().samd_stage_copy(back.data_ptr(), dst.data_ptr(), n_words * 4, K.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:n_words].cpu(), src) and int(dst[n_words:].abs().sum()) == 0
+    assert torch.equal(back, src)
+    assert K.lib().samd_stage_copy(dst.data_ptr() + 4, src.data_ptr(), 16, K.stream_ptr()) != 0
+    assert K.lib().samd_stage_copy(dst.data_ptr(), src.data_ptr(), 6, K.stream_ptr()) != 0
