@@ -387,8 +387,12 @@ class DraftEngine:
             raise K.SamdError("step_host needs pinned host buffers (DraftEngine.host_buffers())")
         if mode not in ("zero_copy", "stage_in", "stage_both", "copy_engine"):
             raise K.SamdError(f"step_host: unknown mode {mode!r}")
+        if not hasattr(self, "_io"):
+            raise K.SamdError("step_host before host_buffers()")
         dev_in, k = self._io
         B = self.dyn.n_requests
+        if inp.numel() != dev_in.numel() or out.numel() != self.out_buf.numel():
+            raise K.SamdError("step_host: buffers do not have the layout of host_buffers()")
         key = (inp.data_ptr(), out.data_ptr(), self.dyn.handle.value, self.flavour, self.n_predicts, self.len_bias,
                self.len_threshold, self.alpha, mode)
         if getattr(self, "_host_graph_key", None) != key:
