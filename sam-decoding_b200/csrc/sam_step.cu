@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(128) sam_step_kernel(StepParams P) {
     if (threadIdx.x < 2) s_mailbox[4 * SCOUT_MAX_TOKENS + threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x >= 32) {
-        const int k = P.tokens ? (P.counts ? P.counts[r] : P.token_stride) : 0;
+        const int k = P.tokens ? (P.counts ? samd_clamp_count(P.counts[r], P.token_stride) : P.token_stride) : 0;
         const int32_t *tk = P.tokens ? P.tokens + (size_t)r * P.token_stride : nullptr;
         const int peek = P.start_tok ? P.start_tok[r] : -1;
         if (threadIdx.x < 64) {
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(128) sam_step_kernel(StepParams P) {
 
     // ---- phase 1: DraftModel.update (draft.py:65-79) ------------------------------------
     if (P.tokens) {
-        const int k = P.counts ? P.counts[r] : P.token_stride;
+        const int k = P.counts ? samd_clamp_count(P.counts[r], P.token_stride) : P.token_stride;
         const int32_t *tk = P.tokens + (size_t)r * P.token_stride;
         bool overflow = false;
         prefetch_rec(recs, g.cur, lane);
@@ -845,7 +845,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
     int32_t *text = P.dyn.text + (size_t)r * P.dyn.t_cap;
     int32_t *meta = P.dyn.meta + (size_t)r * META_WORDS;
     if (threadIdx.x >= 32) {
-        const int k = P.tokens ? (P.counts ? P.counts[r] : P.token_stride) : 0;
+        const int k = P.tokens ? (P.counts ? samd_clamp_count(P.counts[r], P.token_stride) : P.token_stride) : 0;
         const int32_t *tk = P.tokens ? P.tokens + (size_t)r * P.token_stride : nullptr;
         if (lane != 0) {
             // Idle lanes of the third warp, one per token of the step: short-context scouts.  A cursor walk that falls
@@ -921,7 +921,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
             const int4 m2 = *reinterpret_cast<const int4 *>(meta + 8), m3 = *reinterpret_cast<const int4 *>(meta + 12);
             if (tk) {
                 next_tok = tk[0];
-                k = P.counts ? P.counts[r] : P.token_stride;
+                k = P.counts ? samd_clamp_count(P.counts[r], P.token_stride) : P.token_stride;
             }
             if (P.start_tok) start_tok = P.start_tok[r];
             if (P.has_static) {
@@ -1393,7 +1393,7 @@ __global__ void __launch_bounds__(32) static_walk_kernel(StaticDev st, int32_t *
     if (r >= n) return;
     int idx = cursor[2 * r], len = cursor[2 * r + 1];
     if (tokens) {
-        cursor_walk<true>(st.recs, st.slots, st.bmask, idx, len, tokens + (size_t)r * stride, counts ? counts[r] : stride, lane);
+        cursor_walk<true>(st.recs, st.slots, st.bmask, idx, len, tokens + (size_t)r * stride, counts ? samd_clamp_count(counts[r], stride) : stride, lane);
         if (lane == 0) {
             cursor[2 * r] = idx;
             cursor[2 * r + 1] = len;
@@ -1427,7 +1427,7 @@ __global__ void __launch_bounds__(32) dyn_walk_kernel(DynArena a, const int32_t 
     int32_t *meta = a.meta + (size_t)r * META_WORDS;
     int idx = meta[META_CUR], len = meta[META_CURLEN];
     cursor_walk<false>(a.recs + (size_t)r * a.s_cap * SAMD_REC, a.slots + (size_t)r * a.h_cap, a.bmask, idx, len,
-                       tokens + (size_t)r * stride, counts ? counts[r] : stride, lane);
+                       tokens + (size_t)r * stride, counts ? samd_clamp_count(counts[r], stride) : stride, lane);
     if (lane == 0) {
         meta[META_CUR] = idx;
         meta[META_CURLEN] = len;

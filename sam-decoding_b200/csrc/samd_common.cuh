@@ -144,6 +144,9 @@ struct Look {
 
 __device__ __forceinline__ int rec_word(const Look &r, int which) { return __shfl_sync(SAMD_FULL, r.w, which); }
 
+// a request's token count as the kernels use it: never negative, never beyond its row of the token block
+__device__ __forceinline__ int samd_clamp_count(int c, int stride) { return min(max(c, 0), stride); }
+
 // search the overflow table for (state, tok): found -> slot/target; else slot = first free slot
 __device__ __forceinline__ void ovf_probe(const uint4 *slots, uint32_t bmask, uint32_t state, uint32_t tok, int lane,
                                           bool ro, Look &r) {

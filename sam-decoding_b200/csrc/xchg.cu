@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32) xchg_lookup_kernel(StaticDev st, int32_t *
     int idx = cursor[2 * r], len = cursor[2 * r + 1];
     int hops = 0;
     if (tokens) {                                                          // StaticSAM.transfer_tokens first (static_sam.py:102-104)
-        const int k = counts ? counts[r] : stride;
+        const int k = counts ? samd_clamp_count(counts[r], stride) : stride;
         const int32_t *tk = tokens + (size_t)r * stride;
         for (int i = 0; i < k; i += 32) {
             const int mine = (i + lane < k) ? tk[i + lane] : 0;

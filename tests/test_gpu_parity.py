@@ -953,3 +953,33 @@ def test_stage_copy_kernel(n_words):
     assert torch.equal(back, src)
     assert K.lib().samd_stage_copy(dst.data_ptr() + 4, src.data_ptr(), 16, K.stream_ptr()) != 0
     assert K.lib().samd_stage_copy(dst.data_ptr(), src.data_ptr(), 6, K.stream_ptr()) != 0
+
+
+# --------------------------------------------------------------------------------------
+def test_counts_outside_the_token_row_are_clamped():
+    """A per-request count below 0 or beyond the row of the token block is used as 0 / as the row length: the kernel never
+    reads another request's tokens or past the block (both step kernel variants)."""
+    E, K = _engine_mod()
+    from samd_b200 import synth
+    B, N = 6, 300
+    streams = [synth.copy_mix(N + 64, 400, 8100 + r) for r in range(B)]
+    for variant in (1, 0):
+        K.lib().samd_step_set_variant(variant)
+        try:
+            engs = []
+            for _ in range(2):
+                dyn = E.DynSamBatch(B, N + 64)
+                eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=16, len_bias=5, len_threshold=5)
+                eng.step(_dev_i32(np.stack([s[:N] for s in streams])), None, None)
+                engs.append(eng)
+            tok = _dev_i32(np.stack([s[N:N + 8] for s in streams]))
+            start = _dev_i32(np.array([s[N + 8] for s in streams]))
+            wild = _dev_i32(np.array([100, -3, 8, 0, 1 << 30, -(1 << 31)], dtype=np.int64).astype(np.int32))
+            tame = _dev_i32(np.array([8, 0, 8, 0, 8, 0]))
+            engs[0].step(tok, wild, start)
+            engs[1].step(tok, tame, start)
+            torch.cuda.synchronize()
+            assert torch.equal(engs[0].out_buf, engs[1].out_buf)
+            assert np.array_equal(engs[0].dyn.meta()[:, :8], engs[1].dyn.meta()[:, :8])
+        finally:
+            K.lib().samd_step_set_variant(1)
