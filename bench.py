@@ -447,7 +447,8 @@ def run_ours(a):
         eng.step_host(inp, res)
     dyn.copy_from(snap)
     torch.cuda.synchronize()
-    staged = [h_in[s] for s in range(W + S)]     # (row views made outside the timed loop; the copies are inside)
+    inp_np, h_np = inp.numpy(), h_in.numpy()
+    staged = [h_np[s] for s in range(W + S)]     # (row views made outside the timed loop; the copies are inside)
     # The pre-generated input rows are read once so that the per-step staging copy finds them in the CPU cache, as a
     # caller's freshly produced tokens would be (cold rows cost 4 us per step more: a property of pre-generating 11 MB
     # of inputs, not of the path).
@@ -456,7 +457,7 @@ def run_ours(a):
     ev0.record()
     diag_ts = [] if os.environ.get("SAMD_BENCH_E2E_DIAG") else None
     for s in range(W, W + S):
-        inp.copy_(staged[s])                 # the caller's host-side staging of this step's inputs
+        np.copyto(inp_np, staged[s])         # the caller's host-side staging of this step's inputs (40 KB into the pinned buffer)
         eng.step_host(inp, res)
         if diag_ts is not None:
             diag_ts.append(time.perf_counter())
@@ -475,7 +476,7 @@ def run_ours(a):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for s in range(W, W + S):
-                inp.copy_(staged[s])
+                np.copyto(inp_np, staged[s])
                 eng.step_host(inp, res)
             print("e2e diag rep", rep, (time.perf_counter() - t0) / S * 1e6, "us/step; first pass", e2e_wall / S * 1e6, e2e_ms / S * 1e3, file=sys.stderr)
     h2d = inp.numel() * 4
