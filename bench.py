@@ -102,6 +102,14 @@ def make_workload(n_requests, prompt, n_steps, seed0, procs=None):
     return streams, counts, tokens, start
 
 
+def _gate():
+    """A short spin kernel (about 50 us) in front of a device-timed region: the stream stays busy while the host enqueues the
+    start event and the graph launch, so the start event's timestamp is taken when the work is ready to run - device
+    time, not the host's cudaGraphLaunch latency (which a 20-step run would otherwise carry as 1.2 us per step)."""
+    import torch
+    torch.cuda._sleep(int(os.environ.get("SAMD_BENCH_GATE_CYCLES", "100000")))
+
+
 # --------------------------------------------------------------------------------------
 # clocks sampler (B200_PROFILING.md recipe)
 # --------------------------------------------------------------------------------------
@@ -381,28 +389,37 @@ def run_ours(a):
     def step(s):
         eng.step(d_tokens[s], d_counts[s], d_start[s])
 
-    for s in range(W):                       # warm-up steps 0..W-1, eager
-        step(s)
-    torch.cuda.synchronize()
+    # The arenas as the prefill left them: every measured pass below starts from this snapshot and runs its W warm-up
+    # steps (real steps 0..W-1) right before its K timed ones (steps W..W+K-1), so that the timed region never follows
+    # the 2.8 GB restore copy directly (that copy leaves the TLBs and the L2 cold: +40 us on a first device step, +80-120 us
+    # on a first host-path step - an artefact that a short run (K = 20) would mostly measure).
     snap.copy_from(dyn)
-    stats0 = dyn.stats()
-    # the K timed steps as one CUDA graph; dry replay (untimed), restore the arenas, then time
+    torch.cuda.synchronize()
+
+    def warm():
+        dyn.copy_from(snap)
+        for s in range(W):                   # warm-up steps 0..W-1, eager
+            step(s)
+        torch.cuda.synchronize()
+
+    # the K timed steps as one CUDA graph; one dry replay (untimed) instantiates and uploads it
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for s in range(W, W + S):
             step(s)
     g.replay()
     torch.cuda.synchronize()
-    dyn.copy_from(snap)
-    torch.cuda.synchronize()
 
     clocks = Clocks(local)
     clocks.start()
     time.sleep(0.3)
+    warm()
+    stats0 = dyn.stats()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     wall0 = time.time()
+    _gate()
     ev0.record()
     g.replay()
     ev1.record()
@@ -416,8 +433,7 @@ def run_ours(a):
     draft_checksum = int(eng.draft.sum().item())
 
     # per-launch duration of the step kernel, measured live with CUDA events (eager launches)
-    dyn.copy_from(snap)
-    torch.cuda.synchronize()
+    warm()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(S)]
     for i, s in enumerate(range(W, W + S)):
         evs[i][0].record()
@@ -433,26 +449,24 @@ def run_ours(a):
     # host memory; then the stream is synchronised.  Measured host to host: 35.8 us this way, 39.8 fully zero-copy,
     # 38.6 with a copy kernel on both sides, 49.7 with copy-engine memcpys.  h2d / d2h bytes are the sizes of those two
     # host buffers.
-    dyn.copy_from(snap)
     inp, res = eng.host_buffers(8)
     h_in = torch.empty(W + S, inp.numel(), dtype=torch.int32).pin_memory()
     h_in[:, :R] = torch.as_tensor(counts)
     h_in[:, R:2 * R] = torch.as_tensor(start)
     h_in[:, 2 * R:] = torch.as_tensor(tokens).reshape(W + S, R * 8)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    for s in range(W, W + min(W, S)):        # W untimed warm-up steps of the host path itself, then the arenas are restored
-        inp.copy_(h_in[s])
-        eng.step_host(inp, res)
-    dyn.copy_from(snap)
-    torch.cuda.synchronize()
     inp_np, h_np = inp.numpy(), h_in.numpy()
     staged = [h_np[s] for s in range(W + S)]     # (row views made outside the timed loop; the copies are inside)
     # The pre-generated input rows are read once so that the per-step staging copy finds them in the CPU cache, as a
     # caller's freshly produced tokens would be (cold rows cost 4 us per step more: a property of pre-generating 11 MB
     # of inputs, not of the path).
     h_in_checksum = int(h_in.sum())
+    dyn.copy_from(snap)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for s in range(W):                       # the W warm-up steps (0..W-1) through the host path itself
+        np.copyto(inp_np, staged[s])
+        eng.step_host(inp, res)
     e2e_t0 = time.perf_counter()
     ev0.record()
     diag_ts = [] if os.environ.get("SAMD_BENCH_E2E_DIAG") else None
@@ -474,6 +488,9 @@ def run_ours(a):
         for rep in range(3):
             dyn.copy_from(snap)
             torch.cuda.synchronize()
+            for s in range(W):
+                np.copyto(inp_np, staged[s])
+                eng.step_host(inp, res)
             t0 = time.perf_counter()
             for s in range(W, W + S):
                 np.copyto(inp_np, staged[s])
@@ -692,6 +709,7 @@ def bench_verify(a, dev, hbm_peak, iters=40, warm=5, vocab=None, heads=32, kv_le
             cache_len.copy_(cache0)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            _gate()
             e0.record()
             g.replay()
             e1.record()
@@ -777,8 +795,6 @@ def bench_c2_sam_only(a, dev, workload):
     dyn = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
     eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAM_ONLY, n_predicts=40, len_bias=LEN_BIAS, len_threshold=LEN_THRESHOLD, alpha=4.0)
     eng.step(torch.as_tensor(streams[:, :N]).to(dev), None, None)
-    for s in range(W):
-        eng.step(d_tokens[s], d_counts[s], d_start[s])
     torch.cuda.synchronize()
     snap = E.DynSamBatch(R, dyn.max_tokens, dev)
     snap.copy_from(dyn)
@@ -786,10 +802,13 @@ def bench_c2_sam_only(a, dev, workload):
     with torch.cuda.graph(g):
         for s in range(W, W + S):
             eng.step(d_tokens[s], d_counts[s], d_start[s])
-    g.replay()
+    g.replay()                               # dry replay, then the arenas as the prefill left them and the W warm-up steps
     dyn.copy_from(snap)
+    for s in range(W):
+        eng.step(d_tokens[s], d_counts[s], d_start[s])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _gate()
     e0.record()
     g.replay()
     e1.record()
@@ -817,15 +836,18 @@ def bench_c2_concurrent(a, dev, workload, n_streams=4):
             dyn = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
             eng = E.DraftEngine(dyn, None, K.FLAVOUR_SAMD, n_predicts=N_PREDICTS, len_bias=LEN_BIAS, len_threshold=LEN_THRESHOLD)
             eng.step(d_prompt, None, None)
-            for s in range(W):
-                eng.step(d_tokens[s], d_counts[s], d_start[s])
         engines.append(eng)
     torch.cuda.synchronize()
     snaps = []
-    for eng in engines:
+    for eng in engines:                      # the arenas as the prefill left them
         snap = E.DynSamBatch(R, N + 8 * (S + W) + 16, dev)
         snap.copy_from(eng.dyn)
         snaps.append(snap)
+    for eng, cs in zip(engines, cuda_streams):
+        with torch.cuda.stream(cs):
+            for s in range(W):               # warm-up steps right before the timed ones
+                eng.step(d_tokens[s], d_counts[s], d_start[s])
+    torch.cuda.synchronize()
     for eng, cs in zip(engines, cuda_streams):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=cs):
@@ -835,6 +857,7 @@ def bench_c2_concurrent(a, dev, workload, n_streams=4):
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True)
     ends = [torch.cuda.Event(enable_timing=True) for _ in cuda_streams]
+    _gate()
     e0.record()
     for g, cs, ev in zip(graphs, cuda_streams, ends):
         cs.wait_event(e0)
@@ -854,9 +877,13 @@ def bench_c2_concurrent(a, dev, workload, n_streams=4):
     h_in[:, R:2 * R] = torch.as_tensor(start)
     h_in[:, 2 * R:] = torch.as_tensor(tokens).reshape(W + S, R * 8)
     bufs = [eng.host_buffers(8) for eng in engines]
-    for (inp, res), eng, cs in zip(bufs, engines, cuda_streams):          # capture the host graphs (zero counts: no appends)
-        with torch.cuda.stream(cs):
-            eng.step_host(inp, res)
+    for s in range(W):                       # the W warm-up steps through the host path (the first call captures its graph)
+        for (inp, res), eng, cs in zip(bufs, engines, cuda_streams):
+            inp.copy_(h_in[s])
+            with torch.cuda.stream(cs):
+                eng.step_host(inp, res, sync=False)
+        for cs in cuda_streams:
+            cs.synchronize()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for s in range(W, W + S):
@@ -905,6 +932,7 @@ def bench_c1(a, dev, prompt=4096, steps=256):
     torch.cuda.synchronize()
     dyn.copy_from(snap)
     torch.cuda.synchronize()
+    _gate()
     e0.record()
     g.replay()
     e1.record()
@@ -1021,6 +1049,7 @@ def bench_static(a, dev, n_corpus=2_000_000, n_q=4096, steps=64, warm=8, check=F
         eng.static_cursor.copy_(snap_cur)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        _gate()
         e0.record()
         g.replay()
         e1.record()
@@ -1135,6 +1164,8 @@ def bench_sharded_static(a, dev, rank, world, tokens_per_shard=2_000_000, n_q=40
             torch.cuda.synchronize()
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if g is not None:
+            _gate()
         e0.record()
         if g is not None:
             g.replay()
