@@ -286,7 +286,7 @@ def run_reference(a):
     # bounded sample: a step of the reference arm is one pass over `n_sample` requests of the c2 workload
     n_sample = cores * (16 if real else 64)
     steps = min(a.steps, 256)
-    warm = min(a.warmup, 4)
+    warm = min(a.warmup, 16)
     t0 = time.time()
     qps, wall, used = cpu_arm(n_sample, a.prompt, steps, warm, 2000, cores, worker=_cpu_worker_ref if real else None)
     if real:
