@@ -603,30 +603,66 @@ __global__ void __launch_bounds__(32) static_tree_kernel(StaticDev st, int n_req
     const int n = min(min(max_predicts, TREE_MAX), 1 + (int)((double)m * alpha));
     for (int i = lane; i < TREE_MAX; i += 32) s_cnt[i] = 0;
     __syncwarp();
-    if (lane == 0) {
-        int size = 0, nt = 0;
-        heap[size++] = HeapItem{-1.0, start_tok[r], index[r], (short)-1, (short)0};
-        while (nt != n && size != 0) {
-            HeapItem it = heap_pop(heap, size);
-            if (s_cnt[it.depth] + 1 > K) continue;
-            s_cnt[it.depth] += 1;
-            const int me = nt++;
-            s_tok[me] = it.tok;
-            s_par[me] = it.parent;
-            if (nt == n) break;
-            const double total = (double)__ldg(st.occ + it.state);
-            const int2 *tk = st.topk + (size_t)it.state * 8;
+    // Lane 0 owns the heap (the pops and pushes happen in the reference's order, heapq sift for sift); the memory side of
+    // an expansion is the warp's: the popped state's top-K row and its K children's occurrence counts are 1 + K
+    // dependent-free loads issued side by side (two round trips per node instead of K + 2 - the drafter is bound by the
+    // latency of these scattered reads into a multi-gigabyte automaton).
+    {
+        int size = 0, nt = 0;                                   // lane 0's
+        if (lane == 0) heap[size++] = HeapItem{-1.0, start_tok[r], index[r], (short)-1, (short)0};
+        while (true) {
+            int go = 0, state = 0, me = 0, depth = 0;            // go: 0 = done, 1 = expand the popped node, 2 = popped node dropped
+            double prob = 0.0;
+            if (lane == 0 && nt != n && size != 0) {
+                const HeapItem it = heap_pop(heap, size);
+                if (s_cnt[it.depth] + 1 > K) {
+                    go = 2;
+                } else {
+                    s_cnt[it.depth] += 1;
+                    me = nt++;
+                    s_tok[me] = it.tok;
+                    s_par[me] = it.parent;
+                    if (nt != n) {
+                        go = 1;
+                        state = it.state;
+                        prob = it.prob;
+                        depth = it.depth;
+                    }
+                }
+            }
+            go = __shfl_sync(SAMD_FULL, go, 0);
+            if (go == 0) break;
+            if (go == 2) continue;
+            state = __shfl_sync(SAMD_FULL, state, 0);
+            const double total = (double)__ldg(st.occ + state);
+            int2 e = make_int2(-1, -1);
+            int c = 0;
+            if (lane < K && lane < 8) {
+                e = __ldg(st.topk + (size_t)state * 8 + lane);
+                if (e.x >= 0) {
+                    c = __ldg(st.occ + e.y);
+                    // a child that is popped later starts with its own top-K row: requested now (64 bytes, into L2)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(st.topk + (size_t)e.y * 8));
+                }
+            }
+            // every child's probability is computed by its own lane (an fp64 division is a long dependent sequence; eight of
+            // them one after the other were most of an expansion): same operations, same order - division first, then
+            // the multiplication - as the reference's `prob * (cnt / total)`
+            prob = __shfl_sync(SAMD_FULL, prob, 0);
+            const double mine = __dmul_rn(prob, __ddiv_rn((double)c, total));
             for (int j = 0; j < K && j < 8; ++j) {
-                const int2 e = __ldg(tk + j);
-                if (e.x < 0) break;
-                const double ratio = __ddiv_rn((double)__ldg(st.occ + e.y), total);   // division first,
-                HeapItem ch{__dmul_rn(it.prob, ratio), e.x, e.y, (short)me, (short)(it.depth + 1)};   // then multiply
-                heap[size] = ch;
-                heap_sift_down(heap, 0, size);
-                size++;
+                const int ex = __shfl_sync(SAMD_FULL, e.x, j), ey = __shfl_sync(SAMD_FULL, e.y, j);
+                const double pj = __shfl_sync(SAMD_FULL, mine, j);
+                if (ex < 0) break;
+                if (lane == 0) {
+                    HeapItem ch{pj, ex, ey, (short)me, (short)(depth + 1)};
+                    heap[size] = ch;
+                    heap_sift_down(heap, 0, size);
+                    size++;
+                }
             }
         }
-        s_n = nt;
+        if (lane == 0) s_n = nt;
     }
     __syncwarp();
     const int nt = s_n;
