@@ -103,11 +103,11 @@ def make_workload(n_requests, prompt, n_steps, seed0, procs=None):
 
 
 def _gate():
-    """A short spin kernel (about 50 us) in front of a device-timed region: the stream stays busy while the host enqueues the
+    """A short spin kernel (about 200 us) in front of a device-timed region: the stream stays busy while the host enqueues the
     start event and the graph launch, so the start event's timestamp is taken when the work is ready to run - device
     time, not the host's cudaGraphLaunch latency (which a 20-step run would otherwise carry as 1.2 us per step)."""
     import torch
-    torch.cuda._sleep(int(os.environ.get("SAMD_BENCH_GATE_CYCLES", "100000")))
+    torch.cuda._sleep(int(os.environ.get("SAMD_BENCH_GATE_CYCLES", "400000")))
 
 
 # --------------------------------------------------------------------------------------
