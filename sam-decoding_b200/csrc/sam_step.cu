@@ -832,8 +832,11 @@ __device__ __forceinline__ void sc_redirect_scout(const int32_t *recs, const uin
     }
 }
 
-template <bool kProf>
+// kStatic = false: the launch has no static automaton (the c2 / c1 shape) - its cursor, its scout and their registers are
+// compiled out.
+template <bool kProf, bool kStatic>
 __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
+    const bool has_static = kStatic && P.has_static;
     __shared__ int s_mailbox[4 * SCOUT_MAX_TOKENS + 2];
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31;
@@ -873,12 +876,12 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
             return;
         }
         const int peek = P.start_tok ? P.start_tok[r] : -1;
-        if (threadIdx.x < 64 && !(P.has_static && blockDim.x == 64)) {
+        if (threadIdx.x < 64 && !(has_static && blockDim.x == 64)) {
             sc_scout_walk<false>(recs, slots, P.dyn.bmask, text, meta[META_CUR], tk, k, peek, P.n_predicts, (long long)meta[META_N],
-                                 (long long)P.dyn.s_cap, (blockDim.x > 64 && !P.has_static) ? s_mailbox : nullptr, P.prewalk);
+                                 (long long)P.dyn.s_cap, (blockDim.x > 64 && !has_static) ? s_mailbox : nullptr, P.prewalk);
             __threadfence_block();
             atomicExch(&s_mailbox[4 * SCOUT_MAX_TOKENS + 1], 1);         // whatever path the scout left by: no more hand-offs
-        } else if (P.has_static) {
+        } else if (has_static) {
             sc_scout_walk<true>(P.st.recs, P.st.slots, P.st.bmask, P.st.text, P.static_cursor[2 * r], tk, k, peek, P.n_predicts,
                                 (long long)P.st.n_tokens, (long long)P.st.n_states, nullptr, P.prewalk);
         } else {
@@ -896,7 +899,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
         if constexpr (kProf)
             for (int i = 0; i < SC_PF_N; ++i) b.pf[i] = 0;
         // the arena's base pointers stay in registers (otherwise every address is rebuilt from the constant bank)
-        asm volatile("" : "+l"(recs), "+l"(slots), "+l"(text));
+        asm volatile("" : "+l"(recs), "+l"(slots));
         b.d.recs = recs;
         b.d.slots = slots;
         b.d.text = text;
@@ -924,7 +927,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
                 k = P.counts ? samd_clamp_count(P.counts[r], P.token_stride) : P.token_stride;
             }
             if (P.start_tok) start_tok = P.start_tok[r];
-            if (P.has_static) {
+            if (has_static) {
                 s_idx = P.static_cursor[2 * r];
                 s_len = P.static_cursor[2 * r + 1];
             }
@@ -944,7 +947,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
                     flags |= 2;
                     break;
                 }
-                if (P.has_static) sc_prefetch_rec(P.st.recs, s_idx);
+                if (has_static) sc_prefetch_rec(P.st.recs, s_idx);
                 if (b.g.n >= b.d.max_tokens) {
                     // arena full: the token cannot be appended (the flag tells the caller to grow); the cursors still
                     // follow the text so that the lookups keep returning what the automaton knows
@@ -953,7 +956,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
                 } else {
                     b.extend_one(tok);                       // add_tokens: match first, then append (dyn_sam.py:84-88)
                 }
-                if (P.has_static) sc_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, s_idx, s_len, tok, s_hops);
+                if (has_static) sc_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, s_idx, s_len, tok, s_hops);
             }
             *reinterpret_cast<int4 *>(meta) = make_int4(b.g.n_states, b.g.last, b.g.n, b.g.cur);
             meta[META_CURLEN] = b.g.cur_len;
@@ -966,7 +969,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
             meta[META_LLLINK] = b.g.ll_link;
             meta[META_MAXCHAIN] = b.g.max_chain;
             if (flags) meta[META_OVERFLOW] |= flags;
-            if (P.has_static) {
+            if (has_static) {
                 P.static_cursor[2 * r] = s_idx;
                 P.static_cursor[2 * r + 1] = s_len;
             }
@@ -978,7 +981,7 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
             int d_idx = 0, d_len = 0, q_hops = 0;
             b.lookup(tok, d_idx, d_len, q_hops);
             int t_idx = 0, t_len = 0;
-            if (P.has_static) {
+            if (has_static) {
                 t_idx = s_idx;
                 t_len = s_len;
                 sc_transfer<true>(P.st.recs, P.st.slots, P.st.bmask, t_idx, t_len, tok, s_hops);
@@ -1072,12 +1075,22 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
 // Two builds of the same body: the wide one (96 registers, three warps: 7 CTAs per SM, enough for 1024 requests in one
 // wave) and a lean one (64 registers, two warps: 16 CTAs per SM) for batches so large that residency matters more than
 // the third warp - 4096 static-SAM cursors (config c3) would otherwise run in four waves.
+#ifndef SAMD_STEP_DYN_REGS
+#define SAMD_STEP_DYN_REGS 80
+#endif
 template <bool kProf>
 __global__ void __maxnreg__(96) sam_step_scalar_kernel(StepParams P) {
-    sam_step_scalar_body<kProf>(P);
+    sam_step_scalar_body<kProf, true>(P);
+}
+// The dynamic-automaton-only build at 80 registers: a warp of 96-register threads takes 3072 registers of a 16384-register
+// scheduler partition, so only five fit (20 warps = SIX three-warp CTAs per SM, 888 requests per wave - ncu's
+// launch__occupancy_limit_registers - and the 136 late CTAs of a 1024-request step start when the first short requests are
+// done: 16.7 us); at 80 registers six warps fit, eight CTAs per SM, and the whole batch is resident at once.
+__global__ void __maxnreg__(SAMD_STEP_DYN_REGS) sam_step_scalar_dyn_kernel(StepParams P) {
+    sam_step_scalar_body<false, false>(P);
 }
 __global__ void __maxnreg__(64) sam_step_scalar_lean_kernel(StepParams P) {
-    sam_step_scalar_body<false>(P);
+    sam_step_scalar_body<false, true>(P);
 }
 
 static long long *g_dbg_cycles = nullptr;
@@ -1175,10 +1188,12 @@ extern "C" int samd_step(const samd_step_args *a, void *stream) {
             SAMD_CUDA(cudaGetDevice(&dev));
             SAMD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         }
-        const bool lean = g_lean >= 0 ? g_lean != 0 : P.dyn.n_requests > 7 * n_sm;      // more requests than one wave of the wide build
+        // more requests than one wave of the wide build (eight CTAs per SM without a static automaton, six with one)
+        const bool lean = g_lean >= 0 ? g_lean != 0 : P.dyn.n_requests > (P.has_static ? 6 : 8) * n_sm;
         if (lean && threads > 64) threads = 64;
         if (P.dbg_cycles) sam_step_scalar_kernel<true><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
         else if (lean) sam_step_scalar_lean_kernel<<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
+        else if (!P.has_static) sam_step_scalar_dyn_kernel<<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
         else sam_step_scalar_kernel<false><<<P.dyn.n_requests, threads, 0, (cudaStream_t)stream>>>(P);
         samd_count_launch();
         SAMD_CUDA(cudaGetLastError());
