@@ -199,7 +199,8 @@ void samd_step_set_prewalk(int n_tokens);
  * at.  -1 = off, 0 = only the root's slots, default 6. */
 void samd_step_set_ngram(int depth);
 /* tuning hook (variant 1): 1 = always the lean build (64 registers, two warps, 16 CTAs per SM), 0 = always the wide one
- * (96 registers, three warps, 7 CTAs per SM), -1 (default) = lean when the batch exceeds one wave of the wide build. */
+ * (three warps; 80 registers and 8 CTAs per SM without a static automaton, 88 and 6 with one), -1 (default) = lean when the
+ * batch exceeds one wave of the wide build. */
 void samd_step_set_lean(int mode);
 /* profiling hook (variant 1): when non-NULL, every samd_step launch writes, per request, trace_dev[r][0] = the number of
  * state records its builder read and trace_dev[r][1..] = their state indices in order (capacity `cap` words per
