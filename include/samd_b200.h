@@ -385,6 +385,10 @@ int samd_debug_pointer_chase(const void *recs_dev, int64_t n_records, int n_warp
  * and accepted row) can reach at best.  tools/row_move_ceiling.py */
 int samd_debug_granule_copy(void *base_dev, const int64_t *src_off_dev, const int64_t *dst_off_dev, int64_t n_granules,
                             int32_t granule_bytes, int32_t n_blocks, void *stream);
+/* profiling aid: every warp of an n_blocks x threads launch records {%smid, %warpid} into out_dev[warp][2] and lingers
+ * spin_ns so that the grid is resident together - which scheduler partition (slot mod 4) the builder warps of a
+ * step-shaped launch land on.  tools/warp_slots.py */
+int samd_debug_warp_slots(int32_t *out_dev, int n_blocks, int threads, int spin_ns, void *stream);
 /* profiling aid: the floor of samd_step's dependent-load chain.  One thread per request of `h` reads the records listed
  * in trace_dev (layout of samd_step_set_trace) one after the other, every address depending on the previous load's
  * value; with_scout != 0 adds a second thread per request that runs ahead through the same list with independent

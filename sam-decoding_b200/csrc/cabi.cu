@@ -91,3 +91,33 @@ extern "C" int samd_debug_granule_copy(void *base_dev, const int64_t *src_off_de
     SAMD_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Profiling aid: where the hardware puts the warps of a launch shaped like the step kernel's.  Every warp records its
+// %smid and %warpid (the SM's warp slot; slot mod 4 = scheduler partition) and lingers for `spin_ns` so that the whole grid
+// is resident together.  tools/warp_slots.py
+// ---------------------------------------------------------------------------------------
+__global__ void warp_slots_kernel(int32_t *out, unsigned spin_ns) {
+    if ((threadIdx.x & 31) == 0) {
+        unsigned smid, warpid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+        const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        out[2 * w] = (int)smid;
+        out[2 * w + 1] = (int)warpid;
+    }
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < spin_ns);
+}
+
+extern "C" int samd_debug_warp_slots(int32_t *out_dev, int n_blocks, int threads, int spin_ns, void *stream) {
+    SAMD_REQUIRE(out_dev && n_blocks > 0 && threads > 0 && threads % 32 == 0, "samd_debug_warp_slots: bad arguments");
+    warp_slots_kernel<<<n_blocks, threads, 0, (cudaStream_t)stream>>>(out_dev, (unsigned)spin_ns);
+    samd_count_launch();
+    SAMD_CUDA(cudaGetLastError());
+    return 0;
+}

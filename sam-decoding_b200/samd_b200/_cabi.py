@@ -104,6 +104,7 @@ SYMBOLS = {
     "samd_step_set_trace": (None, [vp, C.c_int]),
     "samd_stage_copy": (C.c_int, [vp, vp, C.c_int64, vp]),
     "samd_debug_granule_copy": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, vp]),
+    "samd_debug_warp_slots": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
     "samd_debug_replay_trace": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
     "samd_static_tree_draft": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_int32, C.c_double, C.c_int32, C.c_int32,
                                          vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp]),
