@@ -149,3 +149,28 @@ def test_negative_token_and_full_arena_are_flagged():
     eng.step(_dev(long), None, None)
     m = dyn.meta()
     assert m[1, 6] & 1 and m[1, 2] == 16 and dyn.stats()["overflowed"] >= 1
+
+
+def test_lean_build_state_for_state():
+    """The lean build of the step kernel (two warps, fewer registers: what batches of more than one wave run) forced on a
+    small batch: ragged counts (0..8 per request and step), state for state against the oracle."""
+    E, K = _mods()
+    K.lib().samd_step_set_lean(1)
+    try:
+        rng = np.random.default_rng(77)
+        cases = []
+        for i in range(70):
+            n = int(rng.integers(40, 400))
+            s = rng.integers(3, 3 + int(rng.integers(2, 7)), size=n).tolist()
+            sizes, left = [], n
+            while left > 0:
+                c = min(left, int(rng.integers(0, 9)))
+                sizes.append(c)
+                left -= c
+            cases.append((s, sizes))
+        run_batch(cases, 1, lambda s: [3, 4, 5], check_every=6)
+        streams = A.streams()
+        cases = [(streams[name], A.chunkings(len(streams[name]), 5)["steps1-8"]) for name in sorted(streams)]
+        run_batch(cases, 1, lambda s: sorted(set(s))[:3] + [9999], check_every=3)
+    finally:
+        K.lib().samd_step_set_lean(-1)
