@@ -1072,9 +1072,10 @@ __device__ __forceinline__ void sam_step_scalar_body(const StepParams &P) {
     }
 }
 
-// Two builds of the same body: the wide one (96 registers, three warps: 7 CTAs per SM, enough for 1024 requests in one
-// wave) and a lean one (64 registers, two warps: 16 CTAs per SM) for batches so large that residency matters more than
-// the third warp - 4096 static-SAM cursors (config c3) would otherwise run in four waves.
+// Three builds of the same body: the wide one with a static automaton (three warps, capped at 96 registers: six CTAs per
+// SM), the dynamic-only one below (80 registers: eight CTAs per SM), and a lean one (64 registers, two warps: 16 CTAs per
+// SM) for batches so large that residency matters more than the third warp - 4096 static-SAM cursors (config c3) would
+// otherwise run in four waves.
 #ifndef SAMD_STEP_DYN_REGS
 #define SAMD_STEP_DYN_REGS 80
 #endif
